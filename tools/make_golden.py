@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE ITSELF (oracle/_ref, built from
+/root/reference by `make -C oracle ref`) on small synthetic cases.
+
+Only runs in the build container (needs oracle/_ref); the committed .npz files are what
+travels.  Inputs are regenerated deterministically from tests/refcase.py, so a fixture
+holds only reference OUTPUTS:
+  up_<m>, down_<m>   per-shot images (RVSP_RTM_up_/down_<m>.dat)         kernel.cu:951-990
+  final              stacked/normalised window (RVSP_Migration_Real_new2.dat)  :1061-1084
+  stable             whitening constants printed per shot                       :971-972
+  gather_<m>         forward field sampled at the data positions per step (shim tap after
+                     Hybrid3, kernel.cu:819; the reference writes no gathers itself)
+  snap_last1_<m>, snap_last0_<m>, rel1_<m>, rel2_<m>
+                     the four device->host copies per shot (:822-823, :932-933)
+  M, Index, c        operator table from the reference's funMandC / order
+                     (LSMOrCon_rec_2D.cpp:22, :526), via oracle/_ref/libref_host.so
+Usage: python tools/make_golden.py [case ...]
+"""
+import re
+import shutil
+import sys
+import tempfile
+from dataclasses import asdict
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tests"))
+import oraclelib as O  # noqa: E402
+from refcase import (Case, data_tiny, read_final_image, read_shot_images, run_reference,  # noqa: E402
+                     velocity_tiny, write_inputs)
+from golden_cases import GOLDEN_CASES  # noqa: E402
+
+
+def build(case: Case, outpath: Path):
+    wd = Path(tempfile.mkdtemp(prefix="rtm_golden_", dir=str(ROOT / "gpurun_out")))
+    try:
+        vel = velocity_tiny(case)
+        data = {d: data_tiny(case, d) for d in case.depths}
+        out = write_inputs(case, wd, vel, data)
+        stdout = run_reference(wd, "ref_cpu", env={"RTM_SHIM_DUMP_D2H": str(wd / "d2h.bin"),
+                                                   "RTM_SHIM_GATHER": str(wd / "gather_")})
+        ups, downs = read_shot_images(case, out)
+        res = {"final": read_final_image(case, out)}
+        stables = [float(x) for x in re.findall(r"^(\d+\.\d{16})\s*$", stdout, re.M)]
+        assert len(stables) == case.nrec, stdout[-500:]
+        res["stable"] = np.array(stables, np.float64)
+        d2h = np.fromfile(wd / "d2h.bin", np.float32).reshape(case.nrec, 4, case.NZ, case.NX)
+        for m in range(case.nrec):
+            res[f"up_{m}"] = ups[m]
+            res[f"down_{m}"] = downs[m]
+            res[f"gather_{m}"] = np.fromfile(wd / f"gather_{m+1}.bin", np.float32).reshape(case.n, case.NT)
+        # snapshots / raw accumulators: shot 0 only (size); interior of the accumulators only
+        N2 = case.N2
+        res["snap_last1_0"] = d2h[0, 0]
+        res["snap_last0_0"] = d2h[0, 1]
+        res["rel1_0"] = d2h[0, 2][N2:-N2, N2:-N2].copy()
+        res["rel2_0"] = d2h[0, 3][N2:-N2, N2:-N2].copy()
+        # operator table from the reference's own host code
+        v, _ = O.pad_velocity(vel, case.N2, case.ifv, case.tao, case.h)
+        vmin, vmax, nvel, need = O.velocity_bins(v, case.dv)
+        m = re.search(r"vmin=([\d.]+)\s+vmax=([\d.]+)\s+nvel=(\d+)", stdout)
+        assert (float(m.group(1)), float(m.group(2)), int(m.group(3))) == (vmin, vmax, nvel)
+        if case.iLSTE == 0:
+            NC, M, Index, c = O.ref_funMandC(case.nthita, case.nfdmax, case.nfdmin, nvel, case.tao,
+                                             case.h, case.df, case.eps, case.fmax, vmin, vmax,
+                                             case.dv, need, np.float32(case.hz) / np.float32(case.h))
+            res["M"], res["Index"], res["c"] = M, Index, c
+        else:
+            c = np.zeros(case.nfdmax + 1, np.float32)
+            O.refhost().ref_order(2 * case.nfdmax, c.ctypes.data_as(O.fp))
+            res["c"] = c
+        res["vrange"] = np.array([vmin, vmax, nvel], np.float64)
+        np.savez_compressed(outpath, **res)
+        print(f"{case.name}: wrote {outpath} ({outpath.stat().st_size/1024:.0f} KiB)")
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    want = sys.argv[1:] or list(GOLDEN_CASES)
+    (ROOT / "gpurun_out").mkdir(exist_ok=True)
+    for name in want:
+        build(GOLDEN_CASES[name], ROOT / "tests" / "golden" / f"{name}.npz")
