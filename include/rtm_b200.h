@@ -1,0 +1,161 @@
+/* rtm_b200.h -- C ABI of the B200-native 2D acoustic RTM engine.
+ *
+ * The reference (caixh90/RTM_GPU) has no library boundary: `int main()` in kernel.cu
+ * launches 17 CUDA kernels on raw device pointers.  This header is
+ * the seam that replaces those launch sites and the host code around them; every entry
+ * point names the reference lines it stands in for.  Plain C types only, no CUDA or
+ * torch types; every function returns 0 on success or a negative rtm_status, and
+ * rtm_last_error() returns the message of the calling thread's last failure.
+ *
+ * Threading: one context per GPU, each context driven by one host thread at a time
+ * (the reference's serial shot loop, kernel.cu:791, becomes one thread per GPU, each
+ * migrating batches of shots).  Host buffers are owned by the caller, device buffers by
+ * the context.
+ *
+ * Index conventions are the reference's after kernel.cu:607-612: padded grid
+ * NZ = mod_NZ + 2*N2 rows (z) by NX = mod_NX + 2*N2 columns (x), 0-based, x fastest.
+ */
+#ifndef RTM_B200_H
+#define RTM_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    RTM_OK             = 0,
+    RTM_ERR_ARG        = -1, /* bad argument / inconsistent configuration */
+    RTM_ERR_CUDA       = -2, /* CUDA runtime or driver error (message has the call) */
+    RTM_ERR_STATE      = -3, /* call order (e.g. migrate before set_model) */
+    RTM_ERR_IO         = -4,
+    RTM_ERR_NCCL       = -5,
+    RTM_ERR_NO_DEVICE  = -6  /* no CUDA device: the engine has no CPU fallback */
+} rtm_status;
+
+const char *rtm_last_error(void);
+const char *rtm_version(void);
+
+/* ------------------------------------------------------------------ engine context */
+
+typedef struct rtm_ctx rtm_ctx;
+
+typedef struct {
+    /* grid and operator (2D_Real_RVSP_RTM.txt / Parameter.txt, kernel.cu:544-604) */
+    int   mod_NZ, mod_NX;   /* model size without the absorbing ring                 */
+    int   N2;               /* hybrid ABC width                                      */
+    int   nfdmax;           /* longest operator (strip width); nfdmax <= N2          */
+    int   NT;               /* time slots per shot, kernel.cu:613                    */
+    int   iLSTE;            /* 0 adaptive least-squares operator, 1 fixed Taylor     */
+    int   iCompen;          /* 1 Rel_Compen imaging, 0 Rel_NonCompen                 */
+    float h, hz, tao, f0;   /* dx, dz, dt, Ricker peak frequency                     */
+    float whitecoe;         /* illumination whitening, kernel.cu:971                 */
+    /* data (surface) positions, padded 0-based (kernel.cu:607-610) */
+    int   s_l, s_z, n, ds;
+    /* engine */
+    int   max_batch;        /* shots advanced together per kernel launch (>=1)       */
+    int   flags;            /* RTM_FLAG_*                                            */
+} rtm_params;
+
+#define RTM_FLAG_NONE 0
+
+/* Replaces cudaSetDevice + the 22 cudaMalloc calls (kernel.cu:527, 758-779). */
+int  rtm_create(int device, const rtm_params *params, rtm_ctx **out);
+void rtm_destroy(rtm_ctx *ctx); /* kernel.cu:1241-1256 */
+
+/* Padded velocity [NZ][NX] (host), snapped vmin/vmax and bin width dv
+ * (velocity(), GPU_velocity_real.cpp:6; kernel.cu:704-721, 781). */
+int rtm_set_model(rtm_ctx *ctx, const float *v_padded, float vmin, float vmax, float dv);
+
+/* Packed operator table (funMandC / order, kernel.cu:744-753, 785-786).
+ * iLSTE==0: Index[nvel+1], c[NC] with c[Index[b]..Index[b+1]) the coefficients of bin b.
+ * iLSTE==1: Index may be NULL, c[nfdmax+1]. */
+int rtm_set_operator(rtm_ctx *ctx, const int *Index, int nvel, const float *c, int NC);
+
+/* Forward modelling of `nshots` virtual sources at (r_u[i], r_x[i])
+ * (kernel.cu:798-821: Equal, Add|Add_Con, Hybrid1-3, Deliver).
+ *   gathers  host [nshots][n][NT] or NULL: gather[j][k] = slot_k[s_z][s_l + j*ds]
+ *   snap_k   nsnap requested time slots; snaps host [nshots][nsnap][NZ][NX] or NULL */
+int rtm_forward(rtm_ctx *ctx, int nshots, const int *r_u, const int *r_x, float *gathers,
+                int nsnap, const int *snap_k, float *snaps);
+
+/* Full migration of `nshots` virtual sources (the body of the shot loop,
+ * kernel.cu:798-990): forward modelling with boundary-strip saving, reverse-time source
+ * reconstruction, receiver back-propagation with data replacement, imaging, per-shot
+ * Laplacian filter and whitening.  Shots are processed max_batch at a time.
+ *   seis   host [nshots][n][NT] observed traces at the modelling sample rate
+ *   up     host [nshots][mod_NX][mod_NZ] (RVSP_RTM_up_<m>.dat layout) or NULL
+ *   down   host [nshots][mod_NX][mod_NZ] (RVSP_RTM_down_<m>.dat layout) or NULL
+ *   stable host [nshots] whitening constants (kernel.cu:971-972) or NULL
+ * Every shot is also added, in shot order, to the context's device-resident stack. */
+int rtm_migrate(rtm_ctx *ctx, int nshots, const int *r_u, const int *r_x, const float *seis,
+                float *up, float *down, float *stable);
+
+/* Same, with the observed traces already resident on the device in the engine's
+ * time-major layout (see rtm_upload_gathers); used to time the hot path alone. */
+int rtm_upload_gathers(rtm_ctx *ctx, int nshots, const float *seis);
+int rtm_migrate_resident(rtm_ctx *ctx, int nshots, const int *r_u, const int *r_x);
+
+/* Stack (kernel.cu:992-1059).  The context keeps sum_m up_m and sum_m down_m on the
+ * device.  rtm_stack_get copies them to the host ([mod_NX][mod_NZ]); rtm_stack_device
+ * exposes the device buffers (2 x mod_NX*mod_NZ floats, contiguous: up then down) so a
+ * multi-process launcher can reduce them with its own communicator; rtm_stack_reduce
+ * does the single NCCL reduce for contexts living in one process (one per GPU). */
+int rtm_stack_reset(rtm_ctx *ctx);
+int rtm_stack_get(rtm_ctx *ctx, float *up_sum, float *down_sum, int *nshots);
+int rtm_stack_device(rtm_ctx *ctx, void **dev_ptr, size_t *nfloats, int *nshots);
+int rtm_stack_reduce(rtm_ctx **ctxs, int nctx, float *up_sum, float *down_sum, int *nshots);
+/* sum/nrec, optional up/down normalisation (kernel.cu:1042-1059); in/out [mod_NX][mod_NZ] */
+int rtm_stack_finalize(const float *up_sum, const float *down_sum, int nrec, int iNorm,
+                       size_t ncell, float *image, float *illum);
+
+/* Counters since rtm_create / last reset. */
+typedef struct {
+    double cell_updates;     /* wavefield samples advanced one step                    */
+    double device_seconds;   /* CUDA-event time of the time loops                      */
+    double forward_seconds, backward_seconds;
+    double algorithmic_bytes;/* SURVEY.md 8(d) byte model for the same work            */
+    long   kernel_launches;
+    long   shots;
+} rtm_stats;
+int rtm_get_stats(rtm_ctx *ctx, rtm_stats *out);
+int rtm_reset_stats(rtm_ctx *ctx);
+int rtm_device_count(void);
+
+/* ------------------------------------------------------------------ host-side pieces
+ * (pure CPU; the reference's main() does these before/after the device loop) */
+
+/* Ricker wavelet sample f(t1,f0), kernel.cu:1261-1266. */
+float rtm_ricker(float t1, float f0);
+/* r_u = abs(N/hz)+N2-1, kernel.cu:794-795. */
+int   rtm_source_row(float depth_m, float hz, int N2);
+/* Derived scalars, kernel.cu:613-626; any output may be NULL. */
+void  rtm_derived(float h, float hz, float tao, float tao1, float f0, int NT1, int *NT, int *NT2,
+                  float *taoh, float *tao2, float *h2, float *taoh2, float *hzx2_1);
+/* velocity(): raw [mod_NX][mod_NZ] -> padded [NZ][NX], GPU_velocity_real.cpp:6-100. */
+void  rtm_pad_velocity(const float *vraw, int mod_NZ, int mod_NX, int N2, int ifv, float *v);
+/* vmin/vmax snapping and bin usage, kernel.cu:704-738.  need: int[need_cap] or NULL.
+ * Returns nvel. */
+int   rtm_velocity_bins(const float *v, long ncell, float dv, float *vmin, float *vmax, int *need,
+                        int need_cap);
+/* order(2*M,c), LSMOrCon_rec_2D.cpp:526-551; c[M+1]. */
+void  rtm_taylor_operator(int M, float *c);
+/* funMandC, LSMOrCon_rec_2D.cpp:22-73.  M[nvel], Index[nvel+1]; returns NC and writes at
+ * most c_cap coefficients to c (call with c==NULL to size).  verbose!=0 prints the
+ * reference's search log to stdout. */
+int   rtm_ls_operator(int nthita, int nfdmax, int nfdmin, int nvel, float tao, float h, float df,
+                      float eps, float fmax, float vmin, float dv, float hzx, const int *need,
+                      int *M, int *Index, float *c, int c_cap, int verbose);
+/* CAL2DFDCOE_LSM, LSMOrCon_rec_2D.cpp:236-287; c[M+1] doubles. */
+void  rtm_ls_coefficients(double *c, double r, double bmax, int M, double hzx);
+
+/* Drop-in driver: everything main() does up to the stacked image (kernel.cu:525-1108),
+ * reading the reference's input files and writing its output files.
+ *   run_file  path of 2D_Real_RVSP_RTM.txt
+ *   ngpu      number of GPUs (one host thread each); <=0 means all visible
+ *   batch     shots per launch per GPU; <=0 picks a default from the grid size */
+int rtm_run_driver(const char *run_file, int ngpu, int batch, int verbose);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,67 @@
+// C-ABI wrappers of the host-side pieces (include/rtm_b200.h, "host-side pieces").
+#include "../../include/rtm_b200.h"
+#include "host/rtm_host.h"
+
+#include <cstring>
+#include <vector>
+
+extern "C" float rtm_ricker(float t1, float f0) { return rtm::ricker(t1, f0); }
+
+extern "C" int rtm_source_row(float depth_m, float hz, int N2) { return rtm::source_row(depth_m, hz, N2); }
+
+extern "C" void rtm_derived(float h, float hz, float tao, float tao1, float f0, int NT1, int* NT, int* NT2,
+                            float* taoh, float* tao2, float* h2, float* taoh2, float* hzx2_1)
+{
+    rtm::RunConfig c;
+    c.h = h; c.hz = hz; c.tao = tao; c.tao1 = tao1; c.f0 = f0; c.NT1 = NT1;
+    const rtm::Geometry g = rtm::derive_geometry(c);
+    if (NT) *NT = g.NT;
+    if (NT2) *NT2 = g.NT2;
+    if (taoh) *taoh = g.taoh;
+    if (tao2) *tao2 = g.tao2;
+    if (h2) *h2 = g.h2;
+    if (taoh2) *taoh2 = g.taoh2;
+    if (hzx2_1) *hzx2_1 = g.hzx2_1;
+}
+
+extern "C" void rtm_pad_velocity(const float* vraw, int mod_NZ, int mod_NX, int N2, int ifv, float* v)
+{
+    rtm::pad_velocity(vraw, mod_NZ, mod_NX, N2, ifv, v);
+}
+
+extern "C" int rtm_velocity_bins(const float* v, long ncell, float dv, float* vmin, float* vmax, int* need,
+                                 int need_cap)
+{
+    const rtm::VelocityBins b = rtm::velocity_bins(v, ncell, dv);
+    if (vmin) *vmin = b.vmin;
+    if (vmax) *vmax = b.vmax;
+    if (need)
+        for (int i = 0; i < b.nvel && i < need_cap; ++i) need[i] = b.need[i];
+    return b.nvel;
+}
+
+extern "C" void rtm_taylor_operator(int M, float* c) { rtm::taylor_operator(M, c); }
+
+extern "C" void rtm_ls_coefficients(double* c, double r, double bmax, int M, double hzx)
+{
+    rtm::ls_coefficients(c, r, bmax, M, hzx);
+}
+
+extern "C" int rtm_ls_operator(int nthita, int nfdmax, int nfdmin, int nvel, float tao, float h, float df,
+                               float eps, float fmax, float vmin, float dv, float hzx, const int* need,
+                               int* M, int* Index, float* c, int c_cap, int verbose)
+{
+    // the reference hands its float parameters to funMandC's double arguments (kernel.cu:746)
+    rtm::OperatorSearch q;
+    q.nthita = nthita; q.nfdmax = nfdmax; q.nfdmin = nfdmin;
+    q.tao = tao; q.h = h; q.df = df; q.eps = eps; q.fmax = fmax; q.hzx = hzx;
+    q.nfre = (int)(q.fmax / q.df) + 1;  // LSMOrCon_rec_2D.cpp:29
+    std::vector<int> Mv, Iv;
+    std::vector<float> cv;
+    const int NC = rtm::build_ls_operator(q, nvel, vmin, dv, need, Mv, Iv, cv, verbose ? stdout : nullptr);
+    if (M) std::memcpy(M, Mv.data(), sizeof(int) * nvel);
+    if (Index) std::memcpy(Index, Iv.data(), sizeof(int) * (nvel + 1));
+    if (c)
+        for (int i = 0; i < NC && i < c_cap; ++i) c[i] = cv[i];
+    return NC;
+}

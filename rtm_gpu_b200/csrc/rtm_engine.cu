@@ -1,0 +1,717 @@
+// rtm_engine.cu -- context, memory layout, time loops and the C ABI (include/rtm_b200.h).
+//
+// HBM layout (per context = per GPU), S = max_batch shots advanced together:
+//   field buffers  5 x [S][NZ][pitch] f32   pitch = multiple of 32 floats, the interior's first
+//                                           column sits on a 128-byte boundary (padL)
+//                  forward pass: 3 rotate (slots k-2,k-1,k).  backward pass: the two buffers that
+//                  hold slots NT-1/NT-2 become the reconstructed source field (updated in place),
+//                  the other three rotate as the receiver field.
+//   accumulators   4 x [S][NZ][pitch]       sumS, sumR, rel1, rel2 (only the interior is used)
+//   velocity       [NZ][pitch]              shared by all shots
+//   strips         up/dw [S][NT][nfdmax][mod_NX], lf/rt [S][NT][mod_NZ][nfdmax]   (64-bit sizes)
+//   traces         [S][NT][n] time-major (observed data or recorded gather)
+//   images         up/down [S][mod_NX][mod_NZ]; stack 2 x [mod_NX][mod_NZ]
+// There is no CPU fallback: every entry point fails with RTM_ERR_NO_DEVICE/RTM_ERR_CUDA when
+// no B200-class device is usable.
+#include "../../include/rtm_b200.h"
+#include "host/rtm_host.h"
+#include "rtm_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace rtmk;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+int rtm_fail(int code, const char* fmt, ...);
+extern "C" const char* rtm_last_error(void) { return g_err.c_str(); }
+extern "C" const char* rtm_version(void) { return "rtm_b200 0.1 (sm_100a)"; }
+
+int rtm_fail(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return rtm_fail(RTM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                            __FILE__, __LINE__);                                              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ aux kernels
+namespace {
+
+__global__ void init_source_kernel(float* F1, Geo G, const int2* src, float val)
+{
+    const int s = blockIdx.x;
+    F1[(long long)s * G.shot_stride + G.padL + (size_t)src[s].x * G.pitch + src[s].y] = val;  // :803
+}
+
+// Equal (kernel.cu:18-45): strips of an existing field as time slot k; also samples the
+// gather for that slot.  One thread per strip cell; grid.y = shot.
+__global__ void strips_from_field_kernel(const float* F, Geo G, Strips st, int k, float* gather)
+{
+    const int shot = blockIdx.y;
+    const float* P = F + (long long)shot * G.shot_stride + G.padL;
+    const int nf = G.nfdmax, N2 = G.N2;
+    const size_t nx = (size_t)nf * G.mod_NX, nz = (size_t)nf * G.mod_NZ;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (st.up && i < nx) {
+        const int j = i / G.mod_NX, x = i % G.mod_NX;
+        const size_t o = ((size_t)shot * G.NT + k) * nx + i;
+        st.up[o] = P[(size_t)(N2 - nf + j) * G.pitch + N2 + x];
+        st.dw[o] = P[(size_t)(G.NZ - N2 + j) * G.pitch + N2 + x];
+    }
+    if (st.up && i < nz) {
+        const int z = i / nf, j = i % nf;
+        const size_t o = ((size_t)shot * G.NT + k) * nz + i;
+        st.lf[o] = P[(size_t)(N2 + z) * G.pitch + N2 - nf + j];
+        st.rt[o] = P[(size_t)(N2 + z) * G.pitch + G.NX - N2 + j];
+    }
+    if (gather && i < (size_t)G.n)
+        gather[((size_t)shot * G.NT + k) * G.n + i] = P[(size_t)G.s_z * G.pitch + G.s_l + i * G.ds];
+}
+
+// Accumulator start values (kernel.cu:859-876; host arithmetic there: no fused ops).
+// BW0 = slot NT-1, BW1 = slot NT-2; FW0/FW1 are the forward INITIAL conditions.
+__global__ void acc_init_kernel(Geo G, const float* BW0f, const float* BW1f, const int2* src,
+                                float fw1src, float* sumS, float* sumR, float* rel1, float* rel2)
+{
+    const int shot = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    if (x >= G.NX) return;
+    const size_t o = (long long)shot * G.shot_stride + G.padL + (size_t)z * G.pitch + x;
+    const float FW0 = 0.0f, FW1 = (z == src[shot].x && x == src[shot].y) ? fw1src : 0.0f;
+    const float BW0 = BW0f[o], BW1 = BW1f[o];
+    if (G.iCompen == 1) {
+        const float s = __fadd_rn(BW0, BW1), r = __fadd_rn(FW0, FW1);
+        sumS[o] = s;
+        sumR[o] = r;
+        rel1[o] = __fadd_rn(__fmul_rn(r, s), __fmul_rn(FW0, BW0));
+    } else {
+        sumS[o] = 0.0f;
+        sumR[o] = 0.0f;
+        rel1[o] = __fadd_rn(__fmul_rn(FW1, BW1), __fmul_rn(FW0, BW0));
+    }
+    rel2[o] = __fadd_rn(__fmul_rn(BW1, BW1), __fmul_rn(BW0, BW0));
+}
+
+// Per-shot image filter (kernel.cu:935-949): up = -Lap5(rel1) * v^2 / vmax^2, Laplacian
+// mirrored about the interior edge, evaluated in double as the reference's expression is;
+// output x-outer/z-inner.  Also the max |rel2| of the interior (:963-970).
+__global__ void image_up_kernel(Geo G, const float* rel1, const float* rel2, float vmax2,
+                                float* up, int* maxbits)
+{
+    const int shot = blockIdx.z;
+    const int zi = blockIdx.x * blockDim.x + threadIdx.x, xi = blockIdx.y;  // interior coords
+    if (zi >= G.mod_NZ) return;
+    const int N2 = G.N2, i = zi + N2, j = xi + N2;
+    const float* M1 = rel1 + (long long)shot * G.shot_stride + G.padL;
+    int i1 = i - 1, i2 = i + 1, j1 = j - 1, j2 = j + 1;
+    if (i1 < N2) i1 = 2 * N2 - i1;
+    if (j1 < N2) j1 = 2 * N2 - j1;
+    if (i2 >= G.NZ - N2) i2 = 2 * (G.NZ - N2 - 1) - i2;
+    if (j2 >= G.NX - N2) j2 = 2 * (G.NX - N2 - 1) - j2;
+    float lap = __fadd_rn(M1[(size_t)i * G.pitch + j2], M1[(size_t)i * G.pitch + j1]);
+    lap       = __fadd_rn(lap, M1[(size_t)i2 * G.pitch + j]);
+    lap       = __fadd_rn(lap, M1[(size_t)i1 * G.pitch + j]);
+    lap       = __fsub_rn(lap, __fmul_rn(4.0f, M1[(size_t)i * G.pitch + j]));
+    const double vv = (double)G.v[G.padL + (size_t)i * G.pitch + j];
+    const double d  = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(-1.0, (double)lap), vv), vv), (double)vmax2);
+    up[((size_t)shot * G.mod_NX + xi) * G.mod_NZ + zi] = __double2float_rn(d);
+    const float m = fabsf(rel2[(long long)shot * G.shot_stride + G.padL + (size_t)i * G.pitch + j]);
+    atomicMax(maxbits + shot, __float_as_int(m));  // non-negative floats order like ints
+}
+
+__global__ void image_down_kernel(Geo G, const float* rel2, const int* maxbits, float whitecoe,
+                                  float* down, float* stable_out)
+{
+    const int shot = blockIdx.z;
+    const int zi = blockIdx.x * blockDim.x + threadIdx.x, xi = blockIdx.y;
+    if (zi >= G.mod_NZ) return;
+    const float stable = __fmul_rn(__int_as_float(maxbits[shot]), whitecoe);  // :971
+    if (zi == 0 && xi == 0) stable_out[shot] = stable;
+    const float r = rel2[(long long)shot * G.shot_stride + G.padL + (size_t)(zi + G.N2) * G.pitch + xi + G.N2];
+    down[((size_t)shot * G.mod_NX + xi) * G.mod_NZ + zi] = __fadd_rn(r, stable);
+}
+
+// Stack (kernel.cu:1026-1039): float accumulation in shot order.
+__global__ void stack_add_kernel(size_t ncell, int nshots, const float* up, const float* down,
+                                 float* stack /* up then down */)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncell) return;
+    float a = stack[i], b = stack[ncell + i];
+    for (int s = 0; s < nshots; ++s) {
+        a = __fadd_rn(a, up[(size_t)s * ncell + i]);
+        b = __fadd_rn(b, down[(size_t)s * ncell + i]);
+    }
+    stack[i]         = a;
+    stack[ncell + i] = b;
+}
+
+// [S][n][NT] (trace-major, the reference's file layout :831-837) <-> [S][NT][n] (time-major)
+__global__ void transpose_traces_kernel(const float* in, float* out, int rows, int cols)
+{
+    __shared__ float t[32][33];
+    const size_t base = (size_t)blockIdx.z * rows * cols;
+    int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 32 + threadIdx.y;
+    for (int i = 0; i < 32; i += 8)
+        if (c < cols && r + i < rows) t[threadIdx.y + i][threadIdx.x] = in[base + (size_t)(r + i) * cols + c];
+    __syncthreads();
+    c = blockIdx.y * 32 + threadIdx.x;
+    r = blockIdx.x * 32 + threadIdx.y;
+    for (int i = 0; i < 32; i += 8)
+        if (c < rows && r + i < cols) out[base + (size_t)(r + i) * rows + c] = t[threadIdx.x][threadIdx.y + i];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ context
+struct rtm_ctx {
+    int        device = 0;
+    rtm_params p{};
+    Geo        G{};
+    int        S = 1, RP = 4;
+    bool       have_model = false, have_op = false;
+    float      vmax = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+    // device memory
+    float* field[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* acc[4]   = {nullptr, nullptr, nullptr, nullptr};
+    CUtensorMap tmap[5];
+    float* d_v = nullptr;
+    float* d_c = nullptr;
+    int*   d_Index = nullptr;
+    Strips st{nullptr, nullptr, nullptr, nullptr};
+    float* d_traces = nullptr;   // [S][NT][n]
+    float* d_stage  = nullptr;   // [S][n][NT] transpose staging
+    int2*  d_src = nullptr;
+    float *d_up = nullptr, *d_down = nullptr, *d_stack = nullptr, *d_stable = nullptr;
+    int*   d_maxbits = nullptr;
+    int    stack_shots = 0;
+    size_t field_floats = 0;
+    size_t smem_fwd = 0, smem_bwd = 0;
+    rtm_stats stats{};
+};
+
+static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess)
+            return rtm_fail(RTM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        fn = (EncodeFn)p;
+    }
+    const Geo& G = c->G;
+    cuuint64_t dims[3]    = {(cuuint64_t)G.pitch, (cuuint64_t)G.NZ, (cuuint64_t)c->S};
+    cuuint64_t strides[2] = {(cuuint64_t)G.pitch * 4, (cuuint64_t)G.shot_stride * 4};
+    cuuint32_t box[3]     = {(cuuint32_t)(kTX + 2 * c->RP), (cuuint32_t)(kTZ + 2 * c->RP), 1};
+    cuuint32_t estr[3]    = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return rtm_fail(RTM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return RTM_OK;
+}
+
+extern "C" int rtm_ctx_device(rtm_ctx* c) { return c ? c->device : -1; }
+
+extern "C" int rtm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" void rtm_destroy(rtm_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto& f : c->field) cudaFree(f);
+    for (auto& f : c->acc) cudaFree(f);
+    cudaFree(c->d_v); cudaFree(c->d_c); cudaFree(c->d_Index);
+    cudaFree(c->st.up); cudaFree(c->st.dw); cudaFree(c->st.lf); cudaFree(c->st.rt);
+    cudaFree(c->d_traces); cudaFree(c->d_stage); cudaFree(c->d_src);
+    cudaFree(c->d_up); cudaFree(c->d_down); cudaFree(c->d_stack); cudaFree(c->d_stable);
+    cudaFree(c->d_maxbits);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
+{
+    if (!p || !out) return rtm_fail(RTM_ERR_ARG, "rtm_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return rtm_fail(RTM_ERR_NO_DEVICE, "rtm_create: no CUDA device (this engine has no CPU path)");
+    if (device < 0 || device >= ndev) return rtm_fail(RTM_ERR_ARG, "rtm_create: device %d of %d", device, ndev);
+    if (p->mod_NZ < 4 || p->mod_NX < 4 || p->N2 < 1 || p->N2 > 64 || p->NT < 3)
+        return rtm_fail(RTM_ERR_ARG, "rtm_create: bad grid (mod_NZ=%d mod_NX=%d N2=%d NT=%d)", p->mod_NZ, p->mod_NX, p->N2, p->NT);
+    if (p->nfdmax < 1 || p->nfdmax > kMaxR || p->nfdmax > p->N2)
+        return rtm_fail(RTM_ERR_ARG, "rtm_create: need 1 <= nfdmax (%d) <= min(N2=%d, %d): the boundary strips lie inside the ring (kernel.cu:23-43)", p->nfdmax, p->N2, kMaxR);
+    if (p->n < 1 || p->ds < 1 || p->s_z < 0 || p->s_z >= p->mod_NZ + 2 * p->N2 || p->s_l < 0 ||
+        p->s_l + (p->n - 1) * p->ds >= p->mod_NX + 2 * p->N2)
+        return rtm_fail(RTM_ERR_ARG, "rtm_create: data positions outside the padded grid");
+    if (p->mod_NZ <= 2 * p->N2 + 4 || p->mod_NX <= 2 * p->N2 + 4)
+        return rtm_fail(RTM_ERR_ARG, "rtm_create: model smaller than the absorbing ring");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return rtm_fail(RTM_ERR_NO_DEVICE, "rtm_create: device %d is sm_%d%d; this engine is built for sm_100a only", device, prop.major, prop.minor);
+
+    rtm_ctx* c = new rtm_ctx;
+    c->device = device;
+    c->p      = *p;
+    c->S      = std::max(1, p->max_batch);
+    c->RP     = (p->nfdmax + 3) / 4 * 4;
+    Geo& G    = c->G;
+    G.mod_NZ = p->mod_NZ; G.mod_NX = p->mod_NX; G.N2 = p->N2;
+    G.NZ = p->mod_NZ + 2 * p->N2; G.NX = p->mod_NX + 2 * p->N2;
+    G.padL  = (32 - p->N2 % 32) % 32;
+    if (G.padL + p->N2 < c->RP) G.padL += 32;  // the TMA box may start left of the first interior column
+    G.pitch = (G.padL + G.NX + 4 + 31) / 32 * 32;
+    G.shot_stride = (long long)G.NZ * G.pitch;
+    G.nfdmax = p->nfdmax; G.NT = p->NT; G.iLSTE = p->iLSTE; G.iCompen = p->iCompen;
+    G.tao = p->tao; G.h = p->h;
+    // derived scalars exactly as kernel.cu:614-626
+    G.taoh  = p->tao / p->h;
+    G.tao2  = (float)((double)p->tao * (double)p->tao);
+    G.h2    = (float)(1 / ((double)p->h * (double)p->h));
+    G.taoh2 = G.tao2 * G.h2 / 2;
+    const float hzx = p->hz / p->h;
+    G.hzx2_1 = 1 / (hzx * hzx);
+    G.A      = 1.0 + (double)G.hzx2_1;
+    G.s_l = p->s_l; G.s_z = p->s_z; G.n = p->n; G.ds = p->ds; G.s_r = (p->n - 1) * p->ds + p->s_l;
+    G.ntx = (G.mod_NX + kTX - 1) / kTX; G.ntz = (G.mod_NZ + kTZ - 1) / kTZ;
+    G.nband = (G.NX + kRingTX - 1) / kRingTX; G.nside = (G.mod_NZ + kRingTX - 1) / kRingTX;
+    for (int i = 0; i <= p->N2; ++i) G.w[i] = (float)((1.0 * i) / (1.0 * p->N2));  // :688-691
+
+    auto fail = [&](int rc) { rtm_destroy(c); return rc; };
+#define CKC(call)                                                                              \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(rtm_fail(RTM_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                 \
+                                 cudaGetErrorString(e_), __FILE__, __LINE__));                 \
+    } while (0)
+    CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&c->ev0));
+    CKC(cudaEventCreate(&c->ev1));
+    c->field_floats = (size_t)c->S * G.shot_stride + 64;  // slack for float4 loads past the last row
+    const size_t ncell = (size_t)G.mod_NX * G.mod_NZ;
+    size_t need = (5 + 4) * c->field_floats * 4 + (size_t)G.shot_stride * 4 +
+                  2 * (size_t)c->S * G.NT * G.n * 4 + 2 * c->S * ncell * 4;
+    size_t free_b = 0, total_b = 0;
+    CKC(cudaMemGetInfo(&free_b, &total_b));
+    if (need > free_b)
+        return fail(rtm_fail(RTM_ERR_ARG, "rtm_create: batch of %d shots needs %.1f GB before strips, %.1f GB free", c->S, need / 1e9, free_b / 1e9));
+    for (auto& f : c->field) { CKC(cudaMalloc(&f, c->field_floats * 4)); CKC(cudaMemset(f, 0, c->field_floats * 4)); }
+    for (auto& f : c->acc) { CKC(cudaMalloc(&f, c->field_floats * 4)); CKC(cudaMemset(f, 0, c->field_floats * 4)); }
+    CKC(cudaMalloc(&c->d_v, ((size_t)G.shot_stride + 64) * 4));
+    CKC(cudaMemset(c->d_v, 0, ((size_t)G.shot_stride + 64) * 4));
+    CKC(cudaMalloc(&c->d_traces, (size_t)c->S * G.NT * G.n * 4));
+    CKC(cudaMalloc(&c->d_stage, (size_t)c->S * G.NT * G.n * 4));
+    CKC(cudaMalloc(&c->d_src, sizeof(int2) * c->S));
+    CKC(cudaMalloc(&c->d_up, c->S * ncell * 4));
+    CKC(cudaMalloc(&c->d_down, c->S * ncell * 4));
+    CKC(cudaMalloc(&c->d_stack, 2 * ncell * 4));
+    CKC(cudaMemset(c->d_stack, 0, 2 * ncell * 4));
+    CKC(cudaMalloc(&c->d_stable, sizeof(float) * c->S));
+    CKC(cudaMalloc(&c->d_maxbits, sizeof(int) * c->S));
+    G.v = c->d_v;
+    for (int i = 0; i < 5; ++i) {
+        int rc = encode_tmap(c, &c->tmap[i], c->field[i]);
+        if (rc) return fail(rc);
+    }
+#undef CKC
+    *out = c;
+    return RTM_OK;
+}
+
+extern "C" int rtm_set_model(rtm_ctx* c, const float* v, float vmin, float vmax, float dv)
+{
+    if (!c || !v) return rtm_fail(RTM_ERR_ARG, "rtm_set_model: null argument");
+    if (!(dv > 0)) return rtm_fail(RTM_ERR_ARG, "rtm_set_model: dv must be positive");
+    CK(cudaSetDevice(c->device));
+    Geo& G = c->G;
+    CK(cudaMemcpy2D(c->d_v + G.padL, (size_t)G.pitch * 4, v, (size_t)G.NX * 4, (size_t)G.NX * 4, G.NZ,
+                    cudaMemcpyHostToDevice));
+    G.vmin = vmin; G.dv = dv; c->vmax = vmax;
+    c->have_model = true;
+    return RTM_OK;
+}
+
+extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const float* coef, int NC)
+{
+    if (!c || !coef) return rtm_fail(RTM_ERR_ARG, "rtm_set_operator: null argument");
+    CK(cudaSetDevice(c->device));
+    Geo& G = c->G;
+    if (G.iLSTE == 0) {
+        if (!Index || nvel < 1 || NC < 1) return rtm_fail(RTM_ERR_ARG, "rtm_set_operator: adaptive operator needs Index[nvel+1] and c[NC]");
+        if (Index[nvel] != NC) return rtm_fail(RTM_ERR_ARG, "rtm_set_operator: Index[nvel]=%d != NC=%d", Index[nvel], NC);
+        for (int i = 0; i < nvel; ++i)
+            if (Index[i + 1] - Index[i] - 1 > G.nfdmax)
+                return rtm_fail(RTM_ERR_ARG, "rtm_set_operator: bin %d has length %d > nfdmax %d", i, Index[i + 1] - Index[i] - 1, G.nfdmax);
+        cudaFree(c->d_c); cudaFree(c->d_Index);
+        c->d_c = nullptr; c->d_Index = nullptr;
+        // one spare entry: the lookup reads Index[bin+1] and c[Index[bin]] for any cell
+        CK(cudaMalloc(&c->d_c, sizeof(float) * (NC + 1)));
+        CK(cudaMemset(c->d_c, 0, sizeof(float) * (NC + 1)));
+        CK(cudaMalloc(&c->d_Index, sizeof(int) * (nvel + 2)));
+        CK(cudaMemcpy(c->d_c, coef, sizeof(float) * NC, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_Index, Index, sizeof(int) * (nvel + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_Index + nvel + 1, Index + nvel, sizeof(int), cudaMemcpyHostToDevice));
+        G.c = c->d_c; G.Index = c->d_Index;
+    } else {
+        if (NC != G.nfdmax + 1) return rtm_fail(RTM_ERR_ARG, "rtm_set_operator: Taylor operator needs nfdmax+1=%d coefficients, got %d", G.nfdmax + 1, NC);
+        for (int l = 0; l <= kMaxR; ++l) G.cTE[l] = l < NC ? coef[l] : 0.0f;
+        G.cc0TE = G.A * (double)coef[0];
+    }
+    c->have_op = true;
+    return RTM_OK;
+}
+
+// ------------------------------------------------------------------------------------ launches
+template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, int ns, int cur, const FwdArgs& a)
+{
+    const Geo& G = c->G;
+    const int nring = 2 * G.nband + 2 * G.nside;
+    size_t smem = std::max((size_t)Tile<RP>::BYTES + 16, (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
+    if (smem > c->smem_fwd) {  // per device, once
+        CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->smem_fwd = smem;
+    }
+    dim3 grid(nring + G.ntx * G.ntz, ns);
+    fwd_step_kernel<RP, LS><<<grid, kThreads, smem, c->stream>>>(c->tmap[cur], G, a);
+    return RTM_OK;
+}
+template <int RP, bool LS> static int launch_bwd(rtm_ctx* c, int ns, int s1, int r1, const BwdArgs& a)
+{
+    const Geo& G = c->G;
+    const int nring = 2 * G.nband + 2 * G.nside;
+    size_t smem = std::max((size_t)2 * Tile<RP>::BYTES + 16, (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
+    if (smem > c->smem_bwd) {
+        CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->smem_bwd = smem;
+    }
+    dim3 grid(nring + G.ntx * G.ntz, ns);
+    bwd_step_kernel<RP, LS><<<grid, kThreads, smem, c->stream>>>(c->tmap[s1], c->tmap[r1], G, a);
+    return RTM_OK;
+}
+static int dispatch_fwd(rtm_ctx* c, int ns, int cur, const FwdArgs& a)
+{
+    const bool ls = c->G.iLSTE == 0;
+    switch (c->RP) {
+    case 4:  return ls ? launch_fwd<4, true>(c, ns, cur, a) : launch_fwd<4, false>(c, ns, cur, a);
+    case 8:  return ls ? launch_fwd<8, true>(c, ns, cur, a) : launch_fwd<8, false>(c, ns, cur, a);
+    case 12: return ls ? launch_fwd<12, true>(c, ns, cur, a) : launch_fwd<12, false>(c, ns, cur, a);
+    case 16: return ls ? launch_fwd<16, true>(c, ns, cur, a) : launch_fwd<16, false>(c, ns, cur, a);
+    }
+    return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", c->RP);
+}
+static int dispatch_bwd(rtm_ctx* c, int ns, int s1, int r1, const BwdArgs& a)
+{
+    const bool ls = c->G.iLSTE == 0;
+    switch (c->RP) {
+    case 4:  return ls ? launch_bwd<4, true>(c, ns, s1, r1, a) : launch_bwd<4, false>(c, ns, s1, r1, a);
+    case 8:  return ls ? launch_bwd<8, true>(c, ns, s1, r1, a) : launch_bwd<8, false>(c, ns, s1, r1, a);
+    case 12: return ls ? launch_bwd<12, true>(c, ns, s1, r1, a) : launch_bwd<12, false>(c, ns, s1, r1, a);
+    case 16: return ls ? launch_bwd<16, true>(c, ns, s1, r1, a) : launch_bwd<16, false>(c, ns, s1, r1, a);
+    }
+    return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", c->RP);
+}
+
+static int ensure_strips(rtm_ctx* c)
+{
+    if (c->st.up) return RTM_OK;
+    const Geo& G = c->G;
+    const size_t nx = (size_t)c->S * G.NT * G.nfdmax * G.mod_NX * 4;
+    const size_t nz = (size_t)c->S * G.NT * G.nfdmax * G.mod_NZ * 4;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if (2 * (nx + nz) > free_b)
+        return rtm_fail(RTM_ERR_ARG, "boundary strips for %d shots x %d steps need %.1f GB, %.1f GB free: lower max_batch", c->S, G.NT, 2 * (nx + nz) / 1e9, free_b / 1e9);
+    CK(cudaMalloc(&c->st.up, nx)); CK(cudaMalloc(&c->st.dw, nx));
+    CK(cudaMalloc(&c->st.lf, nz)); CK(cudaMalloc(&c->st.rt, nz));
+    return RTM_OK;
+}
+
+// Forward loop for `ns` shots (sources already in d_src).  On return field[*last1] holds slot
+// NT-1 and field[*last0] slot NT-2.
+static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool strips, float* gather,
+                       int nsnap, const int* snap_k, float* snaps_host, int* last1, int* last0)
+{
+    const Geo& G = c->G;
+    std::vector<int2> src(ns);
+    for (int s = 0; s < ns; ++s) {
+        if (r_u[s] < 0 || r_u[s] >= G.NZ || r_x[s] < 0 || r_x[s] >= G.NX)
+            return rtm_fail(RTM_ERR_ARG, "source %d at (%d,%d) outside the %dx%d grid", s, r_u[s], r_x[s], G.NZ, G.NX);
+        src[s] = make_int2(r_u[s], r_x[s]);
+    }
+    CK(cudaMemcpyAsync(c->d_src, src.data(), sizeof(int2) * ns, cudaMemcpyHostToDevice, c->stream));
+    for (int b = 0; b < 3; ++b) CK(cudaMemsetAsync(c->field[b], 0, c->field_floats * 4, c->stream));
+    const float fw1 = (float)(rtm::ricker(0.0f, c->p.f0) / 2.0);  // :803
+    init_source_kernel<<<ns, 1, 0, c->stream>>>(c->field[1], G, c->d_src, fw1);
+    Strips st = strips ? c->st : Strips{nullptr, nullptr, nullptr, nullptr};
+    {
+        size_t m = std::max({(size_t)G.nfdmax * G.mod_NX, (size_t)G.nfdmax * G.mod_NZ, (size_t)G.n});
+        dim3 grid((unsigned)((m + 255) / 256), ns);
+        if (strips || gather) {
+            strips_from_field_kernel<<<grid, 256, 0, c->stream>>>(c->field[0], G, st, 0, gather);
+            strips_from_field_kernel<<<grid, 256, 0, c->stream>>>(c->field[1], G, st, 1, gather);
+        }
+    }
+    auto snapshot = [&](int k, int buf) -> int {
+        for (int i = 0; i < nsnap; ++i) {
+            if (snap_k[i] != k) continue;
+            CK(cudaStreamSynchronize(c->stream));
+            for (int s = 0; s < ns; ++s)
+                CK(cudaMemcpy2D(snaps_host + ((size_t)s * nsnap + i) * G.NZ * G.NX, (size_t)G.NX * 4,
+                                c->field[buf] + (size_t)s * G.shot_stride + G.padL, (size_t)G.pitch * 4,
+                                (size_t)G.NX * 4, G.NZ, cudaMemcpyDeviceToHost));
+        }
+        return RTM_OK;
+    };
+    if (nsnap) { if (int rc = snapshot(0, 0)) return rc; if (int rc = snapshot(1, 1)) return rc; }
+    int NT2;
+    rtm_derived(c->p.h, c->p.hz, c->p.tao, c->p.tao, c->p.f0, 2, nullptr, &NT2, nullptr, nullptr, nullptr, nullptr, nullptr);
+    int i0 = 0, i1 = 1, i2 = 2;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int k = 2; k < G.NT; ++k) {
+        FwdArgs a;
+        a.P1 = c->field[i1]; a.P0 = c->field[i0]; a.P2 = c->field[i2];
+        a.src = c->d_src;
+        a.wavelet = (k < NT2) ? rtm::ricker((k - 1) * c->p.tao, c->p.f0) : 0.0f;  // :812-813
+        a.k = k; a.st = st; a.gather = gather;
+        if (int rc = dispatch_fwd(c, ns, i1, a)) return rc;
+        if (nsnap) if (int rc = snapshot(k, i2)) return rc;
+        const int t = i0; i0 = i1; i1 = i2; i2 = t;
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    const double cu = (double)(G.NT - 2) * G.NZ * G.NX * ns;
+    c->stats.cell_updates += cu;
+    c->stats.algorithmic_bytes += cu * 16.0;
+    c->stats.forward_seconds += ms * 1e-3;
+    c->stats.device_seconds += ms * 1e-3;
+    c->stats.kernel_launches += G.NT - 2;
+    *last1 = i1; *last0 = i0;
+    return RTM_OK;
+}
+
+extern "C" int rtm_forward(rtm_ctx* c, int nshots, const int* r_u, const int* r_x, float* gathers,
+                           int nsnap, const int* snap_k, float* snaps)
+{
+    if (!c || !r_u || !r_x || nshots < 1) return rtm_fail(RTM_ERR_ARG, "rtm_forward: bad argument");
+    if (!c->have_model || !c->have_op) return rtm_fail(RTM_ERR_STATE, "rtm_forward: set the model and the operator first");
+    if (nsnap && (!snap_k || !snaps)) return rtm_fail(RTM_ERR_ARG, "rtm_forward: snapshots requested without buffers");
+    CK(cudaSetDevice(c->device));
+    const Geo& G = c->G;
+    for (int first = 0; first < nshots; first += c->S) {
+        const int ns = std::min(c->S, nshots - first);
+        int l1, l0;
+        if (int rc = run_forward(c, ns, r_u + first, r_x + first, false, gathers ? c->d_traces : nullptr, nsnap,
+                                 snap_k, snaps ? snaps + (size_t)first * nsnap * G.NZ * G.NX : nullptr, &l1, &l0))
+            return rc;
+        if (gathers) {
+            dim3 grid((G.n + 31) / 32, (G.NT + 31) / 32, ns);  // [NT][n] -> [n][NT]
+            transpose_traces_kernel<<<grid, dim3(32, 8), 0, c->stream>>>(c->d_traces, c->d_stage, G.NT, G.n);
+            CK(cudaMemcpyAsync(gathers + (size_t)first * G.n * G.NT, c->d_stage, (size_t)ns * G.n * G.NT * 4,
+                               cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        c->stats.shots += ns;
+    }
+    return RTM_OK;
+}
+
+// One batch of the shot loop body (kernel.cu:798-990) with the traces already in d_traces.
+static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, float* up, float* down, float* stable)
+{
+    const Geo& G = c->G;
+    if (int rc = ensure_strips(c)) return rc;
+    int l1, l0;
+    if (int rc = run_forward(c, ns, r_u, r_x, true, nullptr, 0, nullptr, nullptr, &l1, &l0)) return rc;
+    // source field: sx = slot NT-1 ("previous", updated in place), sy = slot NT-2 ("current")
+    int sx = l1, sy = l0;
+    int rb[3], nrb = 0;
+    for (int b = 0; b < 5; ++b)
+        if (b != sx && b != sy) rb[nrb++] = b;
+    for (int i = 0; i < 3; ++i) CK(cudaMemsetAsync(c->field[rb[i]], 0, c->field_floats * 4, c->stream));
+    const float fw1 = (float)(rtm::ricker(0.0f, c->p.f0) / 2.0);
+    {
+        dim3 grid((G.NX + 127) / 128, G.NZ, ns);
+        acc_init_kernel<<<grid, 128, 0, c->stream>>>(G, c->field[sx], c->field[sy], c->d_src, fw1, c->acc[0],
+                                                      c->acc[1], c->acc[2], c->acc[3]);
+    }
+    int NT2;
+    rtm_derived(c->p.h, c->p.hz, c->p.tao, c->p.tao, c->p.f0, 2, nullptr, &NT2, nullptr, nullptr, nullptr, nullptr, nullptr);
+    int r0 = rb[0], r1 = rb[1], r2 = rb[2];
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int k = G.NT - 3; k >= 0; --k) {
+        BwdArgs a;
+        a.S1 = c->field[sy]; a.S02 = c->field[sx];
+        a.R1 = c->field[r1]; a.R0 = c->field[r0]; a.R2 = c->field[r2];
+        a.src = c->d_src;
+        a.wavelet = (k < NT2) ? rtm::ricker((k + 1) * c->p.tao, c->p.f0) : 0.0f;  // :889-890
+        a.k = k; a.st = c->st; a.seis = c->d_traces;
+        a.sumS = c->acc[0]; a.sumR = c->acc[1]; a.rel1 = c->acc[2]; a.rel2 = c->acc[3];
+        if (int rc = dispatch_bwd(c, ns, sy, r1, a)) return rc;
+        std::swap(sx, sy);
+        const int t = r0; r0 = r1; r1 = r2; r2 = t;
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    // per-shot image post-processing and stacking
+    const size_t ncell = (size_t)G.mod_NX * G.mod_NZ;
+    CK(cudaMemsetAsync(c->d_maxbits, 0, sizeof(int) * ns, c->stream));
+    {
+        dim3 grid((G.mod_NZ + 127) / 128, G.mod_NX, ns);
+        image_up_kernel<<<grid, 128, 0, c->stream>>>(G, c->acc[2], c->acc[3], c->vmax * c->vmax, c->d_up, c->d_maxbits);
+        image_down_kernel<<<grid, 128, 0, c->stream>>>(G, c->acc[3], c->d_maxbits, c->p.whitecoe, c->d_down, c->d_stable);
+        stack_add_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, c->stream>>>(ncell, ns, c->d_up, c->d_down, c->d_stack);
+    }
+    CK(cudaGetLastError());
+    if (up) CK(cudaMemcpyAsync(up, c->d_up, ns * ncell * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (down) CK(cudaMemcpyAsync(down, c->d_down, ns * ncell * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (stable) CK(cudaMemcpyAsync(stable, c->d_stable, ns * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    const double steps = (double)(G.NT - 2) * ns;
+    c->stats.cell_updates += steps * ((double)G.NZ * G.NX + (double)ncell);
+    c->stats.algorithmic_bytes += steps * (double)G.NZ * G.NX * (G.iCompen == 1 ? 60.0 : 44.0);
+    c->stats.backward_seconds += ms * 1e-3;
+    c->stats.device_seconds += ms * 1e-3;
+    c->stats.kernel_launches += G.NT - 2;
+    c->stats.shots += ns;
+    c->stack_shots += ns;
+    return RTM_OK;
+}
+
+static int upload_traces(rtm_ctx* c, int ns, const float* seis)
+{
+    const Geo& G = c->G;
+    CK(cudaMemcpyAsync(c->d_stage, seis, (size_t)ns * G.n * G.NT * 4, cudaMemcpyHostToDevice, c->stream));
+    dim3 grid((G.NT + 31) / 32, (G.n + 31) / 32, ns);  // [n][NT] -> [NT][n]
+    transpose_traces_kernel<<<grid, dim3(32, 8), 0, c->stream>>>(c->d_stage, c->d_traces, G.n, G.NT);
+    CK(cudaGetLastError());
+    return RTM_OK;
+}
+
+extern "C" int rtm_migrate(rtm_ctx* c, int nshots, const int* r_u, const int* r_x, const float* seis,
+                           float* up, float* down, float* stable)
+{
+    if (!c || !r_u || !r_x || !seis || nshots < 1) return rtm_fail(RTM_ERR_ARG, "rtm_migrate: bad argument");
+    if (!c->have_model || !c->have_op) return rtm_fail(RTM_ERR_STATE, "rtm_migrate: set the model and the operator first");
+    CK(cudaSetDevice(c->device));
+    const Geo& G = c->G;
+    const size_t ncell = (size_t)G.mod_NX * G.mod_NZ;
+    for (int first = 0; first < nshots; first += c->S) {
+        const int ns = std::min(c->S, nshots - first);
+        if (int rc = upload_traces(c, ns, seis + (size_t)first * G.n * G.NT)) return rc;
+        if (int rc = migrate_batch(c, ns, r_u + first, r_x + first, up ? up + first * ncell : nullptr,
+                                   down ? down + first * ncell : nullptr, stable ? stable + first : nullptr))
+            return rc;
+    }
+    return RTM_OK;
+}
+
+extern "C" int rtm_upload_gathers(rtm_ctx* c, int nshots, const float* seis)
+{
+    if (!c || !seis || nshots < 1 || nshots > c->S) return rtm_fail(RTM_ERR_ARG, "rtm_upload_gathers: 1 <= nshots <= max_batch");
+    CK(cudaSetDevice(c->device));
+    if (int rc = upload_traces(c, nshots, seis)) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return RTM_OK;
+}
+
+extern "C" int rtm_migrate_resident(rtm_ctx* c, int nshots, const int* r_u, const int* r_x)
+{
+    if (!c || !r_u || !r_x || nshots < 1 || nshots > c->S) return rtm_fail(RTM_ERR_ARG, "rtm_migrate_resident: 1 <= nshots <= max_batch");
+    if (!c->have_model || !c->have_op) return rtm_fail(RTM_ERR_STATE, "rtm_migrate_resident: set the model and the operator first");
+    CK(cudaSetDevice(c->device));
+    return migrate_batch(c, nshots, r_u, r_x, nullptr, nullptr, nullptr);
+}
+
+extern "C" int rtm_stack_reset(rtm_ctx* c)
+{
+    if (!c) return rtm_fail(RTM_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemset(c->d_stack, 0, 2 * (size_t)c->G.mod_NX * c->G.mod_NZ * 4));
+    c->stack_shots = 0;
+    return RTM_OK;
+}
+extern "C" int rtm_stack_get(rtm_ctx* c, float* up_sum, float* down_sum, int* nshots)
+{
+    if (!c) return rtm_fail(RTM_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    const size_t ncell = (size_t)c->G.mod_NX * c->G.mod_NZ;
+    if (up_sum) CK(cudaMemcpy(up_sum, c->d_stack, ncell * 4, cudaMemcpyDeviceToHost));
+    if (down_sum) CK(cudaMemcpy(down_sum, c->d_stack + ncell, ncell * 4, cudaMemcpyDeviceToHost));
+    if (nshots) *nshots = c->stack_shots;
+    return RTM_OK;
+}
+extern "C" int rtm_stack_device(rtm_ctx* c, void** dev_ptr, size_t* nfloats, int* nshots)
+{
+    if (!c || !dev_ptr) return rtm_fail(RTM_ERR_ARG, "null argument");
+    *dev_ptr = c->d_stack;
+    if (nfloats) *nfloats = 2 * (size_t)c->G.mod_NX * c->G.mod_NZ;
+    if (nshots) *nshots = c->stack_shots;
+    return RTM_OK;
+}
+extern "C" int rtm_stack_finalize(const float* up_sum, const float* down_sum, int nrec, int iNorm,
+                                  size_t ncell, float* image, float* illum)
+{
+    if (!up_sum || !down_sum || !image || nrec < 1) return rtm_fail(RTM_ERR_ARG, "rtm_stack_finalize: bad argument");
+    for (size_t i = 0; i < ncell; ++i) {  // kernel.cu:1042-1059
+        float a = up_sum[i] / nrec, b = down_sum[i] / nrec;
+        if (iNorm == 1) a = a / b;
+        image[i] = a;
+        if (illum) illum[i] = b;
+    }
+    return RTM_OK;
+}
+
+extern "C" int rtm_get_stats(rtm_ctx* c, rtm_stats* out)
+{
+    if (!c || !out) return rtm_fail(RTM_ERR_ARG, "null argument");
+    *out = c->stats;
+    return RTM_OK;
+}
+extern "C" int rtm_reset_stats(rtm_ctx* c)
+{
+    if (!c) return rtm_fail(RTM_ERR_ARG, "null context");
+    c->stats = rtm_stats{};
+    return RTM_OK;
+}
+
+// NCCL reduce of the per-GPU stacks for contexts living in one process: rtm_nccl.cpp

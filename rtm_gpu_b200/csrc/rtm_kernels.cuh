@@ -1,0 +1,697 @@
+// rtm_kernels.cuh -- sm_100a device code of the RTM time loop.
+//
+// One launch per time step.  A launch covers a batch of shots (blockIdx.y) and, per
+// shot, two kinds of CTA:
+//   * interior tiles (fast path): TMA-staged halo tile of the current wavefield in shared
+//     memory, each thread owns a 4 (x, one float4) by NR (z) register block, z neighbours
+//     from a register column, x neighbours from float4 shared loads, coalesced float4
+//     global loads/stores for the other streams;
+//   * ring tiles: the N2-wide hybrid absorbing ring.  They evaluate the two-way update on
+//     the ring plus a one-cell halo, apply the one-way solution and the blend, and move
+//     the boundary strips (save in the forward pass, restore in the backward pass).
+// All CTAs read only time slots k-1/k-2 and write disjoint cells of slot k, so there is no
+// ordering requirement inside a launch and buffers rotate by pointer.
+//
+// FP32 contract.  Results must equal the reference's CUDA build bit for bit, so every
+// operation that nvcc could contract or reorder is written with an explicit intrinsic, in
+// the order the reference's sm_100a SASS has (DESIGN.md "FP contract").
+// Reference kernels restated here (kernel.cu): Add/Add_Con :46-114, Hybrid1/2/3 :116-208,
+// Equal :18-45, BKEqual :222-245, BKAdd_EFF(_Con) :246-320, BKAdd(_Con) :339-418,
+// BKHybrid1/2 :421-487, Rel_Compen/Rel_NonCompen :489-517; Deliver/Deliver_EFF :210-221,
+// :323-337 disappear (pointer rotation).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtmk {
+
+constexpr int kThreads = 256;  // 8 warps per CTA
+constexpr int kTX      = 128;  // interior tile width  (32 lanes x float4)
+constexpr int kNR      = 4;    // rows per thread
+constexpr int kTZ      = (kThreads / 32) * kNR;  // interior tile height = 32
+constexpr int kRingTX  = 64;   // ring tile extent along the band
+constexpr int kMaxR    = 16;
+
+enum SumKind { SUM_FLOAT = 0, SUM_DOUBLE = 1 };
+
+struct Geo {
+    int   NZ, NX, N2, mod_NZ, mod_NX;
+    int   pitch, padL;       // internal row pitch (floats) and left pad: cell (z,x) at z*pitch+padL+x
+    long long shot_stride;   // floats between shots of one field buffer
+    int   nfdmax;            // strip width; Taylor radius
+    int   NT;
+    int   iLSTE, iCompen;
+    float tao2, h2, taoh, taoh2, hzx2_1, vmin, dv;
+    float tao, h;            // for the corner coefficient r = v*tao/h
+    double A;                // 1.0 + (double)hzx2_1
+    int   s_l, s_r, s_z, ds, n;
+    // tiling
+    int   ntx, ntz;          // interior tiles
+    int   nband, nside;      // ring tiles per band (top/bottom) and per side (left/right)
+    // operator
+    const float* c;          // LS: packed table; TE: unused
+    const int*   Index;
+    float  cTE[kMaxR + 1];   // Taylor coefficients
+    double cc0TE;            // (1+hzx2_1)*c[0] in double
+    const float* v;          // [NZ][pitch], shared by all shots
+    float  w[65];            // blend weights l/N2
+};
+
+struct Strips {              // boundary strips, all shots and time slots (64-bit offsets)
+    float *up, *dw;          // [S][NT][nfdmax][mod_NX]   rows z = N2-nfdmax+j / NZ-N2+j
+    float *lf, *rt;          // [S][NT][mod_NZ][nfdmax]   cols x = N2-nfdmax+j / NX-N2+j
+};
+
+// ------------------------------------------------------------------ PTX helpers (TMA)
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int x, int z, int s)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(x), "r"(z), "r"(s)
+        : "memory");
+}
+
+// ------------------------------------------------------------------ exact arithmetic
+// final sum of the two-way update, a = ((v*v)*tao2)*h2
+__device__ __forceinline__ float finish_float(float a, float w1, float p1, float p0)
+{
+    return __fmaf_rn(a, w1, __fsub_rn(__fadd_rn(p1, p1), p0));  // Add, BKAdd, BKAdd_Con
+}
+__device__ __forceinline__ float finish_double(float a, float w1, float p1, float p0)
+{
+    // Add_Con, BKAdd_EFF, BKAdd_EFF_Con: 2.0*P1 - P0 + (float)(a*w1) in double
+    const double d = (double)p1;
+    return __double2float_rn(
+        __dadd_rn(__dsub_rn(__dadd_rn(d, d), (double)p0), (double)__fmul_rn(a, w1)));
+}
+__device__ __forceinline__ float vel_factor(const Geo& G, float v)
+{
+    return __fmul_rn(__fmul_rn(__fmul_rn(v, v), G.tao2), G.h2);
+}
+// velocity bin of the adaptive operator: (int)((v-vmin)/dv+0.5), (int)(...+1.5)
+__device__ __forceinline__ void ls_lookup(const Geo& G, float v, int& top, int& M)
+{
+    const float  q  = __fdiv_rn(__fsub_rn(v, G.vmin), G.dv);
+    const double qd = (double)q;
+    top             = __ldg(G.Index + __double2int_rz(__dadd_rn(qd, 0.5)));
+    M               = __ldg(G.Index + __double2int_rz(__dadd_rn(qd, 1.5))) - top - 1;
+}
+
+// ------------------------------------------------------------------ generic cell (ring path)
+// Two-way update of the cell whose current-field value is *sc in a shared tile of pitch SP.
+template <bool LS>
+__device__ __forceinline__ float two_way_generic(const Geo& G, const float* sc, int SP, float p0,
+                                                 float vv, int sum_kind)
+{
+    const float p1 = sc[0];
+    float       w1;
+    if (LS) {
+        int top, M;
+        ls_lookup(G, vv, top, M);
+        const float* cp = G.c + top;
+        w1 = __double2float_rn(__dmul_rn(__dmul_rn(G.A, (double)__ldg(cp)), (double)p1));
+        for (int l = 1; l <= M; ++l) {
+            const float s = __fadd_rn(sc[-l * SP], sc[l * SP]);
+            const float t = __fmaf_rn(s, G.hzx2_1, sc[-l]);
+            const float u = __fadd_rn(t, sc[l]);
+            w1            = __fmaf_rn(__ldg(cp + l), u, w1);
+        }
+    } else {
+        w1 = __double2float_rn(__dmul_rn(G.cc0TE, (double)p1));
+        for (int l = 1; l <= G.nfdmax; ++l) {
+            const float s = __fadd_rn(sc[-l * SP], sc[l * SP]);
+            const float t = __fmaf_rn(s, G.hzx2_1, sc[-l]);
+            const float u = __fadd_rn(t, sc[l]);
+            w1            = __fmaf_rn(G.cTE[l], u, w1);
+        }
+    }
+    const float a = vel_factor(G, vv);
+    return sum_kind == SUM_FLOAT ? finish_float(a, w1, p1, p0) : finish_double(a, w1, p1, p0);
+}
+
+// data cell test of BKAdd (:349-353): row s_z, s_l <= x <= s_r, (x-s_l)%ds==0
+__device__ __forceinline__ int data_index(const Geo& G, int z, int x)
+{
+    if (z != G.s_z || x < G.s_l || x > G.s_r) return -1;
+    const int d = x - G.s_l;
+    return (d % G.ds == 0) ? d / G.ds : -1;
+}
+
+// One ring tile.  Output rectangle [za,zb) x [xa,xb) lies in the ring; the two-way update is
+// evaluated on that rectangle grown by one cell (clipped to the array), because the one-way
+// formulas need the UNBLENDED two-way values of neighbours (Hybrid1 reads DFW2 before
+// Hybrid2 blends it).  Returns the blended value through `emit(z, x, value)`.
+struct RingRect { int za, zb, xa, xb; };
+
+__device__ __forceinline__ RingRect ring_rect(const Geo& G, int tile)
+{
+    RingRect r;
+    const int N2 = G.N2;
+    if (tile < 2 * G.nband) {  // top / bottom band: all columns
+        const bool top = tile < G.nband;
+        const int  i   = top ? tile : tile - G.nband;
+        r.za = top ? 0 : G.NZ - N2;
+        r.zb = r.za + N2;
+        r.xa = i * kRingTX;
+        r.xb = min(r.xa + kRingTX, G.NX);
+    } else {  // left / right side: interior rows
+        tile -= 2 * G.nband;
+        const bool left = tile < G.nside;
+        const int  i    = left ? tile : tile - G.nside;
+        r.xa = left ? 0 : G.NX - N2;
+        r.xb = r.xa + N2;
+        r.za = N2 + i * kRingTX;
+        r.zb = min(r.za + kRingTX, G.NZ - N2);
+    }
+    return r;
+}
+
+// shared memory needed by a ring tile (floats)
+__host__ __device__ inline int ring_smem_floats(int N2, int R)
+{
+    const int a = (N2 + 2 + 2 * R) * (kRingTX + 2 + 2 * R);  // current field with stencil halo
+    const int b = (N2 + 2) * (kRingTX + 2);                  // previous field, two-way result
+    return a + 2 * b;
+}
+
+template <bool LS, class Emit>
+__device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* __restrict__ P1,
+                                          const float* __restrict__ P0, int sum_kind,
+                                          bool inject, int r_u, int r_x, float wavelet,
+                                          const float* __restrict__ seis_row, float* smem, Emit emit)
+{
+    const RingRect o  = ring_rect(G, tile);
+    const int      NZ = G.NZ, NX = G.NX, N2 = G.N2, R = G.nfdmax, pitch = G.pitch;
+    const float*   V  = G.v + G.padL;  // cell (z,x) of the model at V[z*pitch+x]
+    // compute rectangle = output grown by 1, clipped
+    const int cza = max(o.za - 1, 0), czb = min(o.zb + 1, NZ);
+    const int cxa = max(o.xa - 1, 0), cxb = min(o.xb + 1, NX);
+    const int ch = czb - cza, cw = cxb - cxa;
+    const int SP = cw + 2 * R;  // pitch of the current-field tile (with halo R)
+    float* s1 = smem;                          // (ch+2R) x SP
+    float* s0 = s1 + (ch + 2 * R) * SP;        // ch x cw   previous field
+    float* s2 = s0 + ch * cw;                  // ch x cw   unblended two-way result
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < (ch + 2 * R) * SP; i += kThreads) {
+        int gz = cza - R + i / SP, gx = cxa - R + i % SP;
+        if (gz < 0) gz = -gz;                      // mirror about the array edge (:65-68)
+        if (gz >= NZ) gz = 2 * NZ - 2 - gz;
+        if (gx < 0) gx = -gx;
+        if (gx >= NX) gx = 2 * NX - 2 - gx;
+        s1[i] = P1[(size_t)gz * pitch + gx];
+    }
+    for (int i = tid; i < ch * cw; i += kThreads)
+        s0[i] = P0[(size_t)(cza + i / cw) * pitch + cxa + i % cw];
+    __syncthreads();
+
+    for (int i = tid; i < ch * cw; i += kThreads) {
+        const int lz = i / cw, lx = i % cw, z = cza + lz, x = cxa + lx;
+        float     val;
+        int       j = seis_row ? data_index(G, z, x) : -1;
+        float     d = (j >= 0) ? seis_row[j] : 0.0f;
+        if (j >= 0 && d != 0.0f) {
+            val = d;  // replacement (BKAdd :349-353)
+        } else {
+            const float vv = __ldg(V + (size_t)z * pitch + x);
+            val = two_way_generic<LS>(G, s1 + (lz + R) * SP + lx + R, SP, s0[i], vv, sum_kind);
+        }
+        if (inject && z == r_u && x == r_x) val = __fadd_rn(val, wavelet);
+        s2[i] = val;
+    }
+    __syncthreads();
+
+    const int oh = o.zb - o.za, ow = o.xb - o.xa;
+    for (int i = tid; i < oh * ow; i += kThreads) {
+        const int z = o.za + i / ow, x = o.xa + i % ow;
+        const int lz = z - cza, lx = x - cxa;
+        const int dz = min(z, NZ - 1 - z), dx = min(x, NX - 1 - x);
+        const int a  = min(dz, dx);
+        const int sz = (z < NZ - 1 - z) ? 1 : -1, sx = (x < NX - 1 - x) ? 1 : -1;
+#define S2(zz, xx) s2[(lz + (zz)) * cw + lx + (xx)]
+#define S0(zz, xx) s0[(lz + (zz)) * cw + lx + (xx)]
+#define S1(zz, xx) s1[(lz + R + (zz)) * SP + lx + R + (xx)]
+        float Pb;
+        if (abs(dz - dx) <= 1) {
+            // corner cells (Hybrid1 :138-155): r1 = sqrt((v*tao/h)^2/2) at the cell itself
+            // (GPU_velocity_real.cpp:104-117; tao/h enters as v*tao/h in float)
+            const float vv = __ldg(V + (size_t)z * pitch + x);
+            const float r  = __fdiv_rn(__fmul_rn(vv, G.tao), G.h);
+            const float r2 = __double2float_rn(__dmul_rn(__dmul_rn((double)r, (double)r), 0.5));
+            const float r1 = __fsqrt_rn(r2);
+            const float rcp = __frcp_rn(__fmaf_rn(2.0f, r1, 1.0f));
+            const float nb  = __fadd_rn(S2(0, sx), S2(sz, 0));
+            Pb = __fmul_rn(rcp, __fmaf_rn(r1, nb, S1(0, 0)));
+        } else {
+            int   iz, ix, tz, tx;
+            float vq;
+            if (dz < dx) {  // top :124 / bottom :132
+                iz = sz; ix = 0; tz = 0; tx = 1;
+                vq = __ldg(V + (size_t)a * pitch + x);
+            } else {        // left :128 / right :136: flat index (N2-l)*NX + row
+                iz = 0; ix = sx; tz = 1; tx = 0;
+                const int flat = a * NX + z;
+                vq = __ldg(V + (size_t)(flat / NX) * pitch + flat % NX);
+            }
+            const float vb  = __ldg(V + (size_t)z * pitch + x);
+            const float tv  = __fmul_rn(G.taoh, vb);
+            const float rcp = __frcp_rn(__fadd_rn(tv, 1.0f));
+            const float p2i = S2(iz, ix), p0i = S0(iz, ix), p0b = S0(0, 0);
+            const float p1b = S1(0, 0), p1i = S1(iz, ix);
+            const float A1  = __fadd_rn(__fsub_rn(p2i, p0i), p0b);
+            float B = __fadd_rn(__fmul_rn(-2.0f, p1b), p0b);
+            B       = __fadd_rn(B, p2i);
+            B       = __fsub_rn(B, __fmul_rn(2.0f, p1i));
+            B       = __fadd_rn(B, p0i);
+            float D = __fsub_rn(S2(iz + tz, ix + tx), __fmul_rn(2.0f, p2i));
+            D       = __fadd_rn(D, S2(iz - tz, ix - tx));
+            D       = __fadd_rn(D, S0(tz, tx));
+            D       = __fsub_rn(D, __fmul_rn(2.0f, p0b));
+            D       = __fadd_rn(D, S0(-tz, -tx));
+            const float c2 = __fmul_rn(__fmul_rn(G.taoh2, vq), vq);
+            Pb = __fmul_rn(rcp, __fmaf_rn(c2, D, __fmaf_rn(tv, A1, -B)));
+        }
+        // blend (Hybrid2 :160-183): fma(1-w, P2, w*Pb)
+        const float w   = G.w[N2 - a];
+        const float val = __fmaf_rn(__fsub_rn(1.0f, w), S2(0, 0), __fmul_rn(w, Pb));
+#undef S2
+#undef S0
+#undef S1
+        emit(z, x, val);
+    }
+}
+
+}  // namespace rtmk
+
+// =====================================================================================
+// Interior fast path
+// =====================================================================================
+namespace rtmk {
+
+// Shared-memory tile of the current field for one interior tile: rows [z0-RP, z0+kTZ+RP),
+// columns [x0-RP, x0+kTX+RP), dense, pitch kTX+2RP floats, written by one TMA box copy.
+template <int RP> struct Tile {
+    static constexpr int SP    = kTX + 2 * RP;
+    static constexpr int ROWS  = kTZ + 2 * RP;
+    static constexpr int BYTES = SP * ROWS * 4;
+};
+
+// Stencil sums w1 for this thread's 4 x kNR block.  `sc` points at the thread's first cell
+// (row lz0, column lx0) inside the shared tile.  M <= RP is the (uniform) operator length for
+// the Taylor operator; for the adaptive operator each cell brings its own length/offset.
+template <int RP, bool LS>
+__device__ __forceinline__ void stencil_block(const Geo& G, const float* sc, int M,
+                                              const float4 (&v4)[kNR], float (&w1)[kNR][4],
+                                              float (&p1)[kNR][4])
+{
+    constexpr int SP = Tile<RP>::SP;
+    float col[kNR + 2 * RP][4];  // rows lz0-RP .. lz0+kNR-1+RP at this thread's 4 columns
+#pragma unroll
+    for (int i = 0; i < kNR + 2 * RP; ++i) {
+        const float4 t4 = *reinterpret_cast<const float4*>(sc + (i - RP) * SP);
+        col[i][0] = t4.x; col[i][1] = t4.y; col[i][2] = t4.z; col[i][3] = t4.w;
+    }
+
+#pragma unroll
+    for (int r = 0; r < kNR; ++r) {
+        float xr[4 + 2 * RP];  // row lz0+r, columns lx0-RP .. lx0+3+RP
+#pragma unroll
+        for (int g = 0; g < RP / 4; ++g) {
+            const float4 L = *reinterpret_cast<const float4*>(sc + r * SP - RP + 4 * g);
+            const float4 Rr = *reinterpret_cast<const float4*>(sc + r * SP + 4 + 4 * g);
+            xr[4 * g + 0] = L.x; xr[4 * g + 1] = L.y; xr[4 * g + 2] = L.z; xr[4 * g + 3] = L.w;
+            xr[RP + 4 + 4 * g + 0] = Rr.x; xr[RP + 4 + 4 * g + 1] = Rr.y;
+            xr[RP + 4 + 4 * g + 2] = Rr.z; xr[RP + 4 + 4 * g + 3] = Rr.w;
+        }
+        xr[RP + 0] = col[r + RP][0]; xr[RP + 1] = col[r + RP][1];
+        xr[RP + 2] = col[r + RP][2]; xr[RP + 3] = col[r + RP][3];
+        const float vq[4] = {v4[r].x, v4[r].y, v4[r].z, v4[r].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float pc = xr[RP + q];
+            p1[r][q]       = pc;
+            float w;
+            if (LS) {
+                int top, Mc;
+                ls_lookup(G, vq[q], top, Mc);
+                const float* cp = G.c + top;
+                w = __double2float_rn(__dmul_rn(__dmul_rn(G.A, (double)__ldg(cp)), (double)pc));
+#pragma unroll
+                for (int l = 1; l <= RP; ++l) {
+                    if (l <= Mc) {
+                        const float zm = col[r + RP - l][q], zp = col[r + RP + l][q];
+                        const float s  = __fadd_rn(zm, zp);
+                        const float t  = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
+                        const float u  = __fadd_rn(t, xr[RP + q + l]);
+                        w              = __fmaf_rn(__ldg(cp + l), u, w);
+                    }
+                }
+            } else {
+                w = __double2float_rn(__dmul_rn(G.cc0TE, (double)pc));
+#pragma unroll
+                for (int l = 1; l <= RP; ++l) {
+                    if (l <= M) {
+                        const float zm = col[r + RP - l][q], zp = col[r + RP + l][q];
+                        const float s  = __fadd_rn(zm, zp);
+                        const float t  = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
+                        const float u  = __fadd_rn(t, xr[RP + q + l]);
+                        w              = __fmaf_rn(G.cTE[l], u, w);
+                    }
+                }
+            }
+            w1[r][q] = w;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Forward step: slot k from slots k-1 (P1, via TMA / raw pointer) and k-2 (P0).
+// grid = (ring tiles + interior tiles, shots)
+// ------------------------------------------------------------------------------------
+struct FwdArgs {
+    const float* P1;   // slot k-1, all shots
+    const float* P0;   // slot k-2
+    float*       P2;   // slot k
+    const int2*  src;  // per shot (r_u, r_x)
+    float        wavelet;
+    int          k;    // time slot being produced
+    Strips       st;   // may hold nulls when strips are not wanted (pure modelling)
+    float*       gather;  // [S][NT][n] time-major, or null
+};
+
+template <int RP, bool LS>
+__global__ void __launch_bounds__(kThreads)
+fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ Geo G,
+                const FwdArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int  shot  = blockIdx.y;
+    const int  nring = 2 * G.nband + 2 * G.nside;
+    const long long so = (long long)shot * G.shot_stride + G.padL;  // (z=0,x=0) of this shot
+    const int2 src = a.src[shot];
+    const int  sum_kind = G.iLSTE == 0 ? SUM_FLOAT : SUM_DOUBLE;  // Add vs Add_Con
+
+    if ((int)blockIdx.x < nring) {
+        float* P2 = a.P2 + so;
+        const int N2 = G.N2, nf = G.nfdmax, NZ = G.NZ, NX = G.NX, k = a.k;
+        const Strips st = a.st;
+        float* gather = a.gather;
+        ring_tile<LS>(G, blockIdx.x, a.P1 + so, a.P0 + so, sum_kind, true, src.x, src.y, a.wavelet,
+                      nullptr, reinterpret_cast<float*>(smem_raw),
+                      [&](int z, int x, float val) {
+            P2[(size_t)z * G.pitch + x] = val;
+            if (st.up) {  // Hybrid3 :184-208 (slot k)
+                const size_t sx = ((size_t)shot * G.NT + k) * nf * G.mod_NX;
+                const size_t sz = ((size_t)shot * G.NT + k) * nf * G.mod_NZ;
+                if (x >= N2 && x < NX - N2) {
+                    if (z >= N2 - nf && z < N2) st.up[sx + (size_t)(z - (N2 - nf)) * G.mod_NX + x - N2] = val;
+                    else if (z >= NZ - N2 && z < NZ - N2 + nf) st.dw[sx + (size_t)(z - (NZ - N2)) * G.mod_NX + x - N2] = val;
+                } else if (z >= N2 && z < NZ - N2) {
+                    if (x >= N2 - nf && x < N2) st.lf[sz + (size_t)(z - N2) * nf + x - (N2 - nf)] = val;
+                    else if (x >= NX - N2 && x < NX - N2 + nf) st.rt[sz + (size_t)(z - N2) * nf + x - (NX - N2)] = val;
+                }
+            }
+            if (gather) {
+                const int j = data_index(G, z, x);
+                if (j >= 0) gather[((size_t)shot * G.NT + k) * G.n + j] = val;
+            }
+        });
+        return;
+    }
+
+    // ---- interior tile
+    const int t   = blockIdx.x - nring;
+    const int tz  = t / G.ntx, tx = t % G.ntx;
+    const int z0  = G.N2 + tz * kTZ, x0 = G.N2 + tx * kTX;  // first interior cell of the tile
+    float*    sP  = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Tile<RP>::BYTES);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, Tile<RP>::BYTES);
+        tma_load_3d(sP, &tmP1, bar, G.padL + x0 - RP, z0 - RP, shot);
+    }
+
+    // coalesced float4 loads of the other streams while the TMA copy is in flight
+    const int lz0 = warp * kNR, lx0 = lane * 4;
+    const int z = z0 + lz0, x = x0 + lx0;
+    const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
+    float4 p0[kNR], v4[kNR];
+#pragma unroll
+    for (int r = 0; r < kNR; ++r) {
+        if (z + r < zend && x < xend) {
+            p0[r] = *reinterpret_cast<const float4*>(a.P0 + so + (size_t)(z + r) * G.pitch + x);
+            v4[r] = __ldg(reinterpret_cast<const float4*>(G.v + G.padL + (size_t)(z + r) * G.pitch + x));
+        } else {
+            p0[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v4[r] = make_float4(G.vmin, G.vmin, G.vmin, G.vmin);
+        }
+    }
+    mbar_wait(bar, 0);
+
+    float w1[kNR][4], p1[kNR][4];
+    stencil_block<RP, LS>(G, sP + (lz0 + RP) * Tile<RP>::SP + lx0 + RP, G.nfdmax, v4, w1, p1);
+
+#pragma unroll
+    for (int r = 0; r < kNR; ++r) {
+        const int zz = z + r;
+        if (zz >= zend || x >= xend) continue;
+        const float vq[4] = {v4[r].x, v4[r].y, v4[r].z, v4[r].w};
+        const float pq[4] = {p0[r].x, p0[r].y, p0[r].z, p0[r].w};
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float av = vel_factor(G, vq[q]);
+            o[q] = sum_kind == SUM_FLOAT ? finish_float(av, w1[r][q], p1[r][q], pq[q])
+                                         : finish_double(av, w1[r][q], p1[r][q], pq[q]);
+            if (zz == src.x && x + q == src.y) o[q] = __fadd_rn(o[q], a.wavelet);  // :74-77
+        }
+        float* dst = a.P2 + so + (size_t)zz * G.pitch + x;
+        if (x + 3 < xend) {
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (x + q < xend) dst[q] = o[q];
+        }
+        if (a.gather && zz == G.s_z) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = (x + q < xend) ? data_index(G, zz, x + q) : -1;
+                if (j >= 0) a.gather[((size_t)shot * G.NT + a.k) * G.n + j] = o[q];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Backward step k: source slot k reconstructed in the interior (in place over slot k+2),
+// receiver slot k on the full grid with data replacement and ABC, imaging accumulators.
+// ------------------------------------------------------------------------------------
+struct BwdArgs {
+    const float* S1;   // source slot k+1 (ring = strips of slot k+1)
+    float*       S02;  // in: source slot k+2, out: source slot k (interior), ring := strips of slot k
+    const float* R1;   // receiver, current
+    const float* R0;   // receiver, previous
+    float*       R2;   // receiver, new
+    const int2*  src;
+    float        wavelet;
+    int          k;
+    Strips       st;
+    const float* seis;  // [S][NT][n] time-major; row k+1 is imposed
+    float *sumS, *sumR, *rel1, *rel2;  // accumulators, field layout
+};
+
+template <int RP, bool LS>
+__global__ void __launch_bounds__(kThreads)
+bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmR1,
+                const __grid_constant__ Geo G, const BwdArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int  shot  = blockIdx.y;
+    const int  nring = 2 * G.nband + 2 * G.nside;
+    const long long so = (long long)shot * G.shot_stride + G.padL;
+    const int2 src = a.src[shot];
+    const float* seis_row = a.seis + ((size_t)shot * G.NT + (a.k + 1)) * G.n;
+
+    if ((int)blockIdx.x < nring) {
+        float* R2 = a.R2 + so;
+        float* SX = a.S02 + so;
+        const int N2 = G.N2, nf = G.nfdmax, NZ = G.NZ, NX = G.NX, k = a.k;
+        const Strips st = a.st;
+        ring_tile<LS>(G, blockIdx.x, a.R1 + so, a.R0 + so, SUM_FLOAT, false, 0, 0, 0.0f, seis_row,
+                      reinterpret_cast<float*>(smem_raw), [&](int z, int x, float val) {
+            R2[(size_t)z * G.pitch + x] = val;
+            // BKEqual :222-245, one step early: the ring of the buffer that becomes the
+            // "current" source field at step k-1 receives the strips of slot k.
+            const size_t sx = ((size_t)shot * G.NT + k) * nf * G.mod_NX;
+            const size_t sz = ((size_t)shot * G.NT + k) * nf * G.mod_NZ;
+            if (x >= N2 && x < NX - N2) {
+                if (z >= N2 - nf && z < N2) SX[(size_t)z * G.pitch + x] = st.up[sx + (size_t)(z - (N2 - nf)) * G.mod_NX + x - N2];
+                else if (z >= NZ - N2 && z < NZ - N2 + nf) SX[(size_t)z * G.pitch + x] = st.dw[sx + (size_t)(z - (NZ - N2)) * G.mod_NX + x - N2];
+            } else if (z >= N2 && z < NZ - N2) {
+                if (x >= N2 - nf && x < N2) SX[(size_t)z * G.pitch + x] = st.lf[sz + (size_t)(z - N2) * nf + x - (N2 - nf)];
+                else if (x >= NX - N2 && x < NX - N2 + nf) SX[(size_t)z * G.pitch + x] = st.rt[sz + (size_t)(z - N2) * nf + x - (NX - N2)];
+            }
+        });
+        return;
+    }
+
+    const int t   = blockIdx.x - nring;
+    const int tz  = t / G.ntx, tx = t % G.ntx;
+    const int z0  = G.N2 + tz * kTZ, x0 = G.N2 + tx * kTX;
+    float*    sS  = reinterpret_cast<float*>(smem_raw);
+    float*    sR  = reinterpret_cast<float*>(smem_raw + Tile<RP>::BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * Tile<RP>::BYTES);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, 2 * Tile<RP>::BYTES);
+        tma_load_3d(sS, &tmS1, bar, G.padL + x0 - RP, z0 - RP, shot);
+        tma_load_3d(sR, &tmR1, bar, G.padL + x0 - RP, z0 - RP, shot);
+    }
+
+    const int lz0 = warp * kNR, lx0 = lane * 4;
+    const int z = z0 + lz0, x = x0 + lx0;
+    const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
+    float4 v4[kNR], s0[kNR], r0[kNR];
+#pragma unroll
+    for (int r = 0; r < kNR; ++r) {
+        if (z + r < zend && x < xend) {
+            const size_t o = so + (size_t)(z + r) * G.pitch + x;
+            v4[r] = __ldg(reinterpret_cast<const float4*>(G.v + G.padL + (size_t)(z + r) * G.pitch + x));
+            s0[r] = *reinterpret_cast<const float4*>(a.S02 + o);
+            r0[r] = *reinterpret_cast<const float4*>(a.R0 + o);
+        } else {
+            v4[r] = make_float4(G.vmin, G.vmin, G.vmin, G.vmin);
+            s0[r] = r0[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    mbar_wait(bar, 0);
+
+    float w1[kNR][4], p1[kNR][4];
+    float S2[kNR][4];
+    // source field: BKAdd_EFF / BKAdd_EFF_Con, double final sum, + wavelet at the source
+    stencil_block<RP, LS>(G, sS + (lz0 + RP) * Tile<RP>::SP + lx0 + RP, G.nfdmax, v4, w1, p1);
+#pragma unroll
+    for (int r = 0; r < kNR; ++r) {
+        const float vq[4] = {v4[r].x, v4[r].y, v4[r].z, v4[r].w};
+        const float pq[4] = {s0[r].x, s0[r].y, s0[r].z, s0[r].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float o = finish_double(vel_factor(G, vq[q]), w1[r][q], p1[r][q], pq[q]);
+            if (z + r == src.x && x + q == src.y) o = __fadd_rn(o, a.wavelet);
+            S2[r][q] = o;
+        }
+    }
+    // receiver field: BKAdd / BKAdd_Con, float final sum, data replacement
+    stencil_block<RP, LS>(G, sR + (lz0 + RP) * Tile<RP>::SP + lx0 + RP, G.nfdmax, v4, w1, p1);
+
+#pragma unroll
+    for (int r = 0; r < kNR; ++r) {
+        const int zz = z + r;
+        if (zz >= zend || x >= xend) continue;
+        const float vq[4] = {v4[r].x, v4[r].y, v4[r].z, v4[r].w};
+        const float pq[4] = {r0[r].x, r0[r].y, r0[r].z, r0[r].w};
+        float R2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            R2[q] = finish_float(vel_factor(G, vq[q]), w1[r][q], p1[r][q], pq[q]);
+        if (zz == G.s_z) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = (x + q < xend) ? data_index(G, zz, x + q) : -1;
+                if (j >= 0) {
+                    const float d = seis_row[j];
+                    if (d != 0.0f) R2[q] = d;
+                }
+            }
+        }
+        const size_t o = so + (size_t)zz * G.pitch + x;
+        // imaging (Rel_Compen :503-517 / Rel_NonCompen :489-501), S = source, R = receiver
+        float4 aS, aR, a1, a2;
+        a1 = *reinterpret_cast<const float4*>(a.rel1 + o);
+        a2 = *reinterpret_cast<const float4*>(a.rel2 + o);
+        float r1v[4] = {a1.x, a1.y, a1.z, a1.w}, r2v[4] = {a2.x, a2.y, a2.z, a2.w};
+        float sSv[4], sRv[4];
+        if (G.iCompen == 1) {
+            aS = *reinterpret_cast<const float4*>(a.sumS + o);
+            aR = *reinterpret_cast<const float4*>(a.sumR + o);
+            sSv[0] = aS.x; sSv[1] = aS.y; sSv[2] = aS.z; sSv[3] = aS.w;
+            sRv[0] = aR.x; sRv[1] = aR.y; sRv[2] = aR.z; sRv[3] = aR.w;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                sSv[q] = __fadd_rn(S2[r][q], sSv[q]);
+                sRv[q] = __fadd_rn(R2[q], sRv[q]);
+                r1v[q] = __fmaf_rn(sRv[q], sSv[q], r1v[q]);
+                r2v[q] = __fmaf_rn(S2[r][q], S2[r][q], r2v[q]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                r1v[q] = __fmaf_rn(R2[q], S2[r][q], r1v[q]);
+                r2v[q] = __fmaf_rn(S2[r][q], S2[r][q], r2v[q]);
+            }
+        }
+        if (x + 3 < xend) {
+            *reinterpret_cast<float4*>(a.S02 + o) = make_float4(S2[r][0], S2[r][1], S2[r][2], S2[r][3]);
+            *reinterpret_cast<float4*>(a.R2 + o)  = make_float4(R2[0], R2[1], R2[2], R2[3]);
+            *reinterpret_cast<float4*>(a.rel1 + o) = make_float4(r1v[0], r1v[1], r1v[2], r1v[3]);
+            *reinterpret_cast<float4*>(a.rel2 + o) = make_float4(r2v[0], r2v[1], r2v[2], r2v[3]);
+            if (G.iCompen == 1) {
+                *reinterpret_cast<float4*>(a.sumS + o) = make_float4(sSv[0], sSv[1], sSv[2], sSv[3]);
+                *reinterpret_cast<float4*>(a.sumR + o) = make_float4(sRv[0], sRv[1], sRv[2], sRv[3]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (x + q < xend) {
+                    a.S02[o + q] = S2[r][q];
+                    a.R2[o + q]  = R2[q];
+                    a.rel1[o + q] = r1v[q];
+                    a.rel2[o + q] = r2v[q];
+                    if (G.iCompen == 1) { a.sumS[o + q] = sSv[q]; a.sumR[o + q] = sRv[q]; }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace rtmk

@@ -1,0 +1,130 @@
+"""Host-side pieces of the product (C++ behind the C ABI) against the oracle and against
+golden vectors produced by the reference's own host code.  No GPU needed."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oraclelib as O
+import rtm_gpu_b200 as R
+from golden_cases import GOLDEN_CASES
+from refcase import ROOT, velocity_tiny
+
+
+def golden(name):
+    return np.load(ROOT / "tests" / "golden" / f"{name}.npz")
+
+
+def test_abi_exports_every_declared_symbol():
+    L = R.lib()
+    header = (ROOT / "include" / "rtm_b200.h").read_text()
+    import re
+    declared = set(re.findall(r"\b(rtm_[a-z_0-9]+)\s*\(", header)) - {"rtm_ctx", "rtm_params", "rtm_stats", "rtm_status"}
+    assert declared == set(R.ABI_SYMBOLS), declared ^ set(R.ABI_SYMBOLS)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert b"sm_100a" in L.rtm_version()
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(R.RtmError, match="no CUDA device"):
+        R.engine_for_case(GOLDEN_CASES["tiny_te_compen"])
+
+
+def test_ricker_matches_oracle():
+    for f0 in (15.0, 25.0, 8.5):
+        for k in range(0, 400, 7):
+            t = np.float32(k) * np.float32(0.001)
+            assert R.ricker(t, f0) == O.ricker(t, f0)
+
+
+@pytest.mark.parametrize("args", [(20.0, 20.0, 0.001, 0.001, 15.0, 400), (20.0, 10.0, 0.0008, 0.002, 15.0, 260),
+                                  (4.0, 4.0, 0.0004, 0.0004, 25.0, 7501), (12.5, 5.0, 0.00075, 0.001, 30.0, 3501)])
+def test_derived_scalars(args):
+    assert R.derived(*args) == O.derived(*args)
+
+
+def test_source_row():
+    for depth, hz, N2, want in [(300.0, 20.0, 10, 24), (500.0, 20.0, 10, 34), (5.0, 10.0, 12, 11), (150.0, 10.0, 12, 26)]:
+        assert R.source_row(depth, hz, N2) == want
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_velocity_padding_and_bins(name):
+    case, g = GOLDEN_CASES[name], golden(name)
+    vel = velocity_tiny(case)
+    v = R.pad_velocity(vel, case.N2, case.ifv)
+    vo, _ = O.pad_velocity(vel, case.N2, case.ifv, case.tao, case.h)
+    assert np.array_equal(v, vo)
+    vmin, vmax, nvel, need = R.velocity_bins(v, case.dv)
+    assert (vmin, vmax, nvel) == tuple(g["vrange"])
+    assert np.array_equal(need, O.velocity_bins(v, case.dv)[3])
+
+
+def test_velocity_padding_matches_reference_function(tmp_path):
+    if O.refhost() is None:
+        pytest.skip("oracle/_ref/libref_host.so not built here")
+    case = GOLDEN_CASES["small_aniso_flip"]
+    vel = velocity_tiny(case)
+    path = tmp_path / "v.dat"
+    vel.tofile(path)
+    NZ, NX = case.NZ, case.NX
+    arrs = [np.zeros((NZ, NX), np.float32) for _ in range(5)]
+    O.refhost().ref_velocity(str(path).encode(), *[a.ctypes.data_as(O.fp) for a in arrs], NZ, NX, case.N2,
+                             case.tao, case.h, case.ifv)
+    assert np.array_equal(arrs[0], R.pad_velocity(vel, case.N2, case.ifv))
+    _, r1 = O.pad_velocity(vel, case.N2, case.ifv, case.tao, case.h)
+    assert np.array_equal(arrs[3], r1)  # corner coefficient r_1 restated by the oracle
+
+
+def test_taylor_operator_golden():
+    assert np.array_equal(R.taylor_operator(4), golden("tiny_te_compen")["c"])
+    for M in (1, 2, 6, 8, 12):
+        assert np.array_equal(R.taylor_operator(M), O.taylor(M))
+
+
+@pytest.mark.parametrize("name", ["tiny_ls_compen", "small_aniso_flip"])
+def test_ls_operator_golden(name):
+    """funMandC: operator lengths, prefix index and packed float coefficients, bit-exact
+    against the reference's own implementation (golden)."""
+    case, g = GOLDEN_CASES[name], golden(name)
+    v = R.pad_velocity(velocity_tiny(case), case.N2, case.ifv)
+    vmin, vmax, nvel, need = R.velocity_bins(v, case.dv)
+    hzx = float(np.float32(case.hz) / np.float32(case.h))
+    NC, M, Index, c = R.ls_operator(case.nthita, case.nfdmax, case.nfdmin, nvel, case.tao, case.h, case.df,
+                                    case.eps, case.fmax, vmin, case.dv, hzx, need)
+    assert NC == len(g["c"])
+    assert np.array_equal(M, g["M"])
+    assert np.array_equal(Index, g["Index"])
+    assert np.array_equal(c, g["c"])
+
+
+def test_ls_coefficients_known_answers():
+    """SURVEY 4.3 KATs: h=20 tao=1e-3 fmax=31 hzx=1."""
+    kat = {1500.0: (9, [-3.21630073, 1.92961347, -0.435938716, 0.163882032, -0.0720951483, 0.0330284722,
+                        -0.0147120021, 0.00589827308, -0.00184054766, 0.000314513716]),
+           3000.0: (3, [-2.78983569, 1.55340326, -0.174627692, 0.0161423106]),
+           4500.0: (2, [-2.50473809, 1.33665204, -0.0842829868])}
+    tao, h, fmax = float(np.float32(0.001)), 20.0, 31.0
+    for vel, (M, want) in kat.items():
+        r = vel * (tao / h)
+        b = (2.0 * 3.1415926535898 * fmax * tao) / r
+        c = R.ls_coefficients(r, b, M, 1.0).astype(np.float32)
+        np.testing.assert_allclose(c, np.array(want, np.float32), rtol=2e-7)
+
+
+def test_stack_finalize_matches_oracle():
+    rng = np.random.default_rng(7)
+    ups = [rng.standard_normal((9, 7)).astype(np.float32) for _ in range(3)]
+    downs = [np.abs(rng.standard_normal((9, 7))).astype(np.float32) + 1 for _ in range(3)]
+    su, sd = np.zeros((9, 7), np.float32), np.zeros((9, 7), np.float32)
+    for u, d in zip(ups, downs):
+        su += u
+        sd += d
+    for iNorm in (0, 1):
+        img, ill = R.stack_finalize(su, sd, 3, iNorm)
+        oi, od = O.stack(ups, downs, iNorm)
+        assert np.array_equal(img, oi) and np.array_equal(ill, od)
