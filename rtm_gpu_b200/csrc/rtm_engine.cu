@@ -189,7 +189,7 @@ struct rtm_ctx {
     bool       have_model = false, have_op = false;
     float      vmax = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t  ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
     // device memory
     float* field[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float* acc[4]   = {nullptr, nullptr, nullptr, nullptr};
@@ -206,6 +206,7 @@ struct rtm_ctx {
     int    stack_shots = 0;
     size_t field_floats = 0;
     size_t smem_fwd = 0, smem_bwd = 0;
+    float  last_forward_ms = 0;
     rtm_stats stats{};
 };
 
@@ -258,6 +259,8 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     cudaFree(c->d_maxbits);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evA) cudaEventDestroy(c->evA);
+    if (c->evB) cudaEventDestroy(c->evB);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -323,6 +326,8 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CKC(cudaEventCreate(&c->ev0));
     CKC(cudaEventCreate(&c->ev1));
+    CKC(cudaEventCreate(&c->evA));
+    CKC(cudaEventCreate(&c->evB));
     c->field_floats = (size_t)c->S * G.shot_stride + 64;  // slack for float4 loads past the last row
     const size_t ncell = (size_t)G.mod_NX * G.mod_NZ;
     size_t need = (5 + 4) * c->field_floats * 4 + (size_t)G.shot_stride * 4 +
@@ -522,8 +527,8 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
     c->stats.cell_updates += cu;
     c->stats.algorithmic_bytes += cu * 16.0;
     c->stats.forward_seconds += ms * 1e-3;
-    c->stats.device_seconds += ms * 1e-3;
-    c->stats.kernel_launches += G.NT - 2;
+    c->stats.kernel_launches += G.NT - 2 + 3;
+    c->last_forward_ms = ms;
     *last1 = i1; *last0 = i0;
     return RTM_OK;
 }
@@ -550,6 +555,7 @@ extern "C" int rtm_forward(rtm_ctx* c, int nshots, const int* r_u, const int* r_
             CK(cudaStreamSynchronize(c->stream));
         }
         c->stats.shots += ns;
+        c->stats.device_seconds += c->last_forward_ms * 1e-3;
     }
     return RTM_OK;
 }
@@ -560,6 +566,7 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
     const Geo& G = c->G;
     if (int rc = ensure_strips(c)) return rc;
     int l1, l0;
+    CK(cudaEventRecord(c->evA, c->stream));
     if (int rc = run_forward(c, ns, r_u, r_x, true, nullptr, 0, nullptr, nullptr, &l1, &l0)) return rc;
     // source field: sx = slot NT-1 ("previous", updated in place), sy = slot NT-2 ("current")
     int sx = l1, sy = l0;
@@ -599,6 +606,7 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
         image_down_kernel<<<grid, 128, 0, c->stream>>>(G, c->acc[3], c->d_maxbits, c->p.whitecoe, c->d_down, c->d_stable);
         stack_add_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, c->stream>>>(ncell, ns, c->d_up, c->d_down, c->d_stack);
     }
+    CK(cudaEventRecord(c->evB, c->stream));
     CK(cudaGetLastError());
     if (up) CK(cudaMemcpyAsync(up, c->d_up, ns * ncell * 4, cudaMemcpyDeviceToHost, c->stream));
     if (down) CK(cudaMemcpyAsync(down, c->d_down, ns * ncell * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -610,8 +618,9 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
     c->stats.cell_updates += steps * ((double)G.NZ * G.NX + (double)ncell);
     c->stats.algorithmic_bytes += steps * (double)G.NZ * G.NX * (G.iCompen == 1 ? 60.0 : 44.0);
     c->stats.backward_seconds += ms * 1e-3;
-    c->stats.device_seconds += ms * 1e-3;
-    c->stats.kernel_launches += G.NT - 2;
+    CK(cudaEventElapsedTime(&ms, c->evA, c->evB));
+    c->stats.device_seconds += ms * 1e-3;  // whole batch: init, both loops, image post, stack
+    c->stats.kernel_launches += G.NT - 2 + 4;
     c->stats.shots += ns;
     c->stack_shots += ns;
     return RTM_OK;

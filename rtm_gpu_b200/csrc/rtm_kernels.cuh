@@ -329,71 +329,85 @@ template <int RP> struct Tile {
     static constexpr int BYTES = SP * ROWS * 4;
 };
 
-// Stencil sums w1 for this thread's 4 x kNR block.  `sc` points at the thread's first cell
-// (row lz0, column lx0) inside the shared tile.  M <= RP is the (uniform) operator length for
-// the Taylor operator; for the adaptive operator each cell brings its own length/offset.
+__device__ __forceinline__ void unpack(const float4& a, float (&o)[4])
+{
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+}
+
+// Stencil sums w1 of four x-adjacent cells of one row.  `sc` points at the first of the four
+// cells inside the shared tile.  x neighbours: the row segment [x-RP, x+3+RP] as float4 shared
+// loads; z neighbours: one float4 shared load per row offset (all four cells share it), which
+// keeps the register footprint small enough for 3-4 resident CTAs per SM.
+// M <= RP is the uniform length of the Taylor operator; the adaptive operator brings a length
+// and table offset per cell.
 template <int RP, bool LS>
-__device__ __forceinline__ void stencil_block(const Geo& G, const float* sc, int M,
-                                              const float4 (&v4)[kNR], float (&w1)[kNR][4],
-                                              float (&p1)[kNR][4])
+__device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M, const float (&vq)[4],
+                                            float (&w1)[4], float (&p1)[4])
 {
     constexpr int SP = Tile<RP>::SP;
-    float col[kNR + 2 * RP][4];  // rows lz0-RP .. lz0+kNR-1+RP at this thread's 4 columns
+    float xr[4 + 2 * RP];  // columns x-RP .. x+3+RP of this row
 #pragma unroll
-    for (int i = 0; i < kNR + 2 * RP; ++i) {
-        const float4 t4 = *reinterpret_cast<const float4*>(sc + (i - RP) * SP);
-        col[i][0] = t4.x; col[i][1] = t4.y; col[i][2] = t4.z; col[i][3] = t4.w;
+    for (int g = 0; g < (4 + 2 * RP) / 4; ++g) {
+        const float4 t4 = *reinterpret_cast<const float4*>(sc - RP + 4 * g);
+        xr[4 * g + 0] = t4.x; xr[4 * g + 1] = t4.y; xr[4 * g + 2] = t4.z; xr[4 * g + 3] = t4.w;
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) p1[q] = xr[RP + q];
 
-#pragma unroll
-    for (int r = 0; r < kNR; ++r) {
-        float xr[4 + 2 * RP];  // row lz0+r, columns lx0-RP .. lx0+3+RP
-#pragma unroll
-        for (int g = 0; g < RP / 4; ++g) {
-            const float4 L = *reinterpret_cast<const float4*>(sc + r * SP - RP + 4 * g);
-            const float4 Rr = *reinterpret_cast<const float4*>(sc + r * SP + 4 + 4 * g);
-            xr[4 * g + 0] = L.x; xr[4 * g + 1] = L.y; xr[4 * g + 2] = L.z; xr[4 * g + 3] = L.w;
-            xr[RP + 4 + 4 * g + 0] = Rr.x; xr[RP + 4 + 4 * g + 1] = Rr.y;
-            xr[RP + 4 + 4 * g + 2] = Rr.z; xr[RP + 4 + 4 * g + 3] = Rr.w;
-        }
-        xr[RP + 0] = col[r + RP][0]; xr[RP + 1] = col[r + RP][1];
-        xr[RP + 2] = col[r + RP][2]; xr[RP + 3] = col[r + RP][3];
-        const float vq[4] = {v4[r].x, v4[r].y, v4[r].z, v4[r].w};
+    if (LS) {
+        int top[4], Mc[4], Mx = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float pc = xr[RP + q];
-            p1[r][q]       = pc;
-            float w;
-            if (LS) {
-                int top, Mc;
-                ls_lookup(G, vq[q], top, Mc);
-                const float* cp = G.c + top;
-                w = __double2float_rn(__dmul_rn(__dmul_rn(G.A, (double)__ldg(cp)), (double)pc));
+            ls_lookup(G, vq[q], top[q], Mc[q]);
+            Mx = max(Mx, Mc[q]);
+            w1[q] = __double2float_rn(__dmul_rn(__dmul_rn(G.A, (double)__ldg(G.c + top[q])), (double)p1[q]));
+        }
 #pragma unroll
-                for (int l = 1; l <= RP; ++l) {
-                    if (l <= Mc) {
-                        const float zm = col[r + RP - l][q], zp = col[r + RP + l][q];
-                        const float s  = __fadd_rn(zm, zp);
-                        const float t  = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
-                        const float u  = __fadd_rn(t, xr[RP + q + l]);
-                        w              = __fmaf_rn(__ldg(cp + l), u, w);
-                    }
-                }
-            } else {
-                w = __double2float_rn(__dmul_rn(G.cc0TE, (double)pc));
+        for (int l = 1; l <= RP; ++l) {
+            if (l <= Mx) {
+                float zm[4], zp[4];
+                unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
+                unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
 #pragma unroll
-                for (int l = 1; l <= RP; ++l) {
-                    if (l <= M) {
-                        const float zm = col[r + RP - l][q], zp = col[r + RP + l][q];
-                        const float s  = __fadd_rn(zm, zp);
-                        const float t  = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
-                        const float u  = __fadd_rn(t, xr[RP + q + l]);
-                        w              = __fmaf_rn(G.cTE[l], u, w);
+                for (int q = 0; q < 4; ++q) {
+                    if (l <= Mc[q]) {
+                        const float s = __fadd_rn(zm[q], zp[q]);
+                        const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
+                        const float u = __fadd_rn(t, xr[RP + q + l]);
+                        w1[q]         = __fmaf_rn(__ldg(G.c + top[q] + l), u, w1[q]);
                     }
                 }
             }
-            w1[r][q] = w;
         }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w1[q] = __double2float_rn(__dmul_rn(G.cc0TE, (double)p1[q]));
+#pragma unroll
+        for (int l = 1; l <= RP; ++l) {
+            if (l <= M) {
+                float zm[4], zp[4];
+                unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
+                unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float s = __fadd_rn(zm[q], zp[q]);
+                    const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
+                    const float u = __fadd_rn(t, xr[RP + q + l]);
+                    w1[q]         = __fmaf_rn(G.cTE[l], u, w1[q]);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void store4(float* dst, const float (&o)[4], int x, int xend)
+{
+    if (x + 3 < xend) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (x + q < xend) dst[q] = o[q];
     }
 }
 
@@ -413,7 +427,7 @@ struct FwdArgs {
 };
 
 template <int RP, bool LS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (RP <= 4 ? 4 : (RP <= 8 ? 3 : 2)))
 fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ Geo G,
                 const FwdArgs a)
 {
@@ -467,48 +481,38 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
         tma_load_3d(sP, &tmP1, bar, G.padL + x0 - RP, z0 - RP, shot);
     }
 
-    // coalesced float4 loads of the other streams while the TMA copy is in flight
     const int lz0 = warp * kNR, lx0 = lane * 4;
     const int z = z0 + lz0, x = x0 + lx0;
     const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
-    float4 p0[kNR], v4[kNR];
-#pragma unroll
-    for (int r = 0; r < kNR; ++r) {
-        if (z + r < zend && x < xend) {
-            p0[r] = *reinterpret_cast<const float4*>(a.P0 + so + (size_t)(z + r) * G.pitch + x);
-            v4[r] = __ldg(reinterpret_cast<const float4*>(G.v + G.padL + (size_t)(z + r) * G.pitch + x));
-        } else {
-            p0[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            v4[r] = make_float4(G.vmin, G.vmin, G.vmin, G.vmin);
-        }
-    }
+    if (x >= xend || z >= zend) return;  // (whole 4-cell groups; rows are warp-uniform)
+    const int nrow = min(kNR, zend - z);
+
+    // coalesced float4 loads of the other streams while the TMA copy is in flight
+    float4 p0n = *reinterpret_cast<const float4*>(a.P0 + so + (size_t)z * G.pitch + x);
+    float4 vn  = __ldg(reinterpret_cast<const float4*>(G.v + G.padL + (size_t)z * G.pitch + x));
     mbar_wait(bar, 0);
 
-    float w1[kNR][4], p1[kNR][4];
-    stencil_block<RP, LS>(G, sP + (lz0 + RP) * Tile<RP>::SP + lx0 + RP, G.nfdmax, v4, w1, p1);
-
 #pragma unroll
     for (int r = 0; r < kNR; ++r) {
+        if (r >= nrow) break;
         const int zz = z + r;
-        if (zz >= zend || x >= xend) continue;
-        const float vq[4] = {v4[r].x, v4[r].y, v4[r].z, v4[r].w};
-        const float pq[4] = {p0[r].x, p0[r].y, p0[r].z, p0[r].w};
-        float o[4];
+        float vq[4], pq[4];
+        unpack(vn, vq);
+        unpack(p0n, pq);
+        if (r + 1 < nrow) {  // next row's loads fly during this row's arithmetic
+            p0n = *reinterpret_cast<const float4*>(a.P0 + so + (size_t)(zz + 1) * G.pitch + x);
+            vn  = __ldg(reinterpret_cast<const float4*>(G.v + G.padL + (size_t)(zz + 1) * G.pitch + x));
+        }
+        float w1[4], p1[4], o[4];
+        stencil_row<RP, LS>(G, sP + (lz0 + r + RP) * Tile<RP>::SP + lx0 + RP, G.nfdmax, vq, w1, p1);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float av = vel_factor(G, vq[q]);
-            o[q] = sum_kind == SUM_FLOAT ? finish_float(av, w1[r][q], p1[r][q], pq[q])
-                                         : finish_double(av, w1[r][q], p1[r][q], pq[q]);
+            o[q] = sum_kind == SUM_FLOAT ? finish_float(av, w1[q], p1[q], pq[q])
+                                         : finish_double(av, w1[q], p1[q], pq[q]);
             if (zz == src.x && x + q == src.y) o[q] = __fadd_rn(o[q], a.wavelet);  // :74-77
         }
-        float* dst = a.P2 + so + (size_t)zz * G.pitch + x;
-        if (x + 3 < xend) {
-            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (x + q < xend) dst[q] = o[q];
-        }
+        store4(a.P2 + so + (size_t)zz * G.pitch + x, o, x, xend);
         if (a.gather && zz == G.s_z) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -538,7 +542,7 @@ struct BwdArgs {
 };
 
 template <int RP, bool LS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (RP <= 4 ? 3 : 2))
 bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmR1,
                 const __grid_constant__ Geo G, const BwdArgs a)
 {
@@ -591,49 +595,52 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
     const int lz0 = warp * kNR, lx0 = lane * 4;
     const int z = z0 + lz0, x = x0 + lx0;
     const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
-    float4 v4[kNR], s0[kNR], r0[kNR];
-#pragma unroll
-    for (int r = 0; r < kNR; ++r) {
-        if (z + r < zend && x < xend) {
-            const size_t o = so + (size_t)(z + r) * G.pitch + x;
-            v4[r] = __ldg(reinterpret_cast<const float4*>(G.v + G.padL + (size_t)(z + r) * G.pitch + x));
-            s0[r] = *reinterpret_cast<const float4*>(a.S02 + o);
-            r0[r] = *reinterpret_cast<const float4*>(a.R0 + o);
-        } else {
-            v4[r] = make_float4(G.vmin, G.vmin, G.vmin, G.vmin);
-            s0[r] = r0[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
+    if (x >= xend || z >= zend) return;
+    const int nrow = min(kNR, zend - z);
+    const bool compen = G.iCompen == 1;
+
+    size_t o = so + (size_t)z * G.pitch + x;
+    float4 vn  = __ldg(reinterpret_cast<const float4*>(G.v + G.padL + (size_t)z * G.pitch + x));
+    float4 s0n = *reinterpret_cast<const float4*>(a.S02 + o);
+    float4 r0n = *reinterpret_cast<const float4*>(a.R0 + o);
     mbar_wait(bar, 0);
 
-    float w1[kNR][4], p1[kNR][4];
-    float S2[kNR][4];
-    // source field: BKAdd_EFF / BKAdd_EFF_Con, double final sum, + wavelet at the source
-    stencil_block<RP, LS>(G, sS + (lz0 + RP) * Tile<RP>::SP + lx0 + RP, G.nfdmax, v4, w1, p1);
 #pragma unroll
     for (int r = 0; r < kNR; ++r) {
-        const float vq[4] = {v4[r].x, v4[r].y, v4[r].z, v4[r].w};
-        const float pq[4] = {s0[r].x, s0[r].y, s0[r].z, s0[r].w};
+        if (r >= nrow) break;
+        const int zz = z + r;
+        o = so + (size_t)zz * G.pitch + x;
+        float vq[4], s0[4], r0[4];
+        unpack(vn, vq);
+        unpack(s0n, s0);
+        unpack(r0n, r0);
+        // accumulators of this row and the next row's streams fly during the arithmetic
+        const float4 a1 = *reinterpret_cast<const float4*>(a.rel1 + o);
+        const float4 a2 = *reinterpret_cast<const float4*>(a.rel2 + o);
+        float4 aS = make_float4(0.f, 0.f, 0.f, 0.f), aR = aS;
+        if (compen) {
+            aS = *reinterpret_cast<const float4*>(a.sumS + o);
+            aR = *reinterpret_cast<const float4*>(a.sumR + o);
+        }
+        if (r + 1 < nrow) {
+            vn  = __ldg(reinterpret_cast<const float4*>(G.v + G.padL + (size_t)(zz + 1) * G.pitch + x));
+            s0n = *reinterpret_cast<const float4*>(a.S02 + o + G.pitch);
+            r0n = *reinterpret_cast<const float4*>(a.R0 + o + G.pitch);
+        }
+        float av[4], w1[4], p1[4], S2[4], R2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) av[q] = vel_factor(G, vq[q]);
+        // source field: BKAdd_EFF / BKAdd_EFF_Con, double final sum, + wavelet at the source
+        stencil_row<RP, LS>(G, sS + (lz0 + r + RP) * Tile<RP>::SP + lx0 + RP, G.nfdmax, vq, w1, p1);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            float o = finish_double(vel_factor(G, vq[q]), w1[r][q], p1[r][q], pq[q]);
-            if (z + r == src.x && x + q == src.y) o = __fadd_rn(o, a.wavelet);
-            S2[r][q] = o;
+            S2[q] = finish_double(av[q], w1[q], p1[q], s0[q]);
+            if (zz == src.x && x + q == src.y) S2[q] = __fadd_rn(S2[q], a.wavelet);
         }
-    }
-    // receiver field: BKAdd / BKAdd_Con, float final sum, data replacement
-    stencil_block<RP, LS>(G, sR + (lz0 + RP) * Tile<RP>::SP + lx0 + RP, G.nfdmax, v4, w1, p1);
-
+        // receiver field: BKAdd / BKAdd_Con, float final sum, data replacement
+        stencil_row<RP, LS>(G, sR + (lz0 + r + RP) * Tile<RP>::SP + lx0 + RP, G.nfdmax, vq, w1, p1);
 #pragma unroll
-    for (int r = 0; r < kNR; ++r) {
-        const int zz = z + r;
-        if (zz >= zend || x >= xend) continue;
-        const float vq[4] = {v4[r].x, v4[r].y, v4[r].z, v4[r].w};
-        const float pq[4] = {r0[r].x, r0[r].y, r0[r].z, r0[r].w};
-        float R2[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            R2[q] = finish_float(vel_factor(G, vq[q]), w1[r][q], p1[r][q], pq[q]);
+        for (int q = 0; q < 4; ++q) R2[q] = finish_float(av[q], w1[q], p1[q], r0[q]);
         if (zz == G.s_z) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -644,52 +651,34 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
                 }
             }
         }
-        const size_t o = so + (size_t)zz * G.pitch + x;
         // imaging (Rel_Compen :503-517 / Rel_NonCompen :489-501), S = source, R = receiver
-        float4 aS, aR, a1, a2;
-        a1 = *reinterpret_cast<const float4*>(a.rel1 + o);
-        a2 = *reinterpret_cast<const float4*>(a.rel2 + o);
-        float r1v[4] = {a1.x, a1.y, a1.z, a1.w}, r2v[4] = {a2.x, a2.y, a2.z, a2.w};
-        float sSv[4], sRv[4];
-        if (G.iCompen == 1) {
-            aS = *reinterpret_cast<const float4*>(a.sumS + o);
-            aR = *reinterpret_cast<const float4*>(a.sumR + o);
-            sSv[0] = aS.x; sSv[1] = aS.y; sSv[2] = aS.z; sSv[3] = aS.w;
-            sRv[0] = aR.x; sRv[1] = aR.y; sRv[2] = aR.z; sRv[3] = aR.w;
+        float r1v[4], r2v[4], sSv[4], sRv[4];
+        unpack(a1, r1v);
+        unpack(a2, r2v);
+        unpack(aS, sSv);
+        unpack(aR, sRv);
+        if (compen) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                sSv[q] = __fadd_rn(S2[r][q], sSv[q]);
+                sSv[q] = __fadd_rn(S2[q], sSv[q]);
                 sRv[q] = __fadd_rn(R2[q], sRv[q]);
                 r1v[q] = __fmaf_rn(sRv[q], sSv[q], r1v[q]);
-                r2v[q] = __fmaf_rn(S2[r][q], S2[r][q], r2v[q]);
+                r2v[q] = __fmaf_rn(S2[q], S2[q], r2v[q]);
             }
         } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                r1v[q] = __fmaf_rn(R2[q], S2[r][q], r1v[q]);
-                r2v[q] = __fmaf_rn(S2[r][q], S2[r][q], r2v[q]);
+                r1v[q] = __fmaf_rn(R2[q], S2[q], r1v[q]);
+                r2v[q] = __fmaf_rn(S2[q], S2[q], r2v[q]);
             }
         }
-        if (x + 3 < xend) {
-            *reinterpret_cast<float4*>(a.S02 + o) = make_float4(S2[r][0], S2[r][1], S2[r][2], S2[r][3]);
-            *reinterpret_cast<float4*>(a.R2 + o)  = make_float4(R2[0], R2[1], R2[2], R2[3]);
-            *reinterpret_cast<float4*>(a.rel1 + o) = make_float4(r1v[0], r1v[1], r1v[2], r1v[3]);
-            *reinterpret_cast<float4*>(a.rel2 + o) = make_float4(r2v[0], r2v[1], r2v[2], r2v[3]);
-            if (G.iCompen == 1) {
-                *reinterpret_cast<float4*>(a.sumS + o) = make_float4(sSv[0], sSv[1], sSv[2], sSv[3]);
-                *reinterpret_cast<float4*>(a.sumR + o) = make_float4(sRv[0], sRv[1], sRv[2], sRv[3]);
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (x + q < xend) {
-                    a.S02[o + q] = S2[r][q];
-                    a.R2[o + q]  = R2[q];
-                    a.rel1[o + q] = r1v[q];
-                    a.rel2[o + q] = r2v[q];
-                    if (G.iCompen == 1) { a.sumS[o + q] = sSv[q]; a.sumR[o + q] = sRv[q]; }
-                }
-            }
+        store4(a.S02 + o, S2, x, xend);
+        store4(a.R2 + o, R2, x, xend);
+        store4(a.rel1 + o, r1v, x, xend);
+        store4(a.rel2 + o, r2v, x, xend);
+        if (compen) {
+            store4(a.sumS + o, sSv, x, xend);
+            store4(a.sumR + o, sRv, x, xend);
         }
     }
 }
