@@ -148,6 +148,9 @@ int   rtm_ls_operator(int nthita, int nfdmax, int nfdmin, int nvel, float tao, f
 /* CAL2DFDCOE_LSM, LSMOrCon_rec_2D.cpp:236-287; c[M+1] doubles. */
 void  rtm_ls_coefficients(double *c, double r, double bmax, int M, double hzx);
 
+/* resample(), Resample.cpp:193-225: one trace from nxin samples at dxin to nxout at dxout. */
+void  rtm_resample(int nxin, float dxin, const float *yin, int nxout, float dxout, float *yout);
+
 /* Drop-in driver: everything main() does up to the stacked image (kernel.cu:525-1108),
  * reading the reference's input files and writing its output files.
  *   run_file  path of 2D_Real_RVSP_RTM.txt

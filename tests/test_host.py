@@ -128,3 +128,20 @@ def test_stack_finalize_matches_oracle():
         img, ill = R.stack_finalize(su, sd, 3, iNorm)
         oi, od = O.stack(ups, downs, iNorm)
         assert np.array_equal(img, oi) and np.array_equal(ill, od)
+
+
+def test_resample_matches_reference():
+    """8-point sinc resampling (Resample.cpp:193-225), bit-exact against the golden vector
+    produced by the reference's own function (tools/make_golden.py -> resample.npz) and, where
+    oracle/_ref is built, against the function itself."""
+    g = golden("resample")
+    for i in range(len(g["nxout"])):
+        out = R.resample(g["yin"], float(g["dxin"][i]), int(g["nxout"][i]), float(g["dxout"][i]))
+        assert np.array_equal(out, g[f"yout_{i}"]), i
+    if O.refhost() is not None:
+        rng = np.random.default_rng(3)
+        yin = rng.standard_normal(777).astype(np.float32)
+        for dxin, nxout, dxout in [(0.002, 1553, 0.001), (0.001, 300, 0.0025), (0.004, 2000, 0.0013)]:
+            want = np.zeros(nxout, np.float32)
+            O.refhost().ref_resample(len(yin), dxin, yin.ctypes.data_as(O.fp), nxout, dxout, want.ctypes.data_as(O.fp))
+            assert np.array_equal(R.resample(yin, dxin, nxout, dxout), want)

@@ -78,8 +78,29 @@ def build(case: Case, outpath: Path):
         shutil.rmtree(wd, ignore_errors=True)
 
 
+def build_resample(outpath: Path):
+    """resample() (Resample.cpp:193-225) on a damped sine, four rate changes."""
+    k = np.arange(400, dtype=np.float64)
+    yin = (np.sin(0.07 * k) * np.exp(-((k - 180) / 90.0) ** 2)).astype(np.float32)
+    cfg = [(0.002, 799, 0.001), (0.001, 160, 0.0025), (0.001, 400, 0.001), (0.004, 1201, 0.00133)]
+    res = {"yin": yin, "dxin": np.array([c[0] for c in cfg], np.float32),
+           "nxout": np.array([c[1] for c in cfg]), "dxout": np.array([c[2] for c in cfg], np.float32)}
+    for i, (dxin, nxout, dxout) in enumerate(cfg):
+        out = np.zeros(nxout, np.float32)
+        O.refhost().ref_resample(len(yin), dxin, yin.ctypes.data_as(O.fp), nxout, dxout,
+                                 out.ctypes.data_as(O.fp))
+        res[f"yout_{i}"] = out
+    np.savez_compressed(outpath, **res)
+    print(f"resample: wrote {outpath}")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["resample"]:
+        build_resample(ROOT / "tests" / "golden" / "resample.npz")
+        sys.exit(0)
     want = sys.argv[1:] or list(GOLDEN_CASES)
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     for name in want:
         build(GOLDEN_CASES[name], ROOT / "tests" / "golden" / f"{name}.npz")
+    if not sys.argv[1:]:
+        build_resample(ROOT / "tests" / "golden" / "resample.npz")
