@@ -14,7 +14,9 @@ from pathlib import Path
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "librtm_b200.so"
+import os
+
+LIB_PATH = Path(os.environ.get("RTM_LIB_PATH", PKG / "librtm_b200.so"))  # override: kernel-variant experiments
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int)

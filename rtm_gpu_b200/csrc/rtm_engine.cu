@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -53,6 +54,14 @@ int rtm_fail(int code, const char* fmt, ...)
 
 // ------------------------------------------------------------------------------------ aux kernels
 namespace {
+
+// a = ((v*v)*tao2)*h2 for every cell, with the kernels' own rounding (Taylor path reads it
+// instead of recomputing it every step)
+__global__ void avel_kernel(const float* v, float* a, Geo G, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = vel_factor(G, v[i]);
+}
 
 __global__ void init_source_kernel(float* F1, Geo G, const int2* src, float val)
 {
@@ -193,8 +202,9 @@ struct rtm_ctx {
     // device memory
     float* field[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float* acc[4]   = {nullptr, nullptr, nullptr, nullptr};
-    CUtensorMap tmap[5];
+    CUtensorMap tmap_f[5], tmap_b[5];  // halo boxes of the forward / backward tile shapes
     float* d_v = nullptr;
+    float* d_avel = nullptr;
     float* d_c = nullptr;
     int*   d_Index = nullptr;
     Strips st{nullptr, nullptr, nullptr, nullptr};
@@ -210,7 +220,7 @@ struct rtm_ctx {
     rtm_stats stats{};
 };
 
-static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base)
+static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int tile_rows)
 {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -228,7 +238,7 @@ static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base)
     const Geo& G = c->G;
     cuuint64_t dims[3]    = {(cuuint64_t)G.pitch, (cuuint64_t)G.NZ, (cuuint64_t)c->S};
     cuuint64_t strides[2] = {(cuuint64_t)G.pitch * 4, (cuuint64_t)G.shot_stride * 4};
-    cuuint32_t box[3]     = {(cuuint32_t)(kTX + 2 * c->RP), (cuuint32_t)(kTZ + 2 * c->RP), 1};
+    cuuint32_t box[3]     = {(cuuint32_t)(kTX + 2 * c->RP), (cuuint32_t)(tile_rows + 2 * c->RP), 1};
     cuuint32_t estr[3]    = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -252,7 +262,7 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     cudaSetDevice(c->device);
     for (auto& f : c->field) cudaFree(f);
     for (auto& f : c->acc) cudaFree(f);
-    cudaFree(c->d_v); cudaFree(c->d_c); cudaFree(c->d_Index);
+    cudaFree(c->d_v); cudaFree(c->d_avel); cudaFree(c->d_c); cudaFree(c->d_Index);
     cudaFree(c->st.up); cudaFree(c->st.dw); cudaFree(c->st.lf); cudaFree(c->st.rt);
     cudaFree(c->d_traces); cudaFree(c->d_stage); cudaFree(c->d_src);
     cudaFree(c->d_up); cudaFree(c->d_down); cudaFree(c->d_stack); cudaFree(c->d_stable);
@@ -311,8 +321,12 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     G.hzx2_1 = 1 / (hzx * hzx);
     G.A      = 1.0 + (double)G.hzx2_1;
     G.s_l = p->s_l; G.s_z = p->s_z; G.n = p->n; G.ds = p->ds; G.s_r = (p->n - 1) * p->ds + p->s_l;
-    G.ntx = (G.mod_NX + kTX - 1) / kTX; G.ntz = (G.mod_NZ + kTZ - 1) / kTZ;
+    G.ntx = (G.mod_NX + kTX - 1) / kTX;
+    G.ntz_f = (G.mod_NZ + kWarps * RTM_NR_F - 1) / (kWarps * RTM_NR_F);
+    G.ntz_b = (G.mod_NZ + kWarps * RTM_NR_B - 1) / (kWarps * RTM_NR_B);
     G.nband = (G.NX + kRingTX - 1) / kRingTX; G.nside = (G.mod_NZ + kRingTX - 1) / kRingTX;
+    G.lead = 0;  // L2 look-ahead prefetch: measured slower on B200 for this access mix (profiles/)
+    if (const char* e = std::getenv("RTM_PREFETCH_LEAD")) G.lead = std::atoi(e);
     for (int i = 0; i <= p->N2; ++i) G.w[i] = (float)((1.0 * i) / (1.0 * p->N2));  // :688-691
 
     auto fail = [&](int rc) { rtm_destroy(c); return rc; };
@@ -340,6 +354,8 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     for (auto& f : c->acc) { CKC(cudaMalloc(&f, c->field_floats * 4)); CKC(cudaMemset(f, 0, c->field_floats * 4)); }
     CKC(cudaMalloc(&c->d_v, ((size_t)G.shot_stride + 64) * 4));
     CKC(cudaMemset(c->d_v, 0, ((size_t)G.shot_stride + 64) * 4));
+    CKC(cudaMalloc(&c->d_avel, ((size_t)G.shot_stride + 64) * 4));
+    CKC(cudaMemset(c->d_avel, 0, ((size_t)G.shot_stride + 64) * 4));
     CKC(cudaMalloc(&c->d_traces, (size_t)c->S * G.NT * G.n * 4));
     CKC(cudaMalloc(&c->d_stage, (size_t)c->S * G.NT * G.n * 4));
     CKC(cudaMalloc(&c->d_src, sizeof(int2) * c->S));
@@ -350,10 +366,15 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     CKC(cudaMalloc(&c->d_stable, sizeof(float) * c->S));
     CKC(cudaMalloc(&c->d_maxbits, sizeof(int) * c->S));
     G.v = c->d_v;
+    G.avel = c->d_avel;
     for (int i = 0; i < 5; ++i) {
-        int rc = encode_tmap(c, &c->tmap[i], c->field[i]);
+        int rc = encode_tmap(c, &c->tmap_f[i], c->field[i], kWarps * RTM_NR_F);
+        if (!rc) rc = encode_tmap(c, &c->tmap_b[i], c->field[i], kWarps * RTM_NR_B);
         if (rc) return fail(rc);
     }
+    // The allocations above were cleared with legacy-stream memsets, which are asynchronous to
+    // the host and NOT ordered against the context's non-blocking stream: drain them here.
+    CKC(cudaDeviceSynchronize());
 #undef CKC
     *out = c;
     return RTM_OK;
@@ -365,9 +386,17 @@ extern "C" int rtm_set_model(rtm_ctx* c, const float* v, float vmin, float vmax,
     if (!(dv > 0)) return rtm_fail(RTM_ERR_ARG, "rtm_set_model: dv must be positive");
     CK(cudaSetDevice(c->device));
     Geo& G = c->G;
-    CK(cudaMemcpy2D(c->d_v + G.padL, (size_t)G.pitch * 4, v, (size_t)G.NX * 4, (size_t)G.NX * 4, G.NZ,
-                    cudaMemcpyHostToDevice));
+    // everything on the context's own (non-blocking) stream: a plain cudaMemcpy from pageable
+    // memory may return before the DMA lands and is not ordered against that stream
+    CK(cudaMemcpy2DAsync(c->d_v + G.padL, (size_t)G.pitch * 4, v, (size_t)G.NX * 4, (size_t)G.NX * 4, G.NZ,
+                         cudaMemcpyHostToDevice, c->stream));
     G.vmin = vmin; G.dv = dv; c->vmax = vmax;
+    {
+        const size_t n = (size_t)G.shot_stride;
+        avel_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_v, c->d_avel, G, n);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->stream));
+    }
     c->have_model = true;
     return RTM_OK;
 }
@@ -387,16 +416,23 @@ extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const fl
         c->d_c = nullptr; c->d_Index = nullptr;
         // one spare entry: the lookup reads Index[bin+1] and c[Index[bin]] for any cell
         CK(cudaMalloc(&c->d_c, sizeof(float) * (NC + 1)));
-        CK(cudaMemset(c->d_c, 0, sizeof(float) * (NC + 1)));
         CK(cudaMalloc(&c->d_Index, sizeof(int) * (nvel + 2)));
-        CK(cudaMemcpy(c->d_c, coef, sizeof(float) * NC, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(c->d_Index, Index, sizeof(int) * (nvel + 1), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(c->d_Index + nvel + 1, Index + nvel, sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemsetAsync(c->d_c, 0, sizeof(float) * (NC + 1), c->stream));
+        CK(cudaMemcpyAsync(c->d_c, coef, sizeof(float) * NC, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_Index, Index, sizeof(int) * (nvel + 1), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_Index + nvel + 1, Index + nvel, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
         G.c = c->d_c; G.Index = c->d_Index;
+        // (1+hzx2_1) a power of two (e.g. hz == h): A*c0 is exact in float for every bin
+        int ex = 0;
+        G.cc0_exact = (std::frexp(G.A, &ex) == 0.5 && (double)(float)G.A == G.A) ? 1 : 0;
+        G.cc0f = (float)G.A;
     } else {
         if (NC != G.nfdmax + 1) return rtm_fail(RTM_ERR_ARG, "rtm_set_operator: Taylor operator needs nfdmax+1=%d coefficients, got %d", G.nfdmax + 1, NC);
         for (int l = 0; l <= kMaxR; ++l) G.cTE[l] = l < NC ? coef[l] : 0.0f;
         G.cc0TE = G.A * (double)coef[0];
+        G.cc0f = (float)G.cc0TE;
+        G.cc0_exact = ((double)G.cc0f == G.cc0TE) ? 1 : 0;
     }
     c->have_op = true;
     return RTM_OK;
@@ -407,26 +443,26 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, int ns, int cur, co
 {
     const Geo& G = c->G;
     const int nring = 2 * G.nband + 2 * G.nside;
-    size_t smem = std::max((size_t)Tile<RP>::BYTES + 16, (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
+    size_t smem = std::max((size_t)Tile<RP, RTM_NR_F>::BYTES + 16, (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
     if (smem > c->smem_fwd) {  // per device, once
-        CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS, RTM_NR_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->smem_fwd = smem;
     }
-    dim3 grid(nring + G.ntx * G.ntz, ns);
-    fwd_step_kernel<RP, LS><<<grid, kThreads, smem, c->stream>>>(c->tmap[cur], G, a);
+    dim3 grid((unsigned)((nring + G.ntx * G.ntz_f) * ns));
+    fwd_step_kernel<RP, LS, RTM_NR_F><<<grid, kThreads, smem, c->stream>>>(c->tmap_f[cur], G, a);
     return RTM_OK;
 }
 template <int RP, bool LS> static int launch_bwd(rtm_ctx* c, int ns, int s1, int r1, const BwdArgs& a)
 {
     const Geo& G = c->G;
     const int nring = 2 * G.nband + 2 * G.nside;
-    size_t smem = std::max((size_t)2 * Tile<RP>::BYTES + 16, (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
+    size_t smem = std::max((size_t)2 * Tile<RP, RTM_NR_B>::BYTES + 16, (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
     if (smem > c->smem_bwd) {
-        CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->smem_bwd = smem;
     }
-    dim3 grid(nring + G.ntx * G.ntz, ns);
-    bwd_step_kernel<RP, LS><<<grid, kThreads, smem, c->stream>>>(c->tmap[s1], c->tmap[r1], G, a);
+    dim3 grid((unsigned)((nring + G.ntx * G.ntz_b) * ns));
+    bwd_step_kernel<RP, LS, RTM_NR_B><<<grid, kThreads, smem, c->stream>>>(c->tmap_b[s1], c->tmap_b[r1], G, a);
     return RTM_OK;
 }
 static int dispatch_fwd(rtm_ctx* c, int ns, int cur, const FwdArgs& a)
@@ -497,9 +533,10 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
             if (snap_k[i] != k) continue;
             CK(cudaStreamSynchronize(c->stream));
             for (int s = 0; s < ns; ++s)
-                CK(cudaMemcpy2D(snaps_host + ((size_t)s * nsnap + i) * G.NZ * G.NX, (size_t)G.NX * 4,
-                                c->field[buf] + (size_t)s * G.shot_stride + G.padL, (size_t)G.pitch * 4,
-                                (size_t)G.NX * 4, G.NZ, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy2DAsync(snaps_host + ((size_t)s * nsnap + i) * G.NZ * G.NX, (size_t)G.NX * 4,
+                                     c->field[buf] + (size_t)s * G.shot_stride + G.padL, (size_t)G.pitch * 4,
+                                     (size_t)G.NX * 4, G.NZ, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
         }
         return RTM_OK;
     };
@@ -513,7 +550,7 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
         a.P1 = c->field[i1]; a.P0 = c->field[i0]; a.P2 = c->field[i2];
         a.src = c->d_src;
         a.wavelet = (k < NT2) ? rtm::ricker((k - 1) * c->p.tao, c->p.f0) : 0.0f;  // :812-813
-        a.k = k; a.st = st; a.gather = gather;
+        a.k = k; a.nshots = ns; a.st = st; a.gather = gather;
         if (int rc = dispatch_fwd(c, ns, i1, a)) return rc;
         if (nsnap) if (int rc = snapshot(k, i2)) return rc;
         const int t = i0; i0 = i1; i1 = i2; i2 = t;
@@ -590,7 +627,7 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
         a.R1 = c->field[r1]; a.R0 = c->field[r0]; a.R2 = c->field[r2];
         a.src = c->d_src;
         a.wavelet = (k < NT2) ? rtm::ricker((k + 1) * c->p.tao, c->p.f0) : 0.0f;  // :889-890
-        a.k = k; a.st = c->st; a.seis = c->d_traces;
+        a.k = k; a.nshots = ns; a.st = c->st; a.seis = c->d_traces;
         a.sumS = c->acc[0]; a.sumR = c->acc[1]; a.rel1 = c->acc[2]; a.rel2 = c->acc[3];
         if (int rc = dispatch_bwd(c, ns, sy, r1, a)) return rc;
         std::swap(sx, sy);
@@ -675,7 +712,8 @@ extern "C" int rtm_stack_reset(rtm_ctx* c)
 {
     if (!c) return rtm_fail(RTM_ERR_ARG, "null context");
     CK(cudaSetDevice(c->device));
-    CK(cudaMemset(c->d_stack, 0, 2 * (size_t)c->G.mod_NX * c->G.mod_NZ * 4));
+    CK(cudaMemsetAsync(c->d_stack, 0, 2 * (size_t)c->G.mod_NX * c->G.mod_NZ * 4, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     c->stack_shots = 0;
     return RTM_OK;
 }
@@ -684,8 +722,9 @@ extern "C" int rtm_stack_get(rtm_ctx* c, float* up_sum, float* down_sum, int* ns
     if (!c) return rtm_fail(RTM_ERR_ARG, "null context");
     CK(cudaSetDevice(c->device));
     const size_t ncell = (size_t)c->G.mod_NX * c->G.mod_NZ;
-    if (up_sum) CK(cudaMemcpy(up_sum, c->d_stack, ncell * 4, cudaMemcpyDeviceToHost));
-    if (down_sum) CK(cudaMemcpy(down_sum, c->d_stack + ncell, ncell * 4, cudaMemcpyDeviceToHost));
+    if (up_sum) CK(cudaMemcpyAsync(up_sum, c->d_stack, ncell * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (down_sum) CK(cudaMemcpyAsync(down_sum, c->d_stack + ncell, ncell * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     if (nshots) *nshots = c->stack_shots;
     return RTM_OK;
 }

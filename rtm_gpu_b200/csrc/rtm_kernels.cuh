@@ -1,6 +1,6 @@
 // rtm_kernels.cuh -- sm_100a device code of the RTM time loop.
 //
-// One launch per time step.  A launch covers a batch of shots (blockIdx.y) and, per
+// One launch per time step.  A launch covers a batch of shots (1-D grid) and, per
 // shot, two kinds of CTA:
 //   * interior tiles (fast path): TMA-staged halo tile of the current wavefield in shared
 //     memory, each thread owns a 4 (x, one float4) by NR (z) register block, z neighbours
@@ -28,9 +28,15 @@ namespace rtmk {
 
 constexpr int kThreads = 256;  // 8 warps per CTA
 constexpr int kTX      = 128;  // interior tile width  (32 lanes x float4)
-constexpr int kNR      = 4;    // rows per thread
-constexpr int kTZ      = (kThreads / 32) * kNR;  // interior tile height = 32
-constexpr int kRingTX  = 64;   // ring tile extent along the band
+// rows per thread (tile height = 8 warps x rows); tuned per kernel on the B200 (profiles/)
+#ifndef RTM_NR_F
+#define RTM_NR_F 4
+#endif
+#ifndef RTM_NR_B
+#define RTM_NR_B 2
+#endif
+constexpr int kWarps   = kThreads / 32;
+constexpr int kRingTX  = 128;  // ring tile extent along the band
 constexpr int kMaxR    = 16;
 
 enum SumKind { SUM_FLOAT = 0, SUM_DOUBLE = 1 };
@@ -47,13 +53,17 @@ struct Geo {
     double A;                // 1.0 + (double)hzx2_1
     int   s_l, s_r, s_z, ds, n;
     // tiling
-    int   ntx, ntz;          // interior tiles
+    int   ntx, ntz_f, ntz_b; // interior tiles (forward / backward kernels use different tile heights)
     int   nband, nside;      // ring tiles per band (top/bottom) and per side (left/right)
+    int   lead;              // interior tiles of look-ahead for the L2 prefetch (0 = off)
     // operator
     const float* c;          // LS: packed table; TE: unused
     const int*   Index;
     float  cTE[kMaxR + 1];   // Taylor coefficients
     double cc0TE;            // (1+hzx2_1)*c[0] in double
+    float  cc0f;             // same as float when exactly representable (cc0_exact), else unused
+    int    cc0_exact;        // TE: cc0TE is a float; LS: 1+hzx2_1 is a power of two (A*c0 exact in float)
+    const float* avel;       // [NZ][pitch] a = ((v*v)*tao2)*h2, precomputed with the kernel's own rounding
     const float* v;          // [NZ][pitch], shared by all shots
     float  w[65];            // blend weights l/N2
 };
@@ -104,6 +114,18 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// L2 prefetch of data a later CTA will need (no SM resources are held while it is in flight)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, int z, int s)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"((uint64_t)map),
+                 "r"(x), "r"(z), "r"(s)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // ------------------------------------------------------------------ exact arithmetic
 // final sum of the two-way update, a = ((v*v)*tao2)*h2
 __device__ __forceinline__ float finish_float(float a, float w1, float p1, float p0)
@@ -130,6 +152,19 @@ __device__ __forceinline__ void ls_lookup(const Geo& G, float v, int& top, int& 
     M               = __ldg(G.Index + __double2int_rz(__dadd_rn(qd, 1.5))) - top - 1;
 }
 
+// first term of the stencil sum, w1 = (float)(((1.0+hzx2_1)*c0)*P1) evaluated in double by the
+// reference.  When (1+hzx2_1)*c0 is exactly a float the double product is exact, so a single
+// float multiply rounds identically (no conversions needed).
+__device__ __forceinline__ float w1_first_te(const Geo& G, float p1)
+{
+    return G.cc0_exact ? __fmul_rn(G.cc0f, p1) : __double2float_rn(__dmul_rn(G.cc0TE, (double)p1));
+}
+__device__ __forceinline__ float w1_first_ls(const Geo& G, float c0, float p1)
+{
+    return G.cc0_exact ? __fmul_rn(__fmul_rn(G.cc0f, c0), p1)   // cc0f = 1+hzx2_1 (a power of two)
+                       : __double2float_rn(__dmul_rn(__dmul_rn(G.A, (double)c0), (double)p1));
+}
+
 // ------------------------------------------------------------------ generic cell (ring path)
 // Two-way update of the cell whose current-field value is *sc in a shared tile of pitch SP.
 template <bool LS>
@@ -142,7 +177,7 @@ __device__ __forceinline__ float two_way_generic(const Geo& G, const float* sc, 
         int top, M;
         ls_lookup(G, vv, top, M);
         const float* cp = G.c + top;
-        w1 = __double2float_rn(__dmul_rn(__dmul_rn(G.A, (double)__ldg(cp)), (double)p1));
+        w1 = w1_first_ls(G, __ldg(cp), p1);
         for (int l = 1; l <= M; ++l) {
             const float s = __fadd_rn(sc[-l * SP], sc[l * SP]);
             const float t = __fmaf_rn(s, G.hzx2_1, sc[-l]);
@@ -150,7 +185,7 @@ __device__ __forceinline__ float two_way_generic(const Geo& G, const float* sc, 
             w1            = __fmaf_rn(__ldg(cp + l), u, w1);
         }
     } else {
-        w1 = __double2float_rn(__dmul_rn(G.cc0TE, (double)p1));
+        w1 = w1_first_te(G, p1);
         for (int l = 1; l <= G.nfdmax; ++l) {
             const float s = __fadd_rn(sc[-l * SP], sc[l * SP]);
             const float t = __fmaf_rn(s, G.hzx2_1, sc[-l]);
@@ -207,6 +242,18 @@ __host__ __device__ inline int ring_smem_floats(int N2, int R)
     return a + 2 * b;
 }
 
+// Visit the cells of an h x w rectangle with the CTA's 256 threads: row-per-warp when rows are
+// wide (band tiles, coalesced), flat indexing when they are narrow (side tiles, N2+2 columns).
+template <class F> __device__ __forceinline__ void for_cells(int h, int w, F f)
+{
+    if (w >= 32) {
+        for (int r = threadIdx.x >> 5; r < h; r += kWarps)
+            for (int c = threadIdx.x & 31; c < w; c += 32) f(r, c);
+    } else {
+        for (int i = threadIdx.x; i < h * w; i += kThreads) f(i / w, i % w);
+    }
+}
+
 template <bool LS, class Emit>
 __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* __restrict__ P1,
                                           const float* __restrict__ P0, int sum_kind,
@@ -226,20 +273,19 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
     float* s2 = s0 + ch * cw;                  // ch x cw   unblended two-way result
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < (ch + 2 * R) * SP; i += kThreads) {
-        int gz = cza - R + i / SP, gx = cxa - R + i % SP;
+    for_cells(ch + 2 * R, SP, [&](int r, int cidx) {
+        int gz = cza - R + r, gx = cxa - R + cidx;
         if (gz < 0) gz = -gz;                      // mirror about the array edge (:65-68)
         if (gz >= NZ) gz = 2 * NZ - 2 - gz;
         if (gx < 0) gx = -gx;
         if (gx >= NX) gx = 2 * NX - 2 - gx;
-        s1[i] = P1[(size_t)gz * pitch + gx];
-    }
-    for (int i = tid; i < ch * cw; i += kThreads)
-        s0[i] = P0[(size_t)(cza + i / cw) * pitch + cxa + i % cw];
+        s1[r * SP + cidx] = P1[(size_t)gz * pitch + gx];
+    });
+    for_cells(ch, cw, [&](int r, int cidx) { s0[r * cw + cidx] = P0[(size_t)(cza + r) * pitch + cxa + cidx]; });
     __syncthreads();
 
-    for (int i = tid; i < ch * cw; i += kThreads) {
-        const int lz = i / cw, lx = i % cw, z = cza + lz, x = cxa + lx;
+    for_cells(ch, cw, [&](int lz, int lx) {
+        const int z = cza + lz, x = cxa + lx, i = lz * cw + lx;
         float     val;
         int       j = seis_row ? data_index(G, z, x) : -1;
         float     d = (j >= 0) ? seis_row[j] : 0.0f;
@@ -251,12 +297,12 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
         }
         if (inject && z == r_u && x == r_x) val = __fadd_rn(val, wavelet);
         s2[i] = val;
-    }
+    });
     __syncthreads();
 
     const int oh = o.zb - o.za, ow = o.xb - o.xa;
-    for (int i = tid; i < oh * ow; i += kThreads) {
-        const int z = o.za + i / ow, x = o.xa + i % ow;
+    for_cells(oh, ow, [&](int oz, int ox) {
+        const int z = o.za + oz, x = o.xa + ox;
         const int lz = z - cza, lx = x - cxa;
         const int dz = min(z, NZ - 1 - z), dx = min(x, NX - 1 - x);
         const int a  = min(dz, dx);
@@ -311,7 +357,7 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
 #undef S0
 #undef S1
         emit(z, x, val);
-    }
+    });
 }
 
 }  // namespace rtmk
@@ -321,11 +367,12 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
 // =====================================================================================
 namespace rtmk {
 
-// Shared-memory tile of the current field for one interior tile: rows [z0-RP, z0+kTZ+RP),
+// Shared-memory tile of the current field for one interior tile: rows [z0-RP, z0+TZ+RP),
 // columns [x0-RP, x0+kTX+RP), dense, pitch kTX+2RP floats, written by one TMA box copy.
-template <int RP> struct Tile {
+template <int RP, int NR> struct Tile {
+    static constexpr int TZ    = kWarps * NR;
     static constexpr int SP    = kTX + 2 * RP;
-    static constexpr int ROWS  = kTZ + 2 * RP;
+    static constexpr int ROWS  = TZ + 2 * RP;
     static constexpr int BYTES = SP * ROWS * 4;
 };
 
@@ -344,7 +391,7 @@ template <int RP, bool LS>
 __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M, const float (&vq)[4],
                                             float (&w1)[4], float (&p1)[4])
 {
-    constexpr int SP = Tile<RP>::SP;
+    constexpr int SP = kTX + 2 * RP;
     float xr[4 + 2 * RP];  // columns x-RP .. x+3+RP of this row
 #pragma unroll
     for (int g = 0; g < (4 + 2 * RP) / 4; ++g) {
@@ -360,7 +407,7 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
         for (int q = 0; q < 4; ++q) {
             ls_lookup(G, vq[q], top[q], Mc[q]);
             Mx = max(Mx, Mc[q]);
-            w1[q] = __double2float_rn(__dmul_rn(__dmul_rn(G.A, (double)__ldg(G.c + top[q])), (double)p1[q]));
+            w1[q] = w1_first_ls(G, __ldg(G.c + top[q]), p1[q]);
         }
 #pragma unroll
         for (int l = 1; l <= RP; ++l) {
@@ -381,7 +428,7 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
         }
     } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) w1[q] = __double2float_rn(__dmul_rn(G.cc0TE, (double)p1[q]));
+        for (int q = 0; q < 4; ++q) w1[q] = w1_first_te(G, p1[q]);
 #pragma unroll
         for (int l = 1; l <= RP; ++l) {
             if (l <= M) {
@@ -422,28 +469,39 @@ struct FwdArgs {
     const int2*  src;  // per shot (r_u, r_x)
     float        wavelet;
     int          k;    // time slot being produced
+    int          nshots;
     Strips       st;   // may hold nulls when strips are not wanted (pure modelling)
     float*       gather;  // [S][NT][n] time-major, or null
 };
 
-template <int RP, bool LS>
-__global__ void __launch_bounds__(kThreads, (RP <= 4 ? 4 : (RP <= 8 ? 3 : 2)))
+#ifndef RTM_FWD_MINB
+#define RTM_FWD_MINB 4
+#endif
+#ifndef RTM_BWD_MINB
+#define RTM_BWD_MINB 3
+#endif
+template <int RP, bool LS, int NR>
+__global__ void __launch_bounds__(kThreads, (RP <= 4 ? RTM_FWD_MINB : (RP <= 8 ? 3 : 2)))
 fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ Geo G,
                 const FwdArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int  shot  = blockIdx.y;
-    const int  nring = 2 * G.nband + 2 * G.nside;
+    // 1-D grid: the ring tiles of ALL shots first (they are the longest-running CTAs and would
+    // otherwise form the tail of the launch), then the interior tiles shot by shot.
+    const int  nring = 2 * G.nband + 2 * G.nside, nint = G.ntx * G.ntz_f;
+    const bool is_ring = (int)blockIdx.x < a.nshots * nring;
+    const int  bi   = is_ring ? blockIdx.x : blockIdx.x - a.nshots * nring;
+    const int  shot = is_ring ? bi / nring : bi / nint;
     const long long so = (long long)shot * G.shot_stride + G.padL;  // (z=0,x=0) of this shot
     const int2 src = a.src[shot];
     const int  sum_kind = G.iLSTE == 0 ? SUM_FLOAT : SUM_DOUBLE;  // Add vs Add_Con
 
-    if ((int)blockIdx.x < nring) {
+    if (is_ring) {
         float* P2 = a.P2 + so;
         const int N2 = G.N2, nf = G.nfdmax, NZ = G.NZ, NX = G.NX, k = a.k;
         const Strips st = a.st;
         float* gather = a.gather;
-        ring_tile<LS>(G, blockIdx.x, a.P1 + so, a.P0 + so, sum_kind, true, src.x, src.y, a.wavelet,
+        ring_tile<LS>(G, bi % nring, a.P1 + so, a.P0 + so, sum_kind, true, src.x, src.y, a.wavelet,
                       nullptr, reinterpret_cast<float*>(smem_raw),
                       [&](int z, int x, float val) {
             P2[(size_t)z * G.pitch + x] = val;
@@ -467,33 +525,51 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
     }
 
     // ---- interior tile
-    const int t   = blockIdx.x - nring;
+    const int t   = bi % nint;
     const int tz  = t / G.ntx, tx = t % G.ntx;
-    const int z0  = G.N2 + tz * kTZ, x0 = G.N2 + tx * kTX;  // first interior cell of the tile
+    const int z0  = G.N2 + tz * (kWarps * NR), x0 = G.N2 + tx * kTX;  // first interior cell of the tile
     float*    sP  = reinterpret_cast<float*>(smem_raw);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Tile<RP>::BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Tile<RP, NR>::BYTES);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(bar, Tile<RP>::BYTES);
+        mbar_expect_tx(bar, Tile<RP, NR>::BYTES);
         tma_load_3d(sP, &tmP1, bar, G.padL + x0 - RP, z0 - RP, shot);
     }
-
-    const int lz0 = warp * kNR, lx0 = lane * 4;
-    const int z = z0 + lz0, x = x0 + lx0;
     const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
+    if (G.lead > 0) {
+        // Pull the inputs of the interior tile that runs `lead` tiles after this one into L2:
+        // its DRAM latency is then paid by nobody (the SM holds no registers or smem for it).
+        const int ntile = G.ntx * G.ntz_f;
+        const int L2i = shot * ntile + t + G.lead;
+        if (L2i < a.nshots * ntile) {
+            const int ps = L2i / ntile, pt = L2i % ntile;
+            const int pz0 = G.N2 + (pt / G.ntx) * (kWarps * NR), px0 = G.N2 + (pt % G.ntx) * kTX;
+            if (tid == 32) tma_prefetch_3d(&tmP1, G.padL + px0 - RP, pz0 - RP, ps);
+            if (tid >= 64 && tid < 64 + kWarps * NR && pz0 + tid - 64 < zend) {
+                const size_t po = (long long)ps * G.shot_stride + (size_t)(pz0 + tid - 64) * G.pitch + G.padL + px0;
+                const uint32_t bytes = 4u * (uint32_t)min(kTX, G.pitch - G.padL - px0);
+                bulk_prefetch_l2(a.P0 + po, bytes);
+            }
+        }
+    }
+
+    const int lz0 = warp * NR, lx0 = lane * 4;
+    const int z = z0 + lz0, x = x0 + lx0;
     if (x >= xend || z >= zend) return;  // (whole 4-cell groups; rows are warp-uniform)
-    const int nrow = min(kNR, zend - z);
+    const int nrow = min(NR, zend - z);
 
     // coalesced float4 loads of the other streams while the TMA copy is in flight
+    // Taylor operator: the velocity only enters through a = ((v*v)*tao2)*h2, read precomputed
+    const float* vsrc = (LS ? G.v : G.avel) + G.padL;
     float4 p0n = *reinterpret_cast<const float4*>(a.P0 + so + (size_t)z * G.pitch + x);
-    float4 vn  = __ldg(reinterpret_cast<const float4*>(G.v + G.padL + (size_t)z * G.pitch + x));
+    float4 vn  = __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)z * G.pitch + x));
     mbar_wait(bar, 0);
 
 #pragma unroll
-    for (int r = 0; r < kNR; ++r) {
+    for (int r = 0; r < NR; ++r) {
         if (r >= nrow) break;
         const int zz = z + r;
         float vq[4], pq[4];
@@ -501,16 +577,20 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
         unpack(p0n, pq);
         if (r + 1 < nrow) {  // next row's loads fly during this row's arithmetic
             p0n = *reinterpret_cast<const float4*>(a.P0 + so + (size_t)(zz + 1) * G.pitch + x);
-            vn  = __ldg(reinterpret_cast<const float4*>(G.v + G.padL + (size_t)(zz + 1) * G.pitch + x));
+            vn  = __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)(zz + 1) * G.pitch + x));
         }
         float w1[4], p1[4], o[4];
-        stencil_row<RP, LS>(G, sP + (lz0 + r + RP) * Tile<RP>::SP + lx0 + RP, G.nfdmax, vq, w1, p1);
+        stencil_row<RP, LS>(G, sP + (lz0 + r + RP) * Tile<RP, NR>::SP + lx0 + RP, G.nfdmax, vq, w1, p1);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float av = vel_factor(G, vq[q]);
-            o[q] = sum_kind == SUM_FLOAT ? finish_float(av, w1[q], p1[q], pq[q])
-                                         : finish_double(av, w1[q], p1[q], pq[q]);
-            if (zz == src.x && x + q == src.y) o[q] = __fadd_rn(o[q], a.wavelet);  // :74-77
+            const float av = LS ? vel_factor(G, vq[q]) : vq[q];
+            o[q] = LS ? finish_float(av, w1[q], p1[q], pq[q])     // Add
+                      : finish_double(av, w1[q], p1[q], pq[q]);   // Add_Con
+        }
+        if (zz == src.x) {  // :74-77 (warp-uniform test first)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (x + q == src.y) o[q] = __fadd_rn(o[q], a.wavelet);
         }
         store4(a.P2 + so + (size_t)zz * G.pitch + x, o, x, xend);
         if (a.gather && zz == G.s_z) {
@@ -536,29 +616,32 @@ struct BwdArgs {
     const int2*  src;
     float        wavelet;
     int          k;
+    int          nshots;
     Strips       st;
     const float* seis;  // [S][NT][n] time-major; row k+1 is imposed
     float *sumS, *sumR, *rel1, *rel2;  // accumulators, field layout
 };
 
-template <int RP, bool LS>
-__global__ void __launch_bounds__(kThreads, (RP <= 4 ? 3 : 2))
+template <int RP, bool LS, int NR>
+__global__ void __launch_bounds__(kThreads, (RP <= 4 ? RTM_BWD_MINB : 2))
 bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmR1,
                 const __grid_constant__ Geo G, const BwdArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int  shot  = blockIdx.y;
-    const int  nring = 2 * G.nband + 2 * G.nside;
+    const int  nring = 2 * G.nband + 2 * G.nside, nint = G.ntx * G.ntz_b;
+    const bool is_ring = (int)blockIdx.x < a.nshots * nring;
+    const int  bi   = is_ring ? blockIdx.x : blockIdx.x - a.nshots * nring;
+    const int  shot = is_ring ? bi / nring : bi / nint;
     const long long so = (long long)shot * G.shot_stride + G.padL;
     const int2 src = a.src[shot];
     const float* seis_row = a.seis + ((size_t)shot * G.NT + (a.k + 1)) * G.n;
 
-    if ((int)blockIdx.x < nring) {
+    if (is_ring) {
         float* R2 = a.R2 + so;
         float* SX = a.S02 + so;
         const int N2 = G.N2, nf = G.nfdmax, NZ = G.NZ, NX = G.NX, k = a.k;
         const Strips st = a.st;
-        ring_tile<LS>(G, blockIdx.x, a.R1 + so, a.R0 + so, SUM_FLOAT, false, 0, 0, 0.0f, seis_row,
+        ring_tile<LS>(G, bi % nring, a.R1 + so, a.R0 + so, SUM_FLOAT, false, 0, 0, 0.0f, seis_row,
                       reinterpret_cast<float*>(smem_raw), [&](int z, int x, float val) {
             R2[(size_t)z * G.pitch + x] = val;
             // BKEqual :222-245, one step early: the ring of the buffer that becomes the
@@ -576,37 +659,56 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
         return;
     }
 
-    const int t   = blockIdx.x - nring;
+    const int t   = bi % nint;
     const int tz  = t / G.ntx, tx = t % G.ntx;
-    const int z0  = G.N2 + tz * kTZ, x0 = G.N2 + tx * kTX;
+    const int z0  = G.N2 + tz * (kWarps * NR), x0 = G.N2 + tx * kTX;
     float*    sS  = reinterpret_cast<float*>(smem_raw);
-    float*    sR  = reinterpret_cast<float*>(smem_raw + Tile<RP>::BYTES);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * Tile<RP>::BYTES);
+    float*    sR  = reinterpret_cast<float*>(smem_raw + Tile<RP, NR>::BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * Tile<RP, NR>::BYTES);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(bar, 2 * Tile<RP>::BYTES);
+        mbar_expect_tx(bar, 2 * Tile<RP, NR>::BYTES);
         tma_load_3d(sS, &tmS1, bar, G.padL + x0 - RP, z0 - RP, shot);
         tma_load_3d(sR, &tmR1, bar, G.padL + x0 - RP, z0 - RP, shot);
     }
-
-    const int lz0 = warp * kNR, lx0 = lane * 4;
-    const int z = z0 + lz0, x = x0 + lx0;
     const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
+    if (G.lead > 0) {  // L2 prefetch for the interior tile `lead` tiles ahead (see fwd_step_kernel)
+        const int ntile = G.ntx * G.ntz_b;
+        const int L2i = shot * ntile + t + G.lead;
+        if (L2i < a.nshots * ntile) {
+            const int ps = L2i / ntile, pt = L2i % ntile;
+            const int pz0 = G.N2 + (pt / G.ntx) * (kWarps * NR), px0 = G.N2 + (pt % G.ntx) * kTX;
+            if (tid == 0) tma_prefetch_3d(&tmS1, G.padL + px0 - RP, pz0 - RP, ps);
+            if (tid == 1) tma_prefetch_3d(&tmR1, G.padL + px0 - RP, pz0 - RP, ps);
+            const int row = tid & 31, stream = tid >> 5;  // 8 warps: 6 plain streams (+2 idle)
+            if (row < kWarps * NR && pz0 + row < zend && stream < (G.iCompen == 1 ? 6 : 4)) {
+                const size_t po = (long long)ps * G.shot_stride + (size_t)(pz0 + row) * G.pitch + G.padL + px0;
+                const uint32_t bytes = 4u * (uint32_t)min(kTX, G.pitch - G.padL - px0);
+                const float* base = stream == 0 ? a.S02 : stream == 1 ? a.R0 : stream == 2 ? a.rel1
+                                  : stream == 3 ? a.rel2 : stream == 4 ? a.sumS : a.sumR;
+                bulk_prefetch_l2(base + po, bytes);
+            }
+        }
+    }
+
+    const int lz0 = warp * NR, lx0 = lane * 4;
+    const int z = z0 + lz0, x = x0 + lx0;
     if (x >= xend || z >= zend) return;
-    const int nrow = min(kNR, zend - z);
+    const int nrow = min(NR, zend - z);
     const bool compen = G.iCompen == 1;
 
+    const float* vsrc = (LS ? G.v : G.avel) + G.padL;
     size_t o = so + (size_t)z * G.pitch + x;
-    float4 vn  = __ldg(reinterpret_cast<const float4*>(G.v + G.padL + (size_t)z * G.pitch + x));
+    float4 vn  = __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)z * G.pitch + x));
     float4 s0n = *reinterpret_cast<const float4*>(a.S02 + o);
     float4 r0n = *reinterpret_cast<const float4*>(a.R0 + o);
     mbar_wait(bar, 0);
 
 #pragma unroll
-    for (int r = 0; r < kNR; ++r) {
+    for (int r = 0; r < NR; ++r) {
         if (r >= nrow) break;
         const int zz = z + r;
         o = so + (size_t)zz * G.pitch + x;
@@ -623,22 +725,24 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
             aR = *reinterpret_cast<const float4*>(a.sumR + o);
         }
         if (r + 1 < nrow) {
-            vn  = __ldg(reinterpret_cast<const float4*>(G.v + G.padL + (size_t)(zz + 1) * G.pitch + x));
+            vn  = __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)(zz + 1) * G.pitch + x));
             s0n = *reinterpret_cast<const float4*>(a.S02 + o + G.pitch);
             r0n = *reinterpret_cast<const float4*>(a.R0 + o + G.pitch);
         }
         float av[4], w1[4], p1[4], S2[4], R2[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) av[q] = vel_factor(G, vq[q]);
+        for (int q = 0; q < 4; ++q) av[q] = LS ? vel_factor(G, vq[q]) : vq[q];
         // source field: BKAdd_EFF / BKAdd_EFF_Con, double final sum, + wavelet at the source
-        stencil_row<RP, LS>(G, sS + (lz0 + r + RP) * Tile<RP>::SP + lx0 + RP, G.nfdmax, vq, w1, p1);
+        stencil_row<RP, LS>(G, sS + (lz0 + r + RP) * Tile<RP, NR>::SP + lx0 + RP, G.nfdmax, vq, w1, p1);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            S2[q] = finish_double(av[q], w1[q], p1[q], s0[q]);
-            if (zz == src.x && x + q == src.y) S2[q] = __fadd_rn(S2[q], a.wavelet);
+        for (int q = 0; q < 4; ++q) S2[q] = finish_double(av[q], w1[q], p1[q], s0[q]);
+        if (zz == src.x) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (x + q == src.y) S2[q] = __fadd_rn(S2[q], a.wavelet);
         }
         // receiver field: BKAdd / BKAdd_Con, float final sum, data replacement
-        stencil_row<RP, LS>(G, sR + (lz0 + r + RP) * Tile<RP>::SP + lx0 + RP, G.nfdmax, vq, w1, p1);
+        stencil_row<RP, LS>(G, sR + (lz0 + r + RP) * Tile<RP, NR>::SP + lx0 + RP, G.nfdmax, vq, w1, p1);
 #pragma unroll
         for (int q = 0; q < 4; ++q) R2[q] = finish_float(av[q], w1[q], p1[q], r0[q]);
         if (zz == G.s_z) {

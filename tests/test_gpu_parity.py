@@ -100,6 +100,11 @@ def test_batching_does_not_change_results():
         u1, d1, s1 = e1.migrate(r_u, r_x, seis)
     with make_engine(case, v, vmin, vmax, Index, c, max_batch=4) as e4:
         u4, d4, s4 = e4.migrate(r_u, r_x, seis)
+    p = O.make_params(case, vmin, vmax, contract=1)
+    for m in range(4):
+        ou, od, *_ = O.migrate_shot(p, v, c, Index, r_u[m], r_x[m], seis[m])
+        assert np.array_equal(u1[m], ou), f"batch=1 shot {m} differs from the oracle ({rel_l2(u1[m], ou):.2e})"
+        assert np.array_equal(u4[m], ou), f"batch=4 shot {m} differs from the oracle ({rel_l2(u4[m], ou):.2e})"
     assert np.array_equal(u1, u4) and np.array_equal(d1, d4) and np.array_equal(s1, s4)
 
 
@@ -119,3 +124,21 @@ def test_argument_errors():
     import dataclasses
     with pytest.raises(R.RtmError, match="nfdmax"):
         R.engine_for_case(dataclasses.replace(case, nfdmax=12, N2=10))
+
+
+def test_fresh_contexts_are_deterministic():
+    """Regression: set-up copies/memsets must be ordered against the context's non-blocking
+    stream (a plain cudaMemcpy/cudaMemset is not).  Re-creating contexts back to back used to
+    let the first kernels race with the still-pending model upload."""
+    import dataclasses
+    case = dataclasses.replace(GOLDEN_CASES["tiny_te_compen"], NT1=60)
+    v, vmin, vmax, Index, c = prepare(case)
+    r_u, r_x = [24, 34, 40], [20, 31, 64]
+    seis = np.stack([data_tiny(case, 100 * i)[:, :60] for i in range(3)])
+    first = None
+    for it in range(12):
+        with make_engine(case, v, vmin, vmax, Index, c, max_batch=1 + it % 3) as e:
+            u, d, s = e.migrate(r_u, r_x, seis)
+        if first is None:
+            first = (u, d, s)
+        assert np.array_equal(u, first[0]) and np.array_equal(d, first[1]) and np.array_equal(s, first[2]), it
