@@ -104,6 +104,8 @@ int rtm_stack_reset(rtm_ctx *ctx);
 int rtm_stack_get(rtm_ctx *ctx, float *up_sum, float *down_sum, int *nshots);
 int rtm_stack_device(rtm_ctx *ctx, void **dev_ptr, size_t *nfloats, int *nshots);
 int rtm_stack_reduce(rtm_ctx **ctxs, int nctx, float *up_sum, float *down_sum, int *nshots);
+/* "nccl", "p2p" (NVLink peer copies + device add, used when libnccl cannot be loaded) or "none" */
+const char *rtm_stack_reduce_backend(void);
 /* sum/nrec, optional up/down normalisation (kernel.cu:1042-1059); in/out [mod_NX][mod_NZ] */
 int rtm_stack_finalize(const float *up_sum, const float *down_sum, int nrec, int iNorm,
                        size_t ncell, float *image, float *illum);

@@ -47,7 +47,7 @@ class Stats(C.Structure):
 ABI_SYMBOLS = [
     "rtm_last_error", "rtm_version", "rtm_create", "rtm_destroy", "rtm_set_model", "rtm_set_operator",
     "rtm_forward", "rtm_migrate", "rtm_upload_gathers", "rtm_migrate_resident", "rtm_stack_reset",
-    "rtm_stack_get", "rtm_stack_device", "rtm_stack_reduce", "rtm_stack_finalize", "rtm_get_stats",
+    "rtm_stack_get", "rtm_stack_device", "rtm_stack_reduce", "rtm_stack_reduce_backend", "rtm_stack_finalize", "rtm_get_stats",
     "rtm_reset_stats", "rtm_device_count", "rtm_ricker", "rtm_source_row", "rtm_derived",
     "rtm_pad_velocity", "rtm_velocity_bins", "rtm_taylor_operator", "rtm_ls_operator",
     "rtm_ls_coefficients", "rtm_resample", "rtm_run_driver",
@@ -80,6 +80,7 @@ def lib():
     L.rtm_stack_get.argtypes = [C.c_void_p, _fp, _fp, _ip]
     L.rtm_stack_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _ip]
     L.rtm_stack_reduce.argtypes = [C.POINTER(C.c_void_p), C.c_int, _fp, _fp, _ip]
+    L.rtm_stack_reduce_backend.restype = C.c_char_p
     L.rtm_stack_finalize.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_size_t, _fp, _fp]
     L.rtm_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.rtm_reset_stats.argtypes = [C.c_void_p]
@@ -275,6 +276,17 @@ class Engine:
 
     def reset_stats(self):
         _check(lib().rtm_reset_stats(self._h))
+
+
+def stack_reduce(engines):
+    """One reduce of the stacks of engines living in this process (one per GPU)."""
+    p = engines[0].params
+    up = np.zeros((p.mod_NX, p.mod_NZ), np.float32)
+    down = np.zeros_like(up)
+    ns = C.c_int()
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    _check(lib().rtm_stack_reduce(arr, len(engines), _f(up), _f(down), C.byref(ns)))
+    return up, down, ns.value, lib().rtm_stack_reduce_backend().decode()
 
 
 def stack_finalize(up_sum, down_sum, nrec, iNorm):

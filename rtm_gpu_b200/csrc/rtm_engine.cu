@@ -762,4 +762,31 @@ extern "C" int rtm_reset_stats(rtm_ctx* c)
     return RTM_OK;
 }
 
-// NCCL reduce of the per-GPU stacks for contexts living in one process: rtm_nccl.cpp
+// NCCL reduce of the per-GPU stacks for contexts living in one process: rtm_nccl.cpp.
+// Fallback used when NCCL cannot be loaded: peer copies over NVLink into the first context's
+// GPU and a device-side add, in context order.
+namespace {
+__global__ void add_into_kernel(float* dst, const float* src, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __fadd_rn(dst[i], src[i]);
+}
+}  // namespace
+
+int rtm_stack_reduce_p2p(rtm_ctx** ctxs, int nctx)
+{
+    rtm_ctx* root = ctxs[0];
+    const size_t n = 2 * (size_t)root->G.mod_NX * root->G.mod_NZ;
+    CK(cudaSetDevice(root->device));
+    float* tmp = nullptr;
+    CK(cudaMalloc(&tmp, n * 4));
+    for (int i = 1; i < nctx; ++i) {
+        if (2 * (size_t)ctxs[i]->G.mod_NX * ctxs[i]->G.mod_NZ != n) { cudaFree(tmp); return rtm_fail(RTM_ERR_ARG, "rtm_stack_reduce: contexts differ in image size"); }
+        CK(cudaMemcpyPeerAsync(tmp, root->device, ctxs[i]->d_stack, ctxs[i]->device, n * 4, root->stream));
+        add_into_kernel<<<(unsigned)((n + 255) / 256), 256, 0, root->stream>>>(root->d_stack, tmp, n);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(root->stream));
+    CK(cudaFree(tmp));
+    return RTM_OK;
+}

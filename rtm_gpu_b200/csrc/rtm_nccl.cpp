@@ -56,15 +56,15 @@ Nccl* load_nccl(std::string& why)
 }  // namespace
 
 extern "C" int rtm_ctx_device(rtm_ctx* ctx);
+int rtm_stack_reduce_p2p(rtm_ctx** ctxs, int nctx);  // rtm_engine.cu
+static const char* g_backend = "none";
+extern "C" const char* rtm_stack_reduce_backend(void) { return g_backend; }
 
 extern "C" int rtm_stack_reduce(rtm_ctx** ctxs, int nctx, float* up_sum, float* down_sum, int* nshots)
 {
     if (!ctxs || nctx < 1) return rtm_fail(RTM_ERR_ARG, "rtm_stack_reduce: no contexts");
     int total = 0;
     if (nctx == 1) return rtm_stack_get(ctxs[0], up_sum, down_sum, nshots);
-    std::string why;
-    Nccl* n = load_nccl(why);
-    if (!n) return rtm_fail(RTM_ERR_NCCL, "rtm_stack_reduce: %s", why.c_str());
     std::vector<int> devs(nctx);
     std::vector<void*> buf(nctx);
     size_t nfl = 0;
@@ -74,6 +74,17 @@ extern "C" int rtm_stack_reduce(rtm_ctx** ctxs, int nctx, float* up_sum, float* 
         if (int rc = rtm_stack_device(ctxs[i], &buf[i], &nfl, &ns)) return rc;
         total += ns;
     }
+    std::string why;
+    const char* force = std::getenv("RTM_REDUCE");
+    Nccl* n = (force && std::string(force) == "p2p") ? nullptr : load_nccl(why);
+    if (!n) {
+        // NCCL not loadable (stand-alone executable without the library on its path): the same
+        // sum over NVLink peer copies, gathered and added on the first context's GPU.
+        if (force && std::string(force) == "nccl") return rtm_fail(RTM_ERR_NCCL, "rtm_stack_reduce: %s", why.c_str());
+        int rc = rtm_stack_reduce_p2p(ctxs, nctx);
+        if (rc) return rc;
+        g_backend = "p2p";
+    } else {
     std::vector<ncclComm_t> comms(nctx);
     ncclResult_t r = n->CommInitAll(comms.data(), nctx, devs.data());
     if (r) return rtm_fail(RTM_ERR_NCCL, "ncclCommInitAll: %s", n->GetErrorString(r));
@@ -91,6 +102,8 @@ extern "C" int rtm_stack_reduce(rtm_ctx** ctxs, int nctx, float* up_sum, float* 
     }
     for (auto c : comms) n->CommDestroy(c);
     if (r) return rtm_fail(RTM_ERR_NCCL, "ncclReduce: %s", n->GetErrorString(r));
+    g_backend = "nccl";
+    }
     cudaSetDevice(devs[0]);
     const size_t ncell = nfl / 2;
     if (up_sum && cudaMemcpy(up_sum, buf[0], ncell * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
