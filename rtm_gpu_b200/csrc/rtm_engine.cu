@@ -63,6 +63,43 @@ __global__ void avel_kernel(const float* v, float* a, Geo G, size_t n)
     if (i < n) a[i] = vel_factor(G, v[i]);
 }
 
+// velocity bin of every cell, (int)((v-vmin)/dv+0.5) exactly as the reference's kernels compute it
+// (kernel.cu:55-56), stored once per model as a 2-byte side array
+__global__ void bins_kernel(const float* v, unsigned short* bins, Geo G, size_t n, int nvel)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % G.pitch) - G.padL;
+    int b = 0;
+    if (x >= 0 && x < G.NX) {
+        const float q = __fdiv_rn(__fsub_rn(v[i], G.vmin), G.dv);
+        b = __double2int_rz(__dadd_rn((double)q, 0.5));
+        b = min(max(b, 0), nvel - 1);
+    }
+    bins[i] = (unsigned short)b;
+}
+
+// (min bin, max bin) over the interior cells of every interior tile of height tile_rows
+__global__ void tile_bins_kernel(const unsigned short* bins, Geo G, int tile_rows, int ntx, int2* out)
+{
+    __shared__ int smin, smax;
+    if (threadIdx.x == 0) { smin = 0x7fffffff; smax = 0; }
+    __syncthreads();
+    const int t = blockIdx.x, z0 = G.N2 + (t / ntx) * tile_rows, x0 = G.N2 + (t % ntx) * kTX;
+    int lo = 0x7fffffff, hi = 0;
+    for (int i = threadIdx.x; i < tile_rows * kTX; i += blockDim.x) {
+        const int z = z0 + i / kTX, x = x0 + i % kTX;
+        if (z < G.NZ - G.N2 && x < G.NX - G.N2) {
+            const int b = bins[(size_t)z * G.pitch + G.padL + x];
+            lo = min(lo, b); hi = max(hi, b);
+        }
+    }
+    atomicMin(&smin, lo);
+    atomicMax(&smax, hi);
+    __syncthreads();
+    if (threadIdx.x == 0) out[t] = make_int2(min(smin, smax), smax);
+}
+
 __global__ void init_source_kernel(float* F1, Geo G, const int2* src, float val)
 {
     const int s = blockIdx.x;
@@ -205,6 +242,9 @@ struct rtm_ctx {
     CUtensorMap tmap_f[5], tmap_b[5];  // halo boxes of the forward / backward tile shapes
     float* d_v = nullptr;
     float* d_avel = nullptr;
+    unsigned short* d_bins = nullptr;
+    int2 *d_tile_bins_f = nullptr, *d_tile_bins_b = nullptr;
+    int    nvel = 0;
     float* d_c = nullptr;
     int*   d_Index = nullptr;
     Strips st{nullptr, nullptr, nullptr, nullptr};
@@ -262,7 +302,7 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     cudaSetDevice(c->device);
     for (auto& f : c->field) cudaFree(f);
     for (auto& f : c->acc) cudaFree(f);
-    cudaFree(c->d_v); cudaFree(c->d_avel); cudaFree(c->d_c); cudaFree(c->d_Index);
+    cudaFree(c->d_v); cudaFree(c->d_avel); cudaFree(c->d_bins); cudaFree(c->d_tile_bins_f); cudaFree(c->d_tile_bins_b); cudaFree(c->d_c); cudaFree(c->d_Index);
     cudaFree(c->st.up); cudaFree(c->st.dw); cudaFree(c->st.lf); cudaFree(c->st.rt);
     cudaFree(c->d_traces); cudaFree(c->d_stage); cudaFree(c->d_src);
     cudaFree(c->d_up); cudaFree(c->d_down); cudaFree(c->d_stack); cudaFree(c->d_stable);
@@ -367,6 +407,12 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     CKC(cudaMalloc(&c->d_maxbits, sizeof(int) * c->S));
     G.v = c->d_v;
     G.avel = c->d_avel;
+    CKC(cudaMalloc(&c->d_bins, ((size_t)G.shot_stride + 64) * sizeof(unsigned short)));
+    CKC(cudaMemset(c->d_bins, 0, ((size_t)G.shot_stride + 64) * sizeof(unsigned short)));
+    CKC(cudaMalloc(&c->d_tile_bins_f, sizeof(int2) * G.ntx * G.ntz_f));
+    CKC(cudaMalloc(&c->d_tile_bins_b, sizeof(int2) * G.ntx * G.ntz_b));
+    G.bins = c->d_bins; G.tile_bins_f = c->d_tile_bins_f; G.tile_bins_b = c->d_tile_bins_b;
+    G.slice_cap = 6144;  // 24 KB of shared memory per CTA for the tile's slice of Index/c
     for (int i = 0; i < 5; ++i) {
         int rc = encode_tmap(c, &c->tmap_f[i], c->field[i], kWarps * RTM_NR_F);
         if (!rc) rc = encode_tmap(c, &c->tmap_b[i], c->field[i], kWarps * RTM_NR_B);
@@ -377,6 +423,22 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     CKC(cudaDeviceSynchronize());
 #undef CKC
     *out = c;
+    return RTM_OK;
+}
+
+// Side arrays of the adaptive operator (need both the model and the operator table).
+static int prepare_ls(rtm_ctx* c)
+{
+    if (c->G.iLSTE != 0 || !c->have_model || !c->have_op) return RTM_OK;
+    const Geo& G = c->G;
+    if (c->nvel > 65535)
+        return rtm_fail(RTM_ERR_ARG, "adaptive operator with %d velocity bins: the per-cell bin array is 16-bit, use a larger dv", c->nvel);
+    const size_t n = (size_t)G.shot_stride;
+    bins_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_v, c->d_bins, G, n, c->nvel);
+    tile_bins_kernel<<<G.ntx * G.ntz_f, 256, 0, c->stream>>>(c->d_bins, G, kWarps * RTM_NR_F, G.ntx, c->d_tile_bins_f);
+    tile_bins_kernel<<<G.ntx * G.ntz_b, 256, 0, c->stream>>>(c->d_bins, G, kWarps * RTM_NR_B, G.ntx, c->d_tile_bins_b);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
     return RTM_OK;
 }
 
@@ -398,7 +460,7 @@ extern "C" int rtm_set_model(rtm_ctx* c, const float* v, float vmin, float vmax,
         CK(cudaStreamSynchronize(c->stream));
     }
     c->have_model = true;
-    return RTM_OK;
+    return prepare_ls(c);
 }
 
 extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const float* coef, int NC)
@@ -435,7 +497,8 @@ extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const fl
         G.cc0_exact = ((double)G.cc0f == G.cc0TE) ? 1 : 0;
     }
     c->have_op = true;
-    return RTM_OK;
+    c->nvel = nvel;
+    return prepare_ls(c);
 }
 
 // ------------------------------------------------------------------------------------ launches
@@ -443,7 +506,7 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, int ns, int cur, co
 {
     const Geo& G = c->G;
     const int nring = 2 * G.nband + 2 * G.nside;
-    size_t smem = std::max((size_t)Tile<RP, RTM_NR_F>::BYTES + 16, (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
+    size_t smem = std::max((size_t)Tile<RP, RTM_NR_F>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
     if (smem > c->smem_fwd) {  // per device, once
         CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS, RTM_NR_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->smem_fwd = smem;
@@ -456,7 +519,7 @@ template <int RP, bool LS> static int launch_bwd(rtm_ctx* c, int ns, int s1, int
 {
     const Geo& G = c->G;
     const int nring = 2 * G.nband + 2 * G.nside;
-    size_t smem = std::max((size_t)2 * Tile<RP, RTM_NR_B>::BYTES + 16, (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
+    size_t smem = std::max((size_t)2 * Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
     if (smem > c->smem_bwd) {
         CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->smem_bwd = smem;

@@ -64,6 +64,13 @@ struct Geo {
     float  cc0f;             // same as float when exactly representable (cc0_exact), else unused
     int    cc0_exact;        // TE: cc0TE is a float; LS: 1+hzx2_1 is a power of two (A*c0 exact in float)
     const float* avel;       // [NZ][pitch] a = ((v*v)*tao2)*h2, precomputed with the kernel's own rounding
+    // adaptive operator, interior fast path: per-cell velocity bin (2 B/cell side array, replaces
+    // the per-step IEEE division + double add + two dependent Index loads) and per-tile bin
+    // ranges so that a tile can stage its slice of Index/c in shared memory
+    const unsigned short* bins;   // [NZ][pitch]
+    const int2* tile_bins_f;      // [ntz_f*ntx] (min bin, max bin) of each forward interior tile
+    const int2* tile_bins_b;      // [ntz_b*ntx]
+    int    slice_cap;             // words of shared memory available for the Index/c slice
     const float* v;          // [NZ][pitch], shared by all shots
     float  w[65];            // blend weights l/N2
 };
@@ -387,9 +394,48 @@ __device__ __forceinline__ void unpack(const float4& a, float (&o)[4])
 // keeps the register footprint small enough for 3-4 resident CTAs per SM.
 // M <= RP is the uniform length of the Taylor operator; the adaptive operator brings a length
 // and table offset per cell.
+// Operator-table access of the adaptive path for one interior tile: `ip[bin]` is the packed
+// offset of a bin, `cp[offset]` a coefficient.  Both point either at the tile's slice staged in
+// shared memory (biased so that global bin numbers / offsets index them directly) or at the
+// global tables when the slice does not fit.
+struct LsTable {
+    const int*   ip;
+    const float* cp;
+    int bmin, bmax;
+};
+
+// Stage Index[bmin..bmax+1] and c[Index[bmin]..Index[bmax+1]) of this tile into shared memory.
+// Called by all threads of the CTA; the caller synchronises afterwards.
+__device__ __forceinline__ LsTable ls_stage_slice(const Geo& G, int2 tb, int* smem_words)
+{
+    LsTable T;
+    T.bmin = tb.x; T.bmax = tb.y;
+    const int nI = tb.y - tb.x + 2;
+    const int cBeg = __ldg(G.Index + tb.x), cEnd = __ldg(G.Index + tb.y + 1);
+    const int nC = cEnd - cBeg;
+    if (nI + nC <= G.slice_cap) {
+        int*   sI = smem_words;
+        float* sC = reinterpret_cast<float*>(smem_words + nI);
+        for (int i = threadIdx.x; i < nI; i += kThreads) sI[i] = __ldg(G.Index + tb.x + i);
+        for (int i = threadIdx.x; i < nC; i += kThreads) sC[i] = __ldg(G.c + cBeg + i);
+        T.ip = sI - tb.x;
+        T.cp = sC - cBeg;
+    } else {
+        T.ip = G.Index;
+        T.cp = G.c;
+    }
+    return T;
+}
+
+// Stencil sums w1 of four x-adjacent cells of one row.  `sc` points at the first of the four
+// cells inside the shared tile.  x neighbours: the row segment [x-RP, x+3+RP] as float4 shared
+// loads; z neighbours: one float4 shared load per row offset (all four cells share it), which
+// keeps the register footprint small enough for 3-4 resident CTAs per SM.
+// M <= RP is the uniform length of the Taylor operator; the adaptive operator brings a length
+// and table offset per cell (from the cell's velocity bin).
 template <int RP, bool LS>
-__device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M, const float (&vq)[4],
-                                            float (&w1)[4], float (&p1)[4])
+__device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M, const LsTable& T,
+                                            uint2 bins4, float (&w1)[4], float (&p1)[4])
 {
     constexpr int SP = kTX + 2 * RP;
     float xr[4 + 2 * RP];  // columns x-RP .. x+3+RP of this row
@@ -402,12 +448,17 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
     for (int q = 0; q < 4; ++q) p1[q] = xr[RP + q];
 
     if (LS) {
-        int top[4], Mc[4], Mx = 0;
+        const int b4[4] = {(int)(bins4.x & 0xffffu), (int)(bins4.x >> 16), (int)(bins4.y & 0xffffu), (int)(bins4.y >> 16)};
+        const float* cq[4];
+        int Mc[4], Mx = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            ls_lookup(G, vq[q], top[q], Mc[q]);
-            Mx = max(Mx, Mc[q]);
-            w1[q] = w1_first_ls(G, __ldg(G.c + top[q]), p1[q]);
+            const int b   = min(max(b4[q], T.bmin), T.bmax);  // (cells of a partial group past the interior)
+            const int top = T.ip[b];
+            Mc[q] = T.ip[b + 1] - top - 1;
+            cq[q] = T.cp + top;
+            Mx    = max(Mx, Mc[q]);
+            w1[q] = w1_first_ls(G, cq[q][0], p1[q]);
         }
 #pragma unroll
         for (int l = 1; l <= RP; ++l) {
@@ -421,7 +472,7 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
                         const float s = __fadd_rn(zm[q], zp[q]);
                         const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
                         const float u = __fadd_rn(t, xr[RP + q + l]);
-                        w1[q]         = __fmaf_rn(__ldg(G.c + top[q] + l), u, w1[q]);
+                        w1[q]         = __fmaf_rn(cq[q][l], u, w1[q]);
                     }
                 }
             }
@@ -480,8 +531,14 @@ struct FwdArgs {
 #ifndef RTM_BWD_MINB
 #define RTM_BWD_MINB 3
 #endif
+#ifndef RTM_FWD_MINB_LS
+#define RTM_FWD_MINB_LS 3
+#endif
+#ifndef RTM_BWD_MINB_LS
+#define RTM_BWD_MINB_LS 2
+#endif
 template <int RP, bool LS, int NR>
-__global__ void __launch_bounds__(kThreads, (RP <= 4 ? RTM_FWD_MINB : (RP <= 8 ? 3 : 2)))
+__global__ void __launch_bounds__(kThreads, (RP <= 4 ? (LS ? RTM_FWD_MINB_LS : RTM_FWD_MINB) : (RP <= 8 ? 3 : 2)))
 fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ Geo G,
                 const FwdArgs a)
 {
@@ -556,16 +613,25 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
         }
     }
 
+    LsTable T{};
+    if (LS) {  // this tile's slice of the operator table -> shared memory (behind the halo tile)
+        T = ls_stage_slice(G, G.tile_bins_f[t], reinterpret_cast<int*>(smem_raw + Tile<RP, NR>::BYTES + 16));
+        __syncthreads();
+    }
     const int lz0 = warp * NR, lx0 = lane * 4;
     const int z = z0 + lz0, x = x0 + lx0;
     if (x >= xend || z >= zend) return;  // (whole 4-cell groups; rows are warp-uniform)
     const int nrow = min(NR, zend - z);
 
-    // coalesced float4 loads of the other streams while the TMA copy is in flight
-    // Taylor operator: the velocity only enters through a = ((v*v)*tao2)*h2, read precomputed
-    const float* vsrc = (LS ? G.v : G.avel) + G.padL;
+    // coalesced float4 loads of the other streams while the TMA copy is in flight.
+    // The velocity only enters through a = ((v*v)*tao2)*h2 (read precomputed) and, for the
+    // adaptive operator, through the cell's bin (2-byte side array).
+    const float* vsrc = G.avel + G.padL;
+    const unsigned short* bsrc = G.bins + G.padL;
     float4 p0n = *reinterpret_cast<const float4*>(a.P0 + so + (size_t)z * G.pitch + x);
     float4 vn  = __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)z * G.pitch + x));
+    uint2  bn  = make_uint2(0u, 0u);
+    if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bsrc + (size_t)z * G.pitch + x));
     mbar_wait(bar, 0);
 
 #pragma unroll
@@ -575,17 +641,18 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
         float vq[4], pq[4];
         unpack(vn, vq);
         unpack(p0n, pq);
+        const uint2 bc = bn;
         if (r + 1 < nrow) {  // next row's loads fly during this row's arithmetic
             p0n = *reinterpret_cast<const float4*>(a.P0 + so + (size_t)(zz + 1) * G.pitch + x);
             vn  = __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)(zz + 1) * G.pitch + x));
+            if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bsrc + (size_t)(zz + 1) * G.pitch + x));
         }
         float w1[4], p1[4], o[4];
-        stencil_row<RP, LS>(G, sP + (lz0 + r + RP) * Tile<RP, NR>::SP + lx0 + RP, G.nfdmax, vq, w1, p1);
+        stencil_row<RP, LS>(G, sP + (lz0 + r + RP) * Tile<RP, NR>::SP + lx0 + RP, G.nfdmax, T, bc, w1, p1);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float av = LS ? vel_factor(G, vq[q]) : vq[q];
-            o[q] = LS ? finish_float(av, w1[q], p1[q], pq[q])     // Add
-                      : finish_double(av, w1[q], p1[q], pq[q]);   // Add_Con
+            o[q] = LS ? finish_float(vq[q], w1[q], p1[q], pq[q])     // Add
+                      : finish_double(vq[q], w1[q], p1[q], pq[q]);   // Add_Con
         }
         if (zz == src.x) {  // :74-77 (warp-uniform test first)
 #pragma unroll
@@ -623,7 +690,7 @@ struct BwdArgs {
 };
 
 template <int RP, bool LS, int NR>
-__global__ void __launch_bounds__(kThreads, (RP <= 4 ? RTM_BWD_MINB : 2))
+__global__ void __launch_bounds__(kThreads, (RP <= 4 ? (LS ? RTM_BWD_MINB_LS : RTM_BWD_MINB) : 2))
 bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmR1,
                 const __grid_constant__ Geo G, const BwdArgs a)
 {
@@ -694,15 +761,23 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
         }
     }
 
+    LsTable T{};
+    if (LS) {
+        T = ls_stage_slice(G, G.tile_bins_b[t], reinterpret_cast<int*>(smem_raw + 2 * Tile<RP, NR>::BYTES + 16));
+        __syncthreads();
+    }
     const int lz0 = warp * NR, lx0 = lane * 4;
     const int z = z0 + lz0, x = x0 + lx0;
     if (x >= xend || z >= zend) return;
     const int nrow = min(NR, zend - z);
     const bool compen = G.iCompen == 1;
 
-    const float* vsrc = (LS ? G.v : G.avel) + G.padL;
+    const float* vsrc = G.avel + G.padL;
+    const unsigned short* bsrc = G.bins + G.padL;
     size_t o = so + (size_t)z * G.pitch + x;
     float4 vn  = __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)z * G.pitch + x));
+    uint2  bn  = make_uint2(0u, 0u);
+    if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bsrc + (size_t)z * G.pitch + x));
     float4 s0n = *reinterpret_cast<const float4*>(a.S02 + o);
     float4 r0n = *reinterpret_cast<const float4*>(a.R0 + o);
     mbar_wait(bar, 0);
@@ -724,16 +799,18 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
             aS = *reinterpret_cast<const float4*>(a.sumS + o);
             aR = *reinterpret_cast<const float4*>(a.sumR + o);
         }
+        const uint2 bc = bn;
         if (r + 1 < nrow) {
             vn  = __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)(zz + 1) * G.pitch + x));
+            if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bsrc + (size_t)(zz + 1) * G.pitch + x));
             s0n = *reinterpret_cast<const float4*>(a.S02 + o + G.pitch);
             r0n = *reinterpret_cast<const float4*>(a.R0 + o + G.pitch);
         }
         float av[4], w1[4], p1[4], S2[4], R2[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) av[q] = LS ? vel_factor(G, vq[q]) : vq[q];
+        for (int q = 0; q < 4; ++q) av[q] = vq[q];
         // source field: BKAdd_EFF / BKAdd_EFF_Con, double final sum, + wavelet at the source
-        stencil_row<RP, LS>(G, sS + (lz0 + r + RP) * Tile<RP, NR>::SP + lx0 + RP, G.nfdmax, vq, w1, p1);
+        stencil_row<RP, LS>(G, sS + (lz0 + r + RP) * Tile<RP, NR>::SP + lx0 + RP, G.nfdmax, T, bc, w1, p1);
 #pragma unroll
         for (int q = 0; q < 4; ++q) S2[q] = finish_double(av[q], w1[q], p1[q], s0[q]);
         if (zz == src.x) {
@@ -742,7 +819,7 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
                 if (x + q == src.y) S2[q] = __fadd_rn(S2[q], a.wavelet);
         }
         // receiver field: BKAdd / BKAdd_Con, float final sum, data replacement
-        stencil_row<RP, LS>(G, sR + (lz0 + r + RP) * Tile<RP, NR>::SP + lx0 + RP, G.nfdmax, vq, w1, p1);
+        stencil_row<RP, LS>(G, sR + (lz0 + r + RP) * Tile<RP, NR>::SP + lx0 + RP, G.nfdmax, T, bc, w1, p1);
 #pragma unroll
         for (int q = 0; q < 4; ++q) R2[q] = finish_float(av[q], w1[q], p1[q], r0[q]);
         if (zz == G.s_z) {
