@@ -480,20 +480,25 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
     } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) w1[q] = w1_first_te(G, p1[q]);
+        auto term = [&](int l) {
+            float zm[4], zp[4];
+            unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
+            unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
 #pragma unroll
-        for (int l = 1; l <= RP; ++l) {
-            if (l <= M) {
-                float zm[4], zp[4];
-                unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
-                unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float s = __fadd_rn(zm[q], zp[q]);
-                    const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
-                    const float u = __fadd_rn(t, xr[RP + q + l]);
-                    w1[q]         = __fmaf_rn(G.cTE[l], u, w1[q]);
-                }
+            for (int q = 0; q < 4; ++q) {
+                const float s = __fadd_rn(zm[q], zp[q]);
+                const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
+                const float u = __fadd_rn(t, xr[RP + q + l]);
+                w1[q]         = __fmaf_rn(G.cTE[l], u, w1[q]);
             }
+        };
+        if (M == RP) {  // common case (radius 4, 8, 12, 16): straight-line code
+#pragma unroll
+            for (int l = 1; l <= RP; ++l) term(l);
+        } else {
+#pragma unroll
+            for (int l = 1; l <= RP; ++l)
+                if (l <= M) term(l);
         }
     }
 }
@@ -626,47 +631,60 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
     // coalesced float4 loads of the other streams while the TMA copy is in flight.
     // The velocity only enters through a = ((v*v)*tao2)*h2 (read precomputed) and, for the
     // adaptive operator, through the cell's bin (2-byte side array).
-    const float* vsrc = G.avel + G.padL;
-    const unsigned short* bsrc = G.bins + G.padL;
-    float4 p0n = *reinterpret_cast<const float4*>(a.P0 + so + (size_t)z * G.pitch + x);
-    float4 vn  = __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)z * G.pitch + x));
+    const size_t cell0 = (size_t)z * G.pitch + x;  // row pointers advance by `pitch` per row
+    const float* p0p = a.P0 + so + cell0;
+    float*       p2p = a.P2 + so + cell0;
+    const float* vp  = G.avel + G.padL + cell0;
+    const unsigned short* bp = G.bins + G.padL + cell0;
+    const float* sp  = sP + (lz0 + RP) * Tile<RP, NR>::SP + lx0 + RP;
+    const bool full  = x + 3 < xend;
+    const int  src_r = (src.y >= x && src.y < x + 4) ? src.x - z : -1;  // row of this thread holding the source
+    const int  gat_r = a.gather ? G.s_z - z : -1;
+    float4 p0n = *reinterpret_cast<const float4*>(p0p);
+    float4 vn  = __ldg(reinterpret_cast<const float4*>(vp));
     uint2  bn  = make_uint2(0u, 0u);
-    if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bsrc + (size_t)z * G.pitch + x));
+    if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bp));
     mbar_wait(bar, 0);
 
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         if (r >= nrow) break;
-        const int zz = z + r;
         float vq[4], pq[4];
         unpack(vn, vq);
         unpack(p0n, pq);
         const uint2 bc = bn;
         if (r + 1 < nrow) {  // next row's loads fly during this row's arithmetic
-            p0n = *reinterpret_cast<const float4*>(a.P0 + so + (size_t)(zz + 1) * G.pitch + x);
-            vn  = __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)(zz + 1) * G.pitch + x));
-            if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bsrc + (size_t)(zz + 1) * G.pitch + x));
+            p0n = *reinterpret_cast<const float4*>(p0p + G.pitch);
+            vn  = __ldg(reinterpret_cast<const float4*>(vp + G.pitch));
+            if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bp + G.pitch));
         }
         float w1[4], p1[4], o[4];
-        stencil_row<RP, LS>(G, sP + (lz0 + r + RP) * Tile<RP, NR>::SP + lx0 + RP, G.nfdmax, T, bc, w1, p1);
+        stencil_row<RP, LS>(G, sp, G.nfdmax, T, bc, w1, p1);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             o[q] = LS ? finish_float(vq[q], w1[q], p1[q], pq[q])     // Add
                       : finish_double(vq[q], w1[q], p1[q], pq[q]);   // Add_Con
         }
-        if (zz == src.x) {  // :74-77 (warp-uniform test first)
+        if (r == src_r) {  // :74-77
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 if (x + q == src.y) o[q] = __fadd_rn(o[q], a.wavelet);
         }
-        store4(a.P2 + so + (size_t)zz * G.pitch + x, o, x, xend);
-        if (a.gather && zz == G.s_z) {
+        if (full) {
+            *reinterpret_cast<float4*>(p2p) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (x + q < xend) p2p[q] = o[q];
+        }
+        if (r == gat_r) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int j = (x + q < xend) ? data_index(G, zz, x + q) : -1;
+                const int j = (x + q < xend) ? data_index(G, z + r, x + q) : -1;
                 if (j >= 0) a.gather[((size_t)shot * G.NT + a.k) * G.n + j] = o[q];
             }
         }
+        p0p += G.pitch; p2p += G.pitch; vp += G.pitch; bp += G.pitch; sp += Tile<RP, NR>::SP;
     }
 }
 
@@ -772,23 +790,36 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
     const int nrow = min(NR, zend - z);
     const bool compen = G.iCompen == 1;
 
-    const float* vsrc = G.avel + G.padL;
-    const unsigned short* bsrc = G.bins + G.padL;
-    size_t o = so + (size_t)z * G.pitch + x;
-    float4 vn  = __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)z * G.pitch + x));
+    size_t o = so + (size_t)z * G.pitch + x;  // advances by `pitch` per row
+    const float* vp = G.avel + G.padL + (size_t)z * G.pitch + x;
+    const unsigned short* bp = G.bins + G.padL + (size_t)z * G.pitch + x;
+    const float* spS = sS + (lz0 + RP) * Tile<RP, NR>::SP + lx0 + RP;
+    const float* spR = sR + (lz0 + RP) * Tile<RP, NR>::SP + lx0 + RP;
+    const bool full  = x + 3 < xend;
+    const int  src_r = (src.y >= x && src.y < x + 4) ? src.x - z : -1;
+    const int  dat_r = G.s_z - z;  // row of this thread on the data line (if in 0..NR-1)
+    float4 vn  = __ldg(reinterpret_cast<const float4*>(vp));
     uint2  bn  = make_uint2(0u, 0u);
-    if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bsrc + (size_t)z * G.pitch + x));
+    if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bp));
     float4 s0n = *reinterpret_cast<const float4*>(a.S02 + o);
     float4 r0n = *reinterpret_cast<const float4*>(a.R0 + o);
     mbar_wait(bar, 0);
 
+    auto put = [&](float* base, const float (&val)[4]) {
+        if (full) {
+            *reinterpret_cast<float4*>(base + o) = make_float4(val[0], val[1], val[2], val[3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (x + q < xend) base[o + q] = val[q];
+        }
+    };
+
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         if (r >= nrow) break;
-        const int zz = z + r;
-        o = so + (size_t)zz * G.pitch + x;
-        float vq[4], s0[4], r0[4];
-        unpack(vn, vq);
+        float av[4], s0[4], r0[4];
+        unpack(vn, av);
         unpack(s0n, s0);
         unpack(r0n, r0);
         // accumulators of this row and the next row's streams fly during the arithmetic
@@ -801,31 +832,29 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
         }
         const uint2 bc = bn;
         if (r + 1 < nrow) {
-            vn  = __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)(zz + 1) * G.pitch + x));
-            if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bsrc + (size_t)(zz + 1) * G.pitch + x));
+            vn  = __ldg(reinterpret_cast<const float4*>(vp + G.pitch));
+            if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bp + G.pitch));
             s0n = *reinterpret_cast<const float4*>(a.S02 + o + G.pitch);
             r0n = *reinterpret_cast<const float4*>(a.R0 + o + G.pitch);
         }
-        float av[4], w1[4], p1[4], S2[4], R2[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) av[q] = vq[q];
+        float w1[4], p1[4], S2[4], R2[4];
         // source field: BKAdd_EFF / BKAdd_EFF_Con, double final sum, + wavelet at the source
-        stencil_row<RP, LS>(G, sS + (lz0 + r + RP) * Tile<RP, NR>::SP + lx0 + RP, G.nfdmax, T, bc, w1, p1);
+        stencil_row<RP, LS>(G, spS, G.nfdmax, T, bc, w1, p1);
 #pragma unroll
         for (int q = 0; q < 4; ++q) S2[q] = finish_double(av[q], w1[q], p1[q], s0[q]);
-        if (zz == src.x) {
+        if (r == src_r) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 if (x + q == src.y) S2[q] = __fadd_rn(S2[q], a.wavelet);
         }
         // receiver field: BKAdd / BKAdd_Con, float final sum, data replacement
-        stencil_row<RP, LS>(G, sR + (lz0 + r + RP) * Tile<RP, NR>::SP + lx0 + RP, G.nfdmax, T, bc, w1, p1);
+        stencil_row<RP, LS>(G, spR, G.nfdmax, T, bc, w1, p1);
 #pragma unroll
         for (int q = 0; q < 4; ++q) R2[q] = finish_float(av[q], w1[q], p1[q], r0[q]);
-        if (zz == G.s_z) {
+        if (r == dat_r) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int j = (x + q < xend) ? data_index(G, zz, x + q) : -1;
+                const int j = (x + q < xend) ? data_index(G, z + r, x + q) : -1;
                 if (j >= 0) {
                     const float d = seis_row[j];
                     if (d != 0.0f) R2[q] = d;
@@ -853,14 +882,15 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
                 r2v[q] = __fmaf_rn(S2[q], S2[q], r2v[q]);
             }
         }
-        store4(a.S02 + o, S2, x, xend);
-        store4(a.R2 + o, R2, x, xend);
-        store4(a.rel1 + o, r1v, x, xend);
-        store4(a.rel2 + o, r2v, x, xend);
+        put(a.S02, S2);
+        put(a.R2, R2);
+        put(a.rel1, r1v);
+        put(a.rel2, r2v);
         if (compen) {
-            store4(a.sumS + o, sSv, x, xend);
-            store4(a.sumR + o, sRv, x, xend);
+            put(a.sumS, sSv);
+            put(a.sumR, sRv);
         }
+        o += G.pitch; vp += G.pitch; bp += G.pitch; spS += Tile<RP, NR>::SP; spR += Tile<RP, NR>::SP;
     }
 }
 
