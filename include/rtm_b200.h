@@ -57,6 +57,12 @@ typedef struct {
 } rtm_params;
 
 #define RTM_FLAG_NONE 0
+/* Keep the whole forward wavefield in HBM ([NT][batch][NZ][pitch] floats) when it fits, and
+ * image with it instead of reconstructing the source field backwards in time; falls back to
+ * boundary saving + reconstruction (the reference's scheme, the default) when it does not fit.
+ * NOT a reference mode: images differ from the reference's at the level of its reconstruction
+ * error (~1e-4 relative).  rtm_store_all_active() tells which was chosen. */
+#define RTM_FLAG_STORE_ALL 1
 
 /* Replaces cudaSetDevice + the 22 cudaMalloc calls (kernel.cu:527, 758-779). */
 int  rtm_create(int device, const rtm_params *params, rtm_ctx **out);
@@ -122,6 +128,7 @@ typedef struct {
 int rtm_get_stats(rtm_ctx *ctx, rtm_stats *out);
 int rtm_reset_stats(rtm_ctx *ctx);
 int rtm_device_count(void);
+int rtm_store_all_active(rtm_ctx *ctx); /* 1 if RTM_FLAG_STORE_ALL was requested and fits */
 
 /* ------------------------------------------------------------------ host-side pieces
  * (pure CPU; the reference's main() does these before/after the device loop) */

@@ -395,6 +395,17 @@ void oracle_migrate_shot(const oracle_params *p, const float *v, const float *c,
                          const int *Index, int r_u, int r_x, const float *seis, float *up,
                          float *down, float *rel1_out, float *rel2_out, float *stable_out)
 {
+    oracle_migrate_shot_ex(p, v, c, Index, r_u, r_x, seis, up, down, rel1_out, rel2_out, stable_out, 0);
+}
+
+/* store_all != 0: NOT a reference mode.  The source field used by the imaging condition is the
+ * stored forward field of slot k instead of its reverse-time reconstruction (the engine's
+ * RTM_FLAG_STORE_ALL); everything else is unchanged. */
+void oracle_migrate_shot_ex(const oracle_params *p, const float *v, const float *c,
+                            const int *Index, int r_u, int r_x, const float *seis, float *up,
+                            float *down, float *rel1_out, float *rel2_out, float *stable_out,
+                            int store_all)
+{
     octx g;
     octx_init(&g, p, v, c, Index);
     const int    NZ = g.NZ, NX = g.NX, N2 = g.N2, NT = p->NT, ct = g.contract;
@@ -405,7 +416,14 @@ void oracle_migrate_shot(const oracle_params *p, const float *v, const float *c,
 
     oracle_strips *st = oracle_strips_alloc(p);
     float *A = (float *)malloc(n * sizeof(float)), *B = (float *)malloc(n * sizeof(float));
-    forward_impl(p, &g, r_u, r_x, 0, A, B, st, 0, 0, 0); /* B = slot NT-1, A = slot NT-2 */
+    float **stored = 0;
+    int    *stored_k = 0;
+    if (store_all) {
+        stored   = (float **)malloc(sizeof(float *) * NT);
+        stored_k = (int *)malloc(sizeof(int) * NT);
+        for (int k = 0; k < NT; k++) { stored[k] = (float *)malloc(n * sizeof(float)); stored_k[k] = k; }
+    }
+    forward_impl(p, &g, r_u, r_x, 0, A, B, st, store_all ? NT : 0, stored_k, stored); /* B = slot NT-1, A = slot NT-2 */
 
     /* hand-off :822-825: BW0 = slot NT-1, BW1 = slot NT-2 (current) */
     float *S0 = B, *S1 = A, *S2 = (float *)calloc(n, sizeof(float));
@@ -440,7 +458,7 @@ void oracle_migrate_shot(const oracle_params *p, const float *v, const float *c,
             for (int x = N2; x < NX - N2; x++) {
                 float val = two_way(&g, S1, S0, z, x, SUM_DOUBLE);
                 if (z == r_u && x == r_x) val += wavelet;
-                S2[(size_t)z * NX + x] = val;
+                S2[(size_t)z * NX + x] = store_all ? stored[k][(size_t)z * NX + x] : val;
             }
         for (int z = N2; z < NZ - N2; z++) /* Deliver_EFF: interior only */
             for (int x = N2; x < NX - N2; x++) {
@@ -505,6 +523,7 @@ void oracle_migrate_shot(const oracle_params *p, const float *v, const float *c,
             if (rel2_out) rel2_out[(size_t)(i - N2) * mx + (j - N2)] = rel2[(size_t)i * NX + j];
         }
 
+    if (stored) { for (int k = 0; k < NT; k++) free(stored[k]); free(stored); free(stored_k); }
     free(A); free(B); free(S2); free(R0); free(R1); free(R2); free(scr);
     free(sumS); free(sumR); free(rel1); free(rel2);
     oracle_strips_free(st);

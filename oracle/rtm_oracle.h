@@ -85,6 +85,12 @@ void oracle_migrate_shot(const oracle_params *p, const float *v, const float *c,
                          const int *Index, int r_u, int r_x, const float *seis,
                          float *up, float *down, float *rel1, float *rel2, float *stable);
 
+/* Same with store_all != 0: the engine's non-reference RTM_FLAG_STORE_ALL mode (imaging uses the
+ * stored forward field instead of its reconstruction). */
+void oracle_migrate_shot_ex(const oracle_params *p, const float *v, const float *c,
+                            const int *Index, int r_u, int r_x, const float *seis, float *up,
+                            float *down, float *rel1, float *rel2, float *stable, int store_all);
+
 /* Stack over shots, kernel.cu:992-1059.  ups/downs: nshot images [mod_NX][mod_NZ];
  * out: [mod_NX][mod_NZ];  returns stacked up (optionally / stacked down if iNorm). */
 void oracle_stack(const float *const *ups, const float *const *downs, int nshot,

@@ -16,6 +16,7 @@ import numpy as np
 PKG = Path(__file__).resolve().parent
 import os
 
+STORE_ALL = 1  # RTM_FLAG_STORE_ALL
 LIB_PATH = Path(os.environ.get("RTM_LIB_PATH", PKG / "librtm_b200.so"))  # override: kernel-variant experiments
 
 _fp = C.POINTER(C.c_float)
@@ -48,7 +49,7 @@ ABI_SYMBOLS = [
     "rtm_last_error", "rtm_version", "rtm_create", "rtm_destroy", "rtm_set_model", "rtm_set_operator",
     "rtm_forward", "rtm_migrate", "rtm_upload_gathers", "rtm_migrate_resident", "rtm_stack_reset",
     "rtm_stack_get", "rtm_stack_device", "rtm_stack_reduce", "rtm_stack_reduce_backend", "rtm_stack_finalize", "rtm_get_stats",
-    "rtm_reset_stats", "rtm_device_count", "rtm_ricker", "rtm_source_row", "rtm_derived",
+    "rtm_reset_stats", "rtm_device_count", "rtm_store_all_active", "rtm_ricker", "rtm_source_row", "rtm_derived",
     "rtm_pad_velocity", "rtm_velocity_bins", "rtm_taylor_operator", "rtm_ls_operator",
     "rtm_ls_coefficients", "rtm_resample", "rtm_run_driver",
 ]
@@ -84,6 +85,7 @@ def lib():
     L.rtm_stack_finalize.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_size_t, _fp, _fp]
     L.rtm_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.rtm_reset_stats.argtypes = [C.c_void_p]
+    L.rtm_store_all_active.argtypes = [C.c_void_p]
     L.rtm_ricker.restype = C.c_float
     L.rtm_ricker.argtypes = [C.c_float, C.c_float]
     L.rtm_source_row.argtypes = [C.c_float, C.c_float, C.c_int]
@@ -274,6 +276,9 @@ class Engine:
         _check(lib().rtm_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
+    def store_all_active(self):
+        return bool(lib().rtm_store_all_active(self._h))
+
     def reset_stats(self):
         _check(lib().rtm_reset_stats(self._h))
 
@@ -298,11 +303,11 @@ def stack_finalize(up_sum, down_sum, nrec, iNorm):
     return img, ill
 
 
-def engine_for_case(case, NT=None, max_batch=1, device=0):
+def engine_for_case(case, NT=None, max_batch=1, device=0, flags=0):
     """Engine configured from a tests/refcase.Case-like object (reference parameter names)."""
     d = derived(case.h, case.hz, case.tao, case.tao1, case.f0, case.NT1)
     return Engine(device, mod_NZ=case.mod_NZ, mod_NX=case.mod_NX, N2=case.N2, nfdmax=case.nfdmax,
                   NT=d["NT"] if NT is None else NT, iLSTE=case.iLSTE, iCompen=case.iCompen, h=case.h,
                   hz=case.hz, tao=case.tao, f0=case.f0, whitecoe=case.whitecoe,
                   s_l=case.s_l + case.N2 - 1, s_z=case.s_z + case.N2 - 1, n=case.n, ds=case.ds,
-                  max_batch=max_batch)
+                  max_batch=max_batch, flags=flags)

@@ -240,6 +240,10 @@ struct rtm_ctx {
     float* field[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float* acc[4]   = {nullptr, nullptr, nullptr, nullptr};
     CUtensorMap tmap_f[5], tmap_b[5];  // halo boxes of the forward / backward tile shapes
+    // store-all mode (RTM_FLAG_STORE_ALL): every forward time slot stays in HBM, [NT][S][NZ][pitch]
+    float* store = nullptr;
+    CUtensorMap tmap_store;
+    bool   store_mode = false;
     float* d_v = nullptr;
     float* d_avel = nullptr;
     unsigned short* d_bins = nullptr;
@@ -260,7 +264,7 @@ struct rtm_ctx {
     rtm_stats stats{};
 };
 
-static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int tile_rows)
+static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int tile_rows, long long nslab = 0)
 {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -276,7 +280,7 @@ static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int tile_rows)
         fn = (EncodeFn)p;
     }
     const Geo& G = c->G;
-    cuuint64_t dims[3]    = {(cuuint64_t)G.pitch, (cuuint64_t)G.NZ, (cuuint64_t)c->S};
+    cuuint64_t dims[3]    = {(cuuint64_t)G.pitch, (cuuint64_t)G.NZ, (cuuint64_t)(nslab ? nslab : c->S)};
     cuuint64_t strides[2] = {(cuuint64_t)G.pitch * 4, (cuuint64_t)G.shot_stride * 4};
     cuuint32_t box[3]     = {(cuuint32_t)(kTX + 2 * c->RP), (cuuint32_t)(tile_rows + 2 * c->RP), 1};
     cuuint32_t estr[3]    = {1, 1, 1};
@@ -288,6 +292,7 @@ static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int tile_rows)
 }
 
 extern "C" int rtm_ctx_device(rtm_ctx* c) { return c ? c->device : -1; }
+extern "C" int rtm_store_all_active(rtm_ctx* c) { return (c && c->store_mode) ? 1 : 0; }
 
 extern "C" int rtm_device_count(void)
 {
@@ -300,6 +305,7 @@ extern "C" void rtm_destroy(rtm_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaFree(c->store);
     for (auto& f : c->field) cudaFree(f);
     for (auto& f : c->acc) cudaFree(f);
     cudaFree(c->d_v); cudaFree(c->d_avel); cudaFree(c->d_bins); cudaFree(c->d_tile_bins_f); cudaFree(c->d_tile_bins_b); cudaFree(c->d_c); cudaFree(c->d_Index);
@@ -418,6 +424,20 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
         if (!rc) rc = encode_tmap(c, &c->tmap_b[i], c->field[i], kWarps * RTM_NR_B);
         if (rc) return fail(rc);
     }
+    if (p->flags & RTM_FLAG_STORE_ALL) {
+        // keep the whole forward wavefield when it fits (with 4 GB of head-room for the strips-free
+        // rest); otherwise fall back to boundary saving + reverse-time reconstruction
+        const size_t slot_floats = (size_t)c->S * G.shot_stride;
+        const size_t bytes = ((size_t)G.NT * slot_floats + 64) * 4;
+        CKC(cudaMemGetInfo(&free_b, &total_b));
+        if (bytes + (4ull << 30) < free_b && (size_t)G.NT * c->S < (1ull << 31)) {
+            CKC(cudaMalloc(&c->store, bytes));
+            CKC(cudaMemset(c->store, 0, bytes));
+            int rc = encode_tmap(c, &c->tmap_store, c->store, kWarps * RTM_NR_F, (long long)G.NT * c->S);
+            if (rc) return fail(rc);
+            c->store_mode = true;
+        }
+    }
     // The allocations above were cleared with legacy-stream memsets, which are asynchronous to
     // the host and NOT ordered against the context's non-blocking stream: drain them here.
     CKC(cudaDeviceSynchronize());
@@ -502,7 +522,7 @@ extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const fl
 }
 
 // ------------------------------------------------------------------------------------ launches
-template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, int ns, int cur, const FwdArgs& a)
+template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, int ns, const CUtensorMap& tm, const FwdArgs& a)
 {
     const Geo& G = c->G;
     const int nring = 2 * G.nband + 2 * G.nside;
@@ -512,23 +532,35 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, int ns, int cur, co
         c->smem_fwd = smem;
     }
     dim3 grid((unsigned)((nring + G.ntx * G.ntz_f) * ns));
-    fwd_step_kernel<RP, LS, RTM_NR_F><<<grid, kThreads, smem, c->stream>>>(c->tmap_f[cur], G, a);
+    fwd_step_kernel<RP, LS, RTM_NR_F><<<grid, kThreads, smem, c->stream>>>(tm, G, a);
     return RTM_OK;
 }
 template <int RP, bool LS> static int launch_bwd(rtm_ctx* c, int ns, int s1, int r1, const BwdArgs& a)
 {
+    if (c->store_mode) {
+        const Geo& G = c->G;
+        const int nring = 2 * G.nband + 2 * G.nside;
+        size_t smem = std::max((size_t)Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
+        if (smem > c->smem_bwd) {
+            CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            c->smem_bwd = smem;
+        }
+        dim3 grid((unsigned)((nring + G.ntx * G.ntz_b) * ns));
+        bwd_step_kernel<RP, LS, RTM_NR_B, true><<<grid, kThreads, smem, c->stream>>>(c->tmap_b[r1], c->tmap_b[r1], G, a);
+        return RTM_OK;
+    }
     const Geo& G = c->G;
     const int nring = 2 * G.nband + 2 * G.nside;
     size_t smem = std::max((size_t)2 * Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
     if (smem > c->smem_bwd) {
-        CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->smem_bwd = smem;
     }
     dim3 grid((unsigned)((nring + G.ntx * G.ntz_b) * ns));
-    bwd_step_kernel<RP, LS, RTM_NR_B><<<grid, kThreads, smem, c->stream>>>(c->tmap_b[s1], c->tmap_b[r1], G, a);
+    bwd_step_kernel<RP, LS, RTM_NR_B, false><<<grid, kThreads, smem, c->stream>>>(c->tmap_b[s1], c->tmap_b[r1], G, a);
     return RTM_OK;
 }
-static int dispatch_fwd(rtm_ctx* c, int ns, int cur, const FwdArgs& a)
+static int dispatch_fwd(rtm_ctx* c, int ns, const CUtensorMap& cur, const FwdArgs& a)
 {
     const bool ls = c->G.iLSTE == 0;
     switch (c->RP) {
@@ -569,7 +601,8 @@ static int ensure_strips(rtm_ctx* c)
 // Forward loop for `ns` shots (sources already in d_src).  On return field[*last1] holds slot
 // NT-1 and field[*last0] slot NT-2.
 static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool strips, float* gather,
-                       int nsnap, const int* snap_k, float* snaps_host, int* last1, int* last0)
+                       int nsnap, const int* snap_k, float* snaps_host, bool use_store, float** last1,
+                       float** last0)
 {
     const Geo& G = c->G;
     std::vector<int2> src(ns);
@@ -579,44 +612,50 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
         src[s] = make_int2(r_u[s], r_x[s]);
     }
     CK(cudaMemcpyAsync(c->d_src, src.data(), sizeof(int2) * ns, cudaMemcpyHostToDevice, c->stream));
-    for (int b = 0; b < 3; ++b) CK(cudaMemsetAsync(c->field[b], 0, c->field_floats * 4, c->stream));
+    // time slot k lives in one of three rotating buffers, or -- store-all mode -- in its own slab
+    const size_t slab = (size_t)c->S * G.shot_stride;
+    auto slot = [&](int k) -> float* { return use_store ? c->store + (size_t)k * slab : c->field[k % 3]; };
+    if (use_store) {
+        CK(cudaMemsetAsync(slot(0), 0, 2 * slab * 4, c->stream));
+    } else {
+        for (int b = 0; b < 3; ++b) CK(cudaMemsetAsync(c->field[b], 0, c->field_floats * 4, c->stream));
+    }
     const float fw1 = (float)(rtm::ricker(0.0f, c->p.f0) / 2.0);  // :803
-    init_source_kernel<<<ns, 1, 0, c->stream>>>(c->field[1], G, c->d_src, fw1);
-    Strips st = strips ? c->st : Strips{nullptr, nullptr, nullptr, nullptr};
+    init_source_kernel<<<ns, 1, 0, c->stream>>>(slot(1), G, c->d_src, fw1);
+    Strips st = (strips && !use_store) ? c->st : Strips{nullptr, nullptr, nullptr, nullptr};
     {
         size_t m = std::max({(size_t)G.nfdmax * G.mod_NX, (size_t)G.nfdmax * G.mod_NZ, (size_t)G.n});
         dim3 grid((unsigned)((m + 255) / 256), ns);
-        if (strips || gather) {
-            strips_from_field_kernel<<<grid, 256, 0, c->stream>>>(c->field[0], G, st, 0, gather);
-            strips_from_field_kernel<<<grid, 256, 0, c->stream>>>(c->field[1], G, st, 1, gather);
+        if (st.up || gather) {
+            strips_from_field_kernel<<<grid, 256, 0, c->stream>>>(slot(0), G, st, 0, gather);
+            strips_from_field_kernel<<<grid, 256, 0, c->stream>>>(slot(1), G, st, 1, gather);
         }
     }
-    auto snapshot = [&](int k, int buf) -> int {
+    auto snapshot = [&](int k) -> int {
         for (int i = 0; i < nsnap; ++i) {
             if (snap_k[i] != k) continue;
             CK(cudaStreamSynchronize(c->stream));
             for (int s = 0; s < ns; ++s)
                 CK(cudaMemcpy2DAsync(snaps_host + ((size_t)s * nsnap + i) * G.NZ * G.NX, (size_t)G.NX * 4,
-                                     c->field[buf] + (size_t)s * G.shot_stride + G.padL, (size_t)G.pitch * 4,
+                                     slot(k) + (size_t)s * G.shot_stride + G.padL, (size_t)G.pitch * 4,
                                      (size_t)G.NX * 4, G.NZ, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
         }
         return RTM_OK;
     };
-    if (nsnap) { if (int rc = snapshot(0, 0)) return rc; if (int rc = snapshot(1, 1)) return rc; }
+    if (nsnap) { if (int rc = snapshot(0)) return rc; if (int rc = snapshot(1)) return rc; }
     int NT2;
     rtm_derived(c->p.h, c->p.hz, c->p.tao, c->p.tao, c->p.f0, 2, nullptr, &NT2, nullptr, nullptr, nullptr, nullptr, nullptr);
-    int i0 = 0, i1 = 1, i2 = 2;
     CK(cudaEventRecord(c->ev0, c->stream));
     for (int k = 2; k < G.NT; ++k) {
         FwdArgs a;
-        a.P1 = c->field[i1]; a.P0 = c->field[i0]; a.P2 = c->field[i2];
+        a.P1 = slot(k - 1); a.P0 = slot(k - 2); a.P2 = slot(k);
         a.src = c->d_src;
         a.wavelet = (k < NT2) ? rtm::ricker((k - 1) * c->p.tao, c->p.f0) : 0.0f;  // :812-813
         a.k = k; a.nshots = ns; a.st = st; a.gather = gather;
-        if (int rc = dispatch_fwd(c, ns, i1, a)) return rc;
-        if (nsnap) if (int rc = snapshot(k, i2)) return rc;
-        const int t = i0; i0 = i1; i1 = i2; i2 = t;
+        a.tma_s0 = use_store ? (k - 1) * c->S : 0;
+        if (int rc = dispatch_fwd(c, ns, use_store ? c->tmap_store : c->tmap_f[(k - 1) % 3], a)) return rc;
+        if (nsnap) if (int rc = snapshot(k)) return rc;
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaGetLastError());
@@ -629,7 +668,7 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
     c->stats.forward_seconds += ms * 1e-3;
     c->stats.kernel_launches += G.NT - 2 + 3;
     c->last_forward_ms = ms;
-    *last1 = i1; *last0 = i0;
+    *last1 = slot(G.NT - 1); *last0 = slot(G.NT - 2);
     return RTM_OK;
 }
 
@@ -643,9 +682,9 @@ extern "C" int rtm_forward(rtm_ctx* c, int nshots, const int* r_u, const int* r_
     const Geo& G = c->G;
     for (int first = 0; first < nshots; first += c->S) {
         const int ns = std::min(c->S, nshots - first);
-        int l1, l0;
+        float *l1, *l0;
         if (int rc = run_forward(c, ns, r_u + first, r_x + first, false, gathers ? c->d_traces : nullptr, nsnap,
-                                 snap_k, snaps ? snaps + (size_t)first * nsnap * G.NZ * G.NX : nullptr, &l1, &l0))
+                                 snap_k, snaps ? snaps + (size_t)first * nsnap * G.NZ * G.NX : nullptr, false, &l1, &l0))
             return rc;
         if (gathers) {
             dim3 grid((G.n + 31) / 32, (G.NT + 31) / 32, ns);  // [NT][n] -> [n][NT]
@@ -664,35 +703,40 @@ extern "C" int rtm_forward(rtm_ctx* c, int nshots, const int* r_u, const int* r_
 static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, float* up, float* down, float* stable)
 {
     const Geo& G = c->G;
-    if (int rc = ensure_strips(c)) return rc;
-    int l1, l0;
+    const bool store = c->store_mode;
+    if (!store) if (int rc = ensure_strips(c)) return rc;
+    float *l1, *l0;
     CK(cudaEventRecord(c->evA, c->stream));
-    if (int rc = run_forward(c, ns, r_u, r_x, true, nullptr, 0, nullptr, nullptr, &l1, &l0)) return rc;
-    // source field: sx = slot NT-1 ("previous", updated in place), sy = slot NT-2 ("current")
-    int sx = l1, sy = l0;
-    int rb[3], nrb = 0;
-    for (int b = 0; b < 5; ++b)
-        if (b != sx && b != sy) rb[nrb++] = b;
+    if (int rc = run_forward(c, ns, r_u, r_x, true, nullptr, 0, nullptr, nullptr, store, &l1, &l0)) return rc;
+    // source field: l1 = slot NT-1 ("previous", updated in place), l0 = slot NT-2 ("current");
+    // the receiver field rotates through the remaining buffers (store-all: all of field[0..2])
+    int sx = -1, sy = -1, rb[3], nrb = 0;
+    for (int b = 0; b < 5; ++b) {
+        if (c->field[b] == l1) sx = b;
+        else if (c->field[b] == l0) sy = b;
+        else if (nrb < 3) rb[nrb++] = b;
+    }
     for (int i = 0; i < 3; ++i) CK(cudaMemsetAsync(c->field[rb[i]], 0, c->field_floats * 4, c->stream));
     const float fw1 = (float)(rtm::ricker(0.0f, c->p.f0) / 2.0);
     {
         dim3 grid((G.NX + 127) / 128, G.NZ, ns);
-        acc_init_kernel<<<grid, 128, 0, c->stream>>>(G, c->field[sx], c->field[sy], c->d_src, fw1, c->acc[0],
-                                                      c->acc[1], c->acc[2], c->acc[3]);
+        acc_init_kernel<<<grid, 128, 0, c->stream>>>(G, l1, l0, c->d_src, fw1, c->acc[0], c->acc[1], c->acc[2], c->acc[3]);
     }
     int NT2;
     rtm_derived(c->p.h, c->p.hz, c->p.tao, c->p.tao, c->p.f0, 2, nullptr, &NT2, nullptr, nullptr, nullptr, nullptr, nullptr);
     int r0 = rb[0], r1 = rb[1], r2 = rb[2];
+    const size_t slab = (size_t)c->S * G.shot_stride;
     CK(cudaEventRecord(c->ev0, c->stream));
     for (int k = G.NT - 3; k >= 0; --k) {
         BwdArgs a;
-        a.S1 = c->field[sy]; a.S02 = c->field[sx];
+        a.Sk = store ? c->store + (size_t)k * slab : nullptr;
+        a.S1 = store ? nullptr : c->field[sy]; a.S02 = store ? nullptr : c->field[sx];
         a.R1 = c->field[r1]; a.R0 = c->field[r0]; a.R2 = c->field[r2];
         a.src = c->d_src;
         a.wavelet = (k < NT2) ? rtm::ricker((k + 1) * c->p.tao, c->p.f0) : 0.0f;  // :889-890
         a.k = k; a.nshots = ns; a.st = c->st; a.seis = c->d_traces;
         a.sumS = c->acc[0]; a.sumR = c->acc[1]; a.rel1 = c->acc[2]; a.rel2 = c->acc[3];
-        if (int rc = dispatch_bwd(c, ns, sy, r1, a)) return rc;
+        if (int rc = dispatch_bwd(c, ns, store ? r1 : sy, r1, a)) return rc;
         std::swap(sx, sy);
         const int t = r0; r0 = r1; r1 = r2; r2 = t;
     }
@@ -715,8 +759,8 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     const double steps = (double)(G.NT - 2) * ns;
-    c->stats.cell_updates += steps * ((double)G.NZ * G.NX + (double)ncell);
-    c->stats.algorithmic_bytes += steps * (double)G.NZ * G.NX * (G.iCompen == 1 ? 60.0 : 44.0);
+    c->stats.cell_updates += steps * ((double)G.NZ * G.NX + (store ? 0.0 : (double)ncell));
+    c->stats.algorithmic_bytes += steps * (double)G.NZ * G.NX * ((G.iCompen == 1 ? 60.0 : 44.0) - (store ? 8.0 : 0.0));
     c->stats.backward_seconds += ms * 1e-3;
     CK(cudaEventElapsedTime(&ms, c->evA, c->evB));
     c->stats.device_seconds += ms * 1e-3;  // whole batch: init, both loops, image post, stack

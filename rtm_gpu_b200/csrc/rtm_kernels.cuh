@@ -526,6 +526,7 @@ struct FwdArgs {
     float        wavelet;
     int          k;    // time slot being produced
     int          nshots;
+    int          tma_s0;  // offset of shot 0 along the tensor map's 3rd dimension (store-all: slot*S)
     Strips       st;   // may hold nulls when strips are not wanted (pure modelling)
     float*       gather;  // [S][NT][n] time-major, or null
 };
@@ -598,7 +599,7 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(bar, Tile<RP, NR>::BYTES);
-        tma_load_3d(sP, &tmP1, bar, G.padL + x0 - RP, z0 - RP, shot);
+        tma_load_3d(sP, &tmP1, bar, G.padL + x0 - RP, z0 - RP, a.tma_s0 + shot);
     }
     const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
     if (G.lead > 0) {
@@ -609,7 +610,7 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
         if (L2i < a.nshots * ntile) {
             const int ps = L2i / ntile, pt = L2i % ntile;
             const int pz0 = G.N2 + (pt / G.ntx) * (kWarps * NR), px0 = G.N2 + (pt % G.ntx) * kTX;
-            if (tid == 32) tma_prefetch_3d(&tmP1, G.padL + px0 - RP, pz0 - RP, ps);
+            if (tid == 32) tma_prefetch_3d(&tmP1, G.padL + px0 - RP, pz0 - RP, a.tma_s0 + ps);
             if (tid >= 64 && tid < 64 + kWarps * NR && pz0 + tid - 64 < zend) {
                 const size_t po = (long long)ps * G.shot_stride + (size_t)(pz0 + tid - 64) * G.pitch + G.padL + px0;
                 const uint32_t bytes = 4u * (uint32_t)min(kTX, G.pitch - G.padL - px0);
@@ -693,6 +694,7 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
 // receiver slot k on the full grid with data replacement and ABC, imaging accumulators.
 // ------------------------------------------------------------------------------------
 struct BwdArgs {
+    const float* Sk;   // store-all mode: the stored forward field of slot k (S1/S02/strips unused)
     const float* S1;   // source slot k+1 (ring = strips of slot k+1)
     float*       S02;  // in: source slot k+2, out: source slot k (interior), ring := strips of slot k
     const float* R1;   // receiver, current
@@ -707,7 +709,9 @@ struct BwdArgs {
     float *sumS, *sumR, *rel1, *rel2;  // accumulators, field layout
 };
 
-template <int RP, bool LS, int NR>
+// STORE: the source field of slot k is read from the stored forward wavefield instead of being
+// reconstructed (RTM_FLAG_STORE_ALL; not a reference mode).
+template <int RP, bool LS, int NR, bool STORE>
 __global__ void __launch_bounds__(kThreads, (RP <= 4 ? (LS ? RTM_BWD_MINB_LS : RTM_BWD_MINB) : 2))
 bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmR1,
                 const __grid_constant__ Geo G, const BwdArgs a)
@@ -731,6 +735,7 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
             R2[(size_t)z * G.pitch + x] = val;
             // BKEqual :222-245, one step early: the ring of the buffer that becomes the
             // "current" source field at step k-1 receives the strips of slot k.
+            if (STORE) return;
             const size_t sx = ((size_t)shot * G.NT + k) * nf * G.mod_NX;
             const size_t sz = ((size_t)shot * G.NT + k) * nf * G.mod_NZ;
             if (x >= N2 && x < NX - N2) {
@@ -747,16 +752,17 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
     const int t   = bi % nint;
     const int tz  = t / G.ntx, tx = t % G.ntx;
     const int z0  = G.N2 + tz * (kWarps * NR), x0 = G.N2 + tx * kTX;
+    constexpr int NTILE = STORE ? 1 : 2;  // halo tiles in shared memory
     float*    sS  = reinterpret_cast<float*>(smem_raw);
-    float*    sR  = reinterpret_cast<float*>(smem_raw + Tile<RP, NR>::BYTES);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * Tile<RP, NR>::BYTES);
+    float*    sR  = reinterpret_cast<float*>(smem_raw + (NTILE - 1) * Tile<RP, NR>::BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + NTILE * Tile<RP, NR>::BYTES);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(bar, 2 * Tile<RP, NR>::BYTES);
-        tma_load_3d(sS, &tmS1, bar, G.padL + x0 - RP, z0 - RP, shot);
+        mbar_expect_tx(bar, NTILE * Tile<RP, NR>::BYTES);
+        if (!STORE) tma_load_3d(sS, &tmS1, bar, G.padL + x0 - RP, z0 - RP, shot);
         tma_load_3d(sR, &tmR1, bar, G.padL + x0 - RP, z0 - RP, shot);
     }
     const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
@@ -781,7 +787,7 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
 
     LsTable T{};
     if (LS) {
-        T = ls_stage_slice(G, G.tile_bins_b[t], reinterpret_cast<int*>(smem_raw + 2 * Tile<RP, NR>::BYTES + 16));
+        T = ls_stage_slice(G, G.tile_bins_b[t], reinterpret_cast<int*>(smem_raw + NTILE * Tile<RP, NR>::BYTES + 16));
         __syncthreads();
     }
     const int lz0 = warp * NR, lx0 = lane * 4;
@@ -801,7 +807,7 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
     float4 vn  = __ldg(reinterpret_cast<const float4*>(vp));
     uint2  bn  = make_uint2(0u, 0u);
     if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bp));
-    float4 s0n = *reinterpret_cast<const float4*>(a.S02 + o);
+    float4 s0n = *reinterpret_cast<const float4*>((STORE ? a.Sk : a.S02) + o);  // STORE: slot k itself
     float4 r0n = *reinterpret_cast<const float4*>(a.R0 + o);
     mbar_wait(bar, 0);
 
@@ -834,18 +840,23 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
         if (r + 1 < nrow) {
             vn  = __ldg(reinterpret_cast<const float4*>(vp + G.pitch));
             if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bp + G.pitch));
-            s0n = *reinterpret_cast<const float4*>(a.S02 + o + G.pitch);
+            s0n = *reinterpret_cast<const float4*>((STORE ? a.Sk : a.S02) + o + G.pitch);
             r0n = *reinterpret_cast<const float4*>(a.R0 + o + G.pitch);
         }
         float w1[4], p1[4], S2[4], R2[4];
         // source field: BKAdd_EFF / BKAdd_EFF_Con, double final sum, + wavelet at the source
-        stencil_row<RP, LS>(G, spS, G.nfdmax, T, bc, w1, p1);
+        if (STORE) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) S2[q] = finish_double(av[q], w1[q], p1[q], s0[q]);
-        if (r == src_r) {
+            for (int q = 0; q < 4; ++q) S2[q] = s0[q];
+        } else {
+            stencil_row<RP, LS>(G, spS, G.nfdmax, T, bc, w1, p1);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (x + q == src.y) S2[q] = __fadd_rn(S2[q], a.wavelet);
+            for (int q = 0; q < 4; ++q) S2[q] = finish_double(av[q], w1[q], p1[q], s0[q]);
+            if (r == src_r) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (x + q == src.y) S2[q] = __fadd_rn(S2[q], a.wavelet);
+            }
         }
         // receiver field: BKAdd / BKAdd_Con, float final sum, data replacement
         stencil_row<RP, LS>(G, spR, G.nfdmax, T, bc, w1, p1);
@@ -882,7 +893,7 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
                 r2v[q] = __fmaf_rn(S2[q], S2[q], r2v[q]);
             }
         }
-        put(a.S02, S2);
+        if (!STORE) put(a.S02, S2);
         put(a.R2, R2);
         put(a.rel1, r1v);
         put(a.rel2, r2v);

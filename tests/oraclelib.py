@@ -59,6 +59,8 @@ def oracle():
                                      fp, C.c_void_p, C.c_int, ip, C.POINTER(fp)]
         L.oracle_migrate_shot.argtypes = [C.POINTER(OracleParams), fp, fp, ip, C.c_int, C.c_int,
                                           fp, fp, fp, fp, fp, fp]
+        L.oracle_migrate_shot_ex.argtypes = [C.POINTER(OracleParams), fp, fp, ip, C.c_int, C.c_int,
+                                             fp, fp, fp, fp, fp, fp, C.c_int]
         L.oracle_stack.argtypes = [C.POINTER(fp), C.POINTER(fp), C.c_int, C.c_int, C.c_int,
                                    C.c_int, fp, fp]
         _oracle = L
@@ -126,7 +128,7 @@ def forward(p, v, c, Index, r_u, r_x, want_gather=True, snaps=()):
     return gather, last0, last1, so
 
 
-def migrate_shot(p, v, c, Index, r_u, r_x, seis):
+def migrate_shot(p, v, c, Index, r_u, r_x, seis, store_all=0):
     up = np.zeros((p.mod_NX, p.mod_NZ), np.float32)
     down = np.zeros_like(up)
     rel1 = np.zeros((p.mod_NZ, p.mod_NX), np.float32)
@@ -134,8 +136,8 @@ def migrate_shot(p, v, c, Index, r_u, r_x, seis):
     stable = C.c_float()
     seis = np.ascontiguousarray(seis, np.float32)
     assert seis.shape == (p.n, p.NT)
-    oracle().oracle_migrate_shot(C.byref(p), _f(v), _f(c), _i(Index), r_u, r_x, _f(seis), _f(up),
-                                 _f(down), _f(rel1), _f(rel2), C.byref(stable))
+    oracle().oracle_migrate_shot_ex(C.byref(p), _f(v), _f(c), _i(Index), r_u, r_x, _f(seis), _f(up),
+                                    _f(down), _f(rel1), _f(rel2), C.byref(stable), store_all)
     return up, down, rel1, rel2, stable.value
 
 

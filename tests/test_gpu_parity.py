@@ -142,3 +142,33 @@ def test_fresh_contexts_are_deterministic():
         if first is None:
             first = (u, d, s)
         assert np.array_equal(u, first[0]) and np.array_equal(d, first[1]) and np.array_equal(s, first[2]), it
+
+
+@pytest.mark.parametrize("name", ["tiny_te_compen", "tiny_ls_noncompen", "small_aniso_flip"])
+def test_store_all_mode(name):
+    """RTM_FLAG_STORE_ALL (keep the whole forward wavefield in HBM): bit-exact against the oracle's
+    store-all variant, and within the reference's own reconstruction error of the default mode."""
+    case = GOLDEN_CASES[name]
+    v, vmin, vmax, Index, c = prepare(case)
+    seis = np.stack([data_tiny(case, d) for d in case.depths])
+    with make_engine(case, v, vmin, vmax, Index, c, max_batch=2, flags=R.STORE_ALL) as e:
+        assert e.store_all_active()
+        up, down, stable = e.migrate(case.r_u, [case.r_x0] * case.nrec, seis)
+    with make_engine(case, v, vmin, vmax, Index, c, max_batch=2) as e:
+        assert not e.store_all_active()
+        up0, down0, _ = e.migrate(case.r_u, [case.r_x0] * case.nrec, seis)
+    p = O.make_params(case, vmin, vmax, contract=1)
+    for m in range(case.nrec):
+        ou, od, _, _, ost = O.migrate_shot(p, v, c, Index, case.r_u[m], case.r_x0, seis[m], store_all=1)
+        assert np.array_equal(up[m], ou) and np.array_equal(down[m], od) and stable[m] == np.float32(ost)
+        assert rel_l2(down[m], down0[m]) < 1e-3
+        assert rel_l2(up[m], up0[m]) < (2e-2 if case.iCompen == 1 else 0.5)
+
+
+def test_store_all_falls_back_when_it_does_not_fit():
+    import dataclasses
+    big = dataclasses.replace(GOLDEN_CASES["tiny_te_compen"], mod_NX=2301, mod_NZ=751, NT1=7501, n=100, ds=5,
+                              NX_ED=2301, NZ_ED=751)
+    e = R.engine_for_case(big, max_batch=8, flags=R.STORE_ALL)  # 8 x 7501 x 7.3 MB = 440 GB
+    assert not e.store_all_active()
+    e.close()

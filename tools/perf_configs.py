@@ -32,7 +32,7 @@ def model(mod_NX, mod_NZ, h, hz):
     return np.rint(np.clip(np.where(lens, 4300.0, v), 1500.0, 4500.0)).astype(np.float32)
 
 
-def run(name, mod_NX, mod_NZ, N2, nfdmax, nfdmin, iLSTE, NT, h, tao, f0, fmax, batch, n, ds, reps=2, eps=1e-5):
+def run(name, mod_NX, mod_NZ, N2, nfdmax, nfdmin, iLSTE, NT, h, tao, f0, fmax, batch, n, ds, reps=2, eps=1e-5, flags=0):
     vel = model(mod_NX, mod_NZ, h, h)
     v = R.pad_velocity(vel, N2, 0)
     vmin, vmax, nvel, need = R.velocity_bins(v, 1.0)
@@ -45,7 +45,8 @@ def run(name, mod_NX, mod_NZ, N2, nfdmax, nfdmin, iLSTE, NT, h, tao, f0, fmax, b
     t_op = time.time() - t0
     NZ, NX = mod_NZ + 2 * N2, mod_NX + 2 * N2
     eng = R.Engine(0, mod_NZ=mod_NZ, mod_NX=mod_NX, N2=N2, nfdmax=nfdmax, NT=NT, iLSTE=iLSTE, iCompen=1, h=h, hz=h,
-                   tao=tao, f0=f0, whitecoe=1e-4, s_l=N2, s_z=N2 + 2, n=n, ds=ds, max_batch=batch)
+                   tao=tao, f0=f0, whitecoe=1e-4, s_l=N2, s_z=N2 + 2, n=n, ds=ds, max_batch=batch, flags=flags)
+    store = eng.store_all_active()
     eng.set_model(v, vmin, vmax, 1.0)
     eng.set_operator(c, Index)
     k = np.arange(NT, dtype=np.float32)[None, None, :]
@@ -65,11 +66,12 @@ def run(name, mod_NX, mod_NZ, N2, nfdmax, nfdmin, iLSTE, NT, h, tao, f0, fmax, b
     fwd_us = 1e6 * st["forward_seconds"] / steps
     bwd_us = 1e6 * st["backward_seconds"] / steps
     cells = NZ * NX * batch
-    out = {"config": name, "grid": [mod_NX, mod_NZ], "N2": N2, "operator": "taylor" if iLSTE else "adaptive",
+    bwd_bytes = 52.0 if store else 60.0
+    out = {"config": name, "store_all": store, "grid": [mod_NX, mod_NZ], "N2": N2, "operator": "taylor" if iLSTE else "adaptive",
            "nfdmax": nfdmax, "nfdmin": nfdmin, "length_histogram": mhist, "NT": NT, "batch": batch,
            "Mcell_updates_per_s": st["cell_updates"] / st["device_seconds"] / 1e6,
            "fwd_us": fwd_us, "fwd_GBps": 16.0 * cells / fwd_us / 1e3, "fwd_frac": 16.0 * cells / fwd_us / 1e3 / PEAK,
-           "bwd_us": bwd_us, "bwd_GBps": 60.0 * cells / bwd_us / 1e3, "bwd_frac": 60.0 * cells / bwd_us / 1e3 / PEAK,
+           "bwd_us": bwd_us, "bwd_GBps": bwd_bytes * cells / bwd_us / 1e3, "bwd_frac": bwd_bytes * cells / bwd_us / 1e3 / PEAK,
            "shots_per_hour": reps * batch / st["device_seconds"] * 3600, "operator_seconds": t_op, "peak_GBps": PEAK}
     print(json.dumps(out), flush=True)
 
@@ -86,6 +88,9 @@ if __name__ == "__main__":
         run("C5 4096^2 adaptive 2..12", 4096, 4096, 12, 12, 2, 0, 120, 20.0, 1e-3, 15.0, 34.0, 1, 4096, 1)
         for R_ in (4, 8, 12):
             run(f"C5 4096^2 adaptive forced R={R_}", 4096, 4096, 12, R_, R_, 0, 120, 20.0, 1e-3, 15.0, 34.0, 1, 4096, 1)
+    if "store" in a.which:  # C2 grid, 2 shots per launch: reconstruction vs store-all (NT 3000: 2 x 3000 x 7.3 MB = 44 GB)
+        for fl in (0, 1):
+            run("C2 2301x751 taylor R=4, 2 shots, NT 3000" + (" STORE_ALL" if fl else ""), 2301, 751, 10, 4, 2, 1, 3000, 4.0, 4e-4, 20.0, 50.0, 2, 2301, 1, reps=1, flags=fl)
     if "c5a" in a.which:  # adaptive-path tuning subset
         run("C5 4096^2 adaptive 2..12", 4096, 4096, 12, 12, 2, 0, 120, 20.0, 1e-3, 15.0, 34.0, 1, 4096, 1)
         run("C5 4096^2 adaptive forced R=4", 4096, 4096, 12, 4, 4, 0, 120, 20.0, 1e-3, 15.0, 34.0, 1, 4096, 1)
