@@ -96,6 +96,15 @@ int rtm_forward(rtm_ctx *ctx, int nshots, const int *r_u, const int *r_x, float 
 int rtm_migrate(rtm_ctx *ctx, int nshots, const int *r_u, const int *r_x, const float *seis,
                 float *up, float *down, float *stable);
 
+/* Same from traces at their recording rate: seis_raw host [nshots][n][NT1] sampled at tao1.  When
+ * NT1 != NT they are resampled to the modelling rate ON THE DEVICE (resample(), Resample.cpp:193-225,
+ * fused with the transpose into the engine's time-major layout), bit-identically to the host
+ * routine; when NT1 == NT they are used as they are (kernel.cu:839-856). */
+int rtm_migrate_raw(rtm_ctx *ctx, int nshots, const int *r_u, const int *r_x, const float *seis_raw,
+                    int NT1, float tao1, float *up, float *down, float *stable);
+/* The device resampler on its own: in host [ntr][NT1] at tao1 -> out host [ntr][NT] at tao. */
+int rtm_resample_device(rtm_ctx *ctx, int ntr, const float *in, int NT1, float tao1, float *out);
+
 /* Same, with the observed traces already resident on the device in the engine's
  * time-major layout (see rtm_upload_gathers); used to time the hot path alone. */
 int rtm_upload_gathers(rtm_ctx *ctx, int nshots, const float *seis);

@@ -47,7 +47,7 @@ class Stats(C.Structure):
 # every symbol include/rtm_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "rtm_last_error", "rtm_version", "rtm_create", "rtm_destroy", "rtm_set_model", "rtm_set_operator",
-    "rtm_forward", "rtm_migrate", "rtm_upload_gathers", "rtm_migrate_resident", "rtm_stack_reset",
+    "rtm_forward", "rtm_migrate", "rtm_migrate_raw", "rtm_resample_device", "rtm_upload_gathers", "rtm_migrate_resident", "rtm_stack_reset",
     "rtm_stack_get", "rtm_stack_device", "rtm_stack_reduce", "rtm_stack_reduce_backend", "rtm_stack_finalize", "rtm_get_stats",
     "rtm_reset_stats", "rtm_device_count", "rtm_store_all_active", "rtm_ricker", "rtm_source_row", "rtm_derived",
     "rtm_pad_velocity", "rtm_velocity_bins", "rtm_taylor_operator", "rtm_ls_operator",
@@ -75,6 +75,8 @@ def lib():
     L.rtm_set_operator.argtypes = [C.c_void_p, _ip, C.c_int, _fp, C.c_int]
     L.rtm_forward.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _fp, C.c_int, _ip, _fp]
     L.rtm_migrate.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _fp, _fp, _fp, _fp]
+    L.rtm_migrate_raw.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _fp, C.c_int, C.c_float, _fp, _fp, _fp]
+    L.rtm_resample_device.argtypes = [C.c_void_p, C.c_int, _fp, C.c_int, C.c_float, _fp]
     L.rtm_upload_gathers.argtypes = [C.c_void_p, C.c_int, _fp]
     L.rtm_migrate_resident.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
     L.rtm_stack_reset.argtypes = [C.c_void_p]
@@ -245,6 +247,26 @@ class Engine:
         stable = np.zeros(ns, np.float32)
         _check(lib().rtm_migrate(self._h, ns, _i(r_u), _i(r_x), _f(seis), _f(up), _f(down), _f(stable)))
         return up, down, stable
+
+    def migrate_raw(self, r_u, r_x, seis_raw, tao1):
+        p = self.params
+        r_u = np.ascontiguousarray(r_u, np.int32)
+        r_x = np.ascontiguousarray(r_x, np.int32)
+        ns = len(r_u)
+        seis_raw = np.ascontiguousarray(seis_raw, np.float32)
+        assert seis_raw.shape[:2] == (ns, p.n)
+        up = np.zeros((ns, p.mod_NX, p.mod_NZ), np.float32)
+        down = np.zeros_like(up)
+        stable = np.zeros(ns, np.float32)
+        _check(lib().rtm_migrate_raw(self._h, ns, _i(r_u), _i(r_x), _f(seis_raw), seis_raw.shape[2], tao1,
+                                     _f(up), _f(down), _f(stable)))
+        return up, down, stable
+
+    def resample_device(self, traces, tao1):
+        traces = np.ascontiguousarray(traces, np.float32)
+        out = np.zeros((traces.shape[0], self.params.NT), np.float32)
+        _check(lib().rtm_resample_device(self._h, traces.shape[0], _f(traces), traces.shape[1], tao1, _f(out)))
+        return out
 
     def upload_gathers(self, seis):
         seis = np.ascontiguousarray(seis, np.float32)

@@ -61,9 +61,9 @@ void run_worker(const Job& job, Worker& w)
     if (rtm_set_operator(w.ctx, c.iLSTE == 0 ? job.Index.data() : nullptr, job.bins.nvel, job.c.data(), (int)job.c.size()))
         return fail(RTM_ERR_ARG, rtm_last_error());
 
-    const size_t ncell = (size_t)c.mod_NX * c.mod_NZ, ntr = (size_t)c.n * g.NT;
+    const size_t ncell = (size_t)c.mod_NX * c.mod_NZ, ntr = (size_t)c.n * c.NT1;
     std::vector<float> seis((size_t)p.max_batch * ntr), up((size_t)p.max_batch * ncell),
-        down((size_t)p.max_batch * ncell), raw((size_t)c.n * c.NT1), stable(p.max_batch);
+        down((size_t)p.max_batch * ncell), stable(p.max_batch);
     std::vector<int> r_u(p.max_batch), r_x(p.max_batch);
     for (int b0 = 0; b0 < w.count; b0 += p.max_batch) {
         const int ns = std::min(p.max_batch, w.count - b0);
@@ -77,18 +77,14 @@ void run_worker(const Job& job, Worker& w)
             const std::string path = c.OutNameseis + name;
             std::FILE* f = std::fopen(path.c_str(), "rb");
             if (!f) return fail(RTM_ERR_IO, "cannot open data file " + path);
-            const size_t got = std::fread(raw.data(), sizeof(float), raw.size(), f);
+            const size_t got = std::fread(seis.data() + (size_t)s * ntr, sizeof(float), ntr, f);
             std::fclose(f);
-            if (got != raw.size()) return fail(RTM_ERR_IO, "short data file " + path);
-            float* dst = seis.data() + (size_t)s * ntr;
-            if (g.NT != c.NT1) {  // :839-845
-                for (int i = 0; i < c.n; ++i)
-                    rtm::resample_trace(c.NT1, c.tao1, raw.data() + (size_t)i * c.NT1, g.NT, c.tao, dst + (size_t)i * g.NT);
-            } else {
-                std::memcpy(dst, raw.data(), ntr * sizeof(float));
-            }
+            if (got != ntr) return fail(RTM_ERR_IO, "short data file " + path);
         }
-        if (rtm_migrate(w.ctx, ns, r_u.data(), r_x.data(), seis.data(), up.data(), down.data(), stable.data()))
+        // traces go up at their recording rate; resampling to the modelling rate (:839-845) and the
+        // transpose to the engine's layout happen on the device
+        if (rtm_migrate_raw(w.ctx, ns, r_u.data(), r_x.data(), seis.data(), c.NT1, c.tao1, up.data(), down.data(),
+                            stable.data()))
             return fail(RTM_ERR_CUDA, rtm_last_error());
         for (int s = 0; s < ns; ++s) {
             const int m = w.first + b0 + s;

@@ -76,6 +76,13 @@ const SincTable& table()
 
 }  // namespace
 
+const float* sinc_table(int* nshifts, int* ntaps)
+{
+    if (nshifts) *nshifts = kShifts;
+    if (ntaps) *ntaps = kTaps;
+    return &table().t[0][0];
+}
+
 void resample_trace(int nxin, float dxin, const float* yin, int nxout, float dxout, float* yout)
 {
     // intt8r :69-129 with fxin = 0 and zero extrapolation on both sides (resample :193-225)

@@ -73,5 +73,7 @@ void taylor_operator(int M, float* c);
 // ---------------------------------------------------------------- data preparation
 // resample(), Resample.cpp:193-225: 8-point tabulated-sinc interpolation of one trace
 void resample_trace(int nxin, float dxin, const float* yin, int nxout, float dxout, float* yout);
+// the 513 x 8 interpolation table (for the device version of the same interpolation)
+const float* sinc_table(int* nshifts, int* ntaps);
 
 }  // namespace rtm

@@ -224,6 +224,45 @@ __global__ void transpose_traces_kernel(const float* in, float* out, int rows, i
         if (c < rows && r + i < cols) out[base + (size_t)(r + i) * rows + c] = t[threadIdx.x][threadIdx.y + i];
 }
 
+// resample() (Resample.cpp:193-225) for a whole gather on the device, fused with the transpose
+// into the engine's time-major layout: raw [S][n][NT1] at dxin -> out [S][NT][n] at dxout.
+// Same table, same float/double evaluation order as csrc/host/resample.cpp (bit-identical).
+__global__ void resample_traces_kernel(const float* raw, float* out, int n, int NT1, int NT, float dxout,
+                                       float xouts, float xoutb, const float* table)
+{
+    __shared__ float t[32][33];
+    const size_t ibase = (size_t)blockIdx.z * n * NT1, obase = (size_t)blockIdx.z * n * NT;
+    const int k = blockIdx.x * 32 + threadIdx.x;
+    for (int i = 0; i < 32; i += 8) {
+        const int j = blockIdx.y * 32 + threadIdx.y + i;
+        float val = 0.0f;
+        if (k < NT && j < n) {
+            const float* yin  = raw + ibase + (size_t)j * NT1;
+            const float xout  = __fmul_rn((float)k, dxout);
+            const float xoutn = __fadd_rn(xoutb, __fmul_rn(xout, xouts));
+            const int   ix    = (int)xoutn;
+            int         ky    = -11 + ix;
+            const float frac  = __fsub_rn(xoutn, (float)ix);
+            const int   kt    = frac >= 0.0f ? (int)((double)__fmul_rn(frac, 512.0f) + 0.5)
+                                             : (int)(((double)frac + 1.0) * 512.0 - 0.5);
+            const float* w = table + kt * 8;
+#pragma unroll
+            for (int q = 0; q < 8; ++q, ++ky) {
+                const float y = (ky < 0 || ky >= NT1) ? 0.0f : yin[ky];
+                const float p = __fmul_rn(y, w[q]);
+                val = (q == 0) ? p : __fadd_rn(val, p);
+            }
+        }
+        t[threadIdx.y + i][threadIdx.x] = val;
+    }
+    __syncthreads();
+    const int j = blockIdx.y * 32 + threadIdx.x;
+    for (int i = 0; i < 32; i += 8) {
+        const int kk = blockIdx.x * 32 + threadIdx.y + i;
+        if (kk < NT && j < n) out[obase + (size_t)kk * n + j] = t[threadIdx.x][threadIdx.y + i];
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------ context
@@ -254,6 +293,9 @@ struct rtm_ctx {
     Strips st{nullptr, nullptr, nullptr, nullptr};
     float* d_traces = nullptr;   // [S][NT][n]
     float* d_stage  = nullptr;   // [S][n][NT] transpose staging
+    float* d_raw    = nullptr;   // [S][n][NT1] raw-rate traces (rtm_migrate_raw)
+    size_t raw_floats = 0;
+    float* d_sinc   = nullptr;   // 513 x 8 interpolation table
     int2*  d_src = nullptr;
     float *d_up = nullptr, *d_down = nullptr, *d_stack = nullptr, *d_stable = nullptr;
     int*   d_maxbits = nullptr;
@@ -310,7 +352,7 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     for (auto& f : c->acc) cudaFree(f);
     cudaFree(c->d_v); cudaFree(c->d_avel); cudaFree(c->d_bins); cudaFree(c->d_tile_bins_f); cudaFree(c->d_tile_bins_b); cudaFree(c->d_c); cudaFree(c->d_Index);
     cudaFree(c->st.up); cudaFree(c->st.dw); cudaFree(c->st.lf); cudaFree(c->st.rt);
-    cudaFree(c->d_traces); cudaFree(c->d_stage); cudaFree(c->d_src);
+    cudaFree(c->d_traces); cudaFree(c->d_stage); cudaFree(c->d_raw); cudaFree(c->d_sinc); cudaFree(c->d_src);
     cudaFree(c->d_up); cudaFree(c->d_down); cudaFree(c->d_stack); cudaFree(c->d_stable);
     cudaFree(c->d_maxbits);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -777,6 +819,74 @@ static int upload_traces(rtm_ctx* c, int ns, const float* seis)
     dim3 grid((G.NT + 31) / 32, (G.n + 31) / 32, ns);  // [n][NT] -> [NT][n]
     transpose_traces_kernel<<<grid, dim3(32, 8), 0, c->stream>>>(c->d_stage, c->d_traces, G.n, G.NT);
     CK(cudaGetLastError());
+    return RTM_OK;
+}
+
+// Raw-rate traces -> d_traces: resampled on the device when NT1 != NT (kernel.cu:839-845), plain
+// transpose otherwise (the reference copies in that case whatever the two rates are).
+static int upload_raw_traces(rtm_ctx* c, int ns, const float* raw, int NT1, float tao1)
+{
+    const Geo& G = c->G;
+    if (NT1 == G.NT) return upload_traces(c, ns, raw);
+    const size_t need = (size_t)c->S * G.n * NT1;
+    if (need > c->raw_floats) {
+        cudaFree(c->d_raw);
+        c->d_raw = nullptr;
+        CK(cudaMalloc(&c->d_raw, need * 4));
+        c->raw_floats = need;
+    }
+    if (!c->d_sinc) {
+        int ns_, nt_;
+        const float* tb = rtm::sinc_table(&ns_, &nt_);
+        CK(cudaMalloc(&c->d_sinc, sizeof(float) * ns_ * nt_));
+        CK(cudaMemcpyAsync(c->d_sinc, tb, sizeof(float) * ns_ * nt_, cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaMemcpyAsync(c->d_raw, raw, (size_t)ns * G.n * NT1 * 4, cudaMemcpyHostToDevice, c->stream));
+    const float xouts = (float)(1.0 / tao1), xoutb = (float)(8.0 - 0.0f * xouts);
+    dim3 grid((G.NT + 31) / 32, (G.n + 31) / 32, ns);
+    resample_traces_kernel<<<grid, dim3(32, 8), 0, c->stream>>>(c->d_raw, c->d_traces, G.n, NT1, G.NT, c->p.tao, xouts,
+                                                                 xoutb, c->d_sinc);
+    CK(cudaGetLastError());
+    return RTM_OK;
+}
+
+extern "C" int rtm_migrate_raw(rtm_ctx* c, int nshots, const int* r_u, const int* r_x, const float* seis_raw,
+                               int NT1, float tao1, float* up, float* down, float* stable)
+{
+    if (!c || !r_u || !r_x || !seis_raw || nshots < 1 || NT1 < 1 || !(tao1 > 0))
+        return rtm_fail(RTM_ERR_ARG, "rtm_migrate_raw: bad argument");
+    if (!c->have_model || !c->have_op) return rtm_fail(RTM_ERR_STATE, "rtm_migrate_raw: set the model and the operator first");
+    CK(cudaSetDevice(c->device));
+    const Geo& G = c->G;
+    const size_t ncell = (size_t)G.mod_NX * G.mod_NZ;
+    for (int first = 0; first < nshots; first += c->S) {
+        const int ns = std::min(c->S, nshots - first);
+        if (int rc = upload_raw_traces(c, ns, seis_raw + (size_t)first * G.n * NT1, NT1, tao1)) return rc;
+        if (int rc = migrate_batch(c, ns, r_u + first, r_x + first, up ? up + first * ncell : nullptr,
+                                   down ? down + first * ncell : nullptr, stable ? stable + first : nullptr))
+            return rc;
+    }
+    return RTM_OK;
+}
+
+// Device resampling on its own (parity tests): traces host [ntr][NT1] -> host [ntr][NT_out].
+extern "C" int rtm_resample_device(rtm_ctx* c, int ntr, const float* in, int NT1, float tao1, float* out)
+{
+    if (!c || !in || !out || ntr < 1) return rtm_fail(RTM_ERR_ARG, "rtm_resample_device: bad argument");
+    CK(cudaSetDevice(c->device));
+    const Geo& G = c->G;
+    if (ntr > c->S * G.n) return rtm_fail(RTM_ERR_ARG, "rtm_resample_device: at most max_batch*n = %d traces", c->S * G.n);
+    // reuse the gather path: treat the traces as one shot of `ntr` traces
+    Geo saved = c->G;
+    const int S_saved = c->S;
+    c->G.n = ntr; c->S = 1;
+    int rc = (NT1 == G.NT) ? upload_traces(c, 1, in) : upload_raw_traces(c, 1, in, NT1, tao1);
+    c->G = saved; c->S = S_saved;
+    if (rc) return rc;
+    dim3 grid((ntr + 31) / 32, (G.NT + 31) / 32, 1);  // [NT][ntr] -> [ntr][NT]
+    transpose_traces_kernel<<<grid, dim3(32, 8), 0, c->stream>>>(c->d_traces, c->d_stage, G.NT, ntr);
+    CK(cudaMemcpyAsync(out, c->d_stage, (size_t)ntr * G.NT * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return RTM_OK;
 }
 

@@ -172,3 +172,30 @@ def test_store_all_falls_back_when_it_does_not_fit():
     e = R.engine_for_case(big, max_batch=8, flags=R.STORE_ALL)  # 8 x 7501 x 7.3 MB = 440 GB
     assert not e.store_all_active()
     e.close()
+
+
+def test_device_resampler_matches_host_routine():
+    """resample() on the device (fused with the transpose) == the host routine, bit for bit; the
+    host routine itself is pinned to the reference's function in tests/test_host.py."""
+    import dataclasses
+    case = dataclasses.replace(GOLDEN_CASES["tiny_te_compen"], tao=0.001, NT1=239)  # engine NT = 239
+    rng = np.random.default_rng(11)
+    with R.engine_for_case(case, max_batch=2) as e:
+        for NT1, tao1 in [(120, 0.002), (477, 0.0005), (300, 0.0013), (96, 0.0025)]:
+            tr = rng.standard_normal((37, NT1)).astype(np.float32)
+            got = e.resample_device(tr, tao1)
+            want = np.stack([R.resample(t, tao1, 239, 0.001) for t in tr])
+            assert np.array_equal(got, want), (NT1, tao1)
+
+
+def test_migrate_raw_equals_host_resampling_then_migrate():
+    import dataclasses
+    case = dataclasses.replace(GOLDEN_CASES["tiny_te_compen"], tao1=0.002, NT1=120)  # NT = 239
+    v, vmin, vmax, Index, c = prepare(case)
+    raw = np.stack([data_tiny(case, d) for d in case.depths])  # [2][n][120] at 2 ms
+    with make_engine(case, v, vmin, vmax, Index, c, max_batch=2) as e:
+        NT = e.params.NT
+        u1, d1, s1 = e.migrate_raw(case.r_u, [case.r_x0] * 2, raw, case.tao1)
+        host = np.stack([[R.resample(t, case.tao1, NT, case.tao) for t in shot] for shot in raw])
+        u2, d2, s2 = e.migrate(case.r_u, [case.r_x0] * 2, host)
+    assert np.array_equal(u1, u2) and np.array_equal(d1, d2) and np.array_equal(s1, s2)
