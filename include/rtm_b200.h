@@ -169,6 +169,19 @@ void  rtm_ls_coefficients(double *c, double r, double bmax, int M, double hzx);
 /* resample(), Resample.cpp:193-225: one trace from nxin samples at dxin to nxout at dxout. */
 void  rtm_resample(int nxin, float dxin, const float *yin, int nxout, float dxout, float *yout);
 
+/* SEG-Y (big-endian; sample formats 1 IBM, 2 int32, 3 int16, 5 IEEE).
+ * rtm_segy_decode / rtm_segy_encode: segy2trace / trace2segy, segy.cpp:653-695.
+ * rtm_segy_info / rtm_segy_read: a whole file as [ntr][ns] floats -- a SEG-Y velocity model is read
+ * this way (trace = x position, sample = depth), giving the raw [mod_NX][mod_NZ] layout.
+ * rtm_segy_write_image: WriteSGY, SGYWrite.cpp:3-55 (headers from a template file). */
+void rtm_segy_decode(const unsigned char *buf, float *out, int ns, int format);
+void rtm_segy_encode(unsigned char *buf, const float *in, int ns, int format);
+int  rtm_segy_info(const char *path, int *ns, int *ntr, int *format, float *dt);
+int  rtm_segy_read(const char *path, float *out, int ns, int ntr);
+int  rtm_segy_write_image(const char *template_path, const char *out_path, const float *data, int ntr,
+                          int ns, int dt_value, const float *SX, const float *SY, float RX, float RY,
+                          const float *DSR);
+
 /* Drop-in driver: everything main() does up to the stacked image (kernel.cu:525-1108),
  * reading the reference's input files and writing its output files.
  *   run_file  path of 2D_Real_RVSP_RTM.txt

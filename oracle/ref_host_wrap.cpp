@@ -64,4 +64,14 @@ void ref_resample(int nxin, float dxin, float *yin, int nxout, float dxout, floa
     resample(nxin, dxin, yin, nxout, dxout, yout);
 }
 
+void ref_segy2trace(const char *buf, float *trace, int ns, int format) { segy2trace(buf, trace, ns, format); }
+void ref_trace2segy(char *buf, const float *trace, int ns, int format) { trace2segy(buf, trace, ns, format); }
+void ref_segy2head(const char *buf, int *words, int nk) { segy2head(buf, words, nk); }
+void ref_head2segy(char *buf, const int *words, int nk) { head2segy(buf, words, nk); }
+/* WriteSGY reads "SGY_Model.sgy" from the current directory (SGYWrite.cpp:14) */
+void ref_WriteSGY(float *Data, int NX, int NT, int tao3, float *SX, float *SY, float RX, float RY, float *DSR, char *name)
+{
+    WriteSGY(Data, NX, NT, tao3, SX, SY, RX, RY, DSR, name);
+}
+
 } /* extern "C" */

@@ -51,7 +51,8 @@ ABI_SYMBOLS = [
     "rtm_stack_get", "rtm_stack_device", "rtm_stack_reduce", "rtm_stack_reduce_backend", "rtm_stack_finalize", "rtm_get_stats",
     "rtm_reset_stats", "rtm_device_count", "rtm_store_all_active", "rtm_ricker", "rtm_source_row", "rtm_derived",
     "rtm_pad_velocity", "rtm_velocity_bins", "rtm_taylor_operator", "rtm_ls_operator",
-    "rtm_ls_coefficients", "rtm_resample", "rtm_run_driver",
+    "rtm_ls_coefficients", "rtm_resample", "rtm_segy_decode", "rtm_segy_encode", "rtm_segy_info",
+    "rtm_segy_read", "rtm_segy_write_image", "rtm_run_driver",
 ]
 
 _lib = None
@@ -103,6 +104,15 @@ def lib():
     L.rtm_ls_coefficients.argtypes = [_dp, C.c_double, C.c_double, C.c_int, C.c_double]
     L.rtm_resample.restype = None
     L.rtm_resample.argtypes = [C.c_int, C.c_float, _fp, C.c_int, C.c_float, _fp]
+    _bp = C.POINTER(C.c_ubyte)
+    L.rtm_segy_decode.restype = None
+    L.rtm_segy_decode.argtypes = [_bp, _fp, C.c_int, C.c_int]
+    L.rtm_segy_encode.restype = None
+    L.rtm_segy_encode.argtypes = [_bp, _fp, C.c_int, C.c_int]
+    L.rtm_segy_info.argtypes = [C.c_char_p, _ip, _ip, _ip, _fp]
+    L.rtm_segy_read.argtypes = [C.c_char_p, _fp, C.c_int, C.c_int]
+    L.rtm_segy_write_image.argtypes = [C.c_char_p, C.c_char_p, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp,
+                                       C.c_float, C.c_float, _fp]
     L.rtm_run_driver.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
     _lib = L
     return L
@@ -183,6 +193,37 @@ def resample(yin, dxin, nxout, dxout):
     out = np.zeros(nxout, np.float32)
     lib().rtm_resample(len(yin), dxin, _f(yin), nxout, dxout, _f(out))
     return out
+
+
+def segy_decode(buf: bytes, ns, fmt):
+    out = np.zeros(ns, np.float32)
+    b = (C.c_ubyte * len(buf)).from_buffer_copy(buf)
+    lib().rtm_segy_decode(b, _f(out), ns, fmt)
+    return out
+
+
+def segy_encode(x, fmt):
+    x = np.ascontiguousarray(x, np.float32)
+    b = (C.c_ubyte * (len(x) * (2 if fmt == 3 else 4)))()
+    lib().rtm_segy_encode(b, _f(x), len(x), fmt)
+    return bytes(b)
+
+
+def segy_read(path):
+    ns, ntr, fmt = C.c_int(), C.c_int(), C.c_int()
+    dt = C.c_float()
+    _check(lib().rtm_segy_info(str(path).encode(), C.byref(ns), C.byref(ntr), C.byref(fmt), C.byref(dt)))
+    out = np.zeros((ntr.value, ns.value), np.float32)
+    _check(lib().rtm_segy_read(str(path).encode(), _f(out), ns.value, ntr.value))
+    return out, fmt.value, dt.value
+
+
+def segy_write_image(template, out_path, data, dt_value, SX, SY, RX, RY, DSR):
+    data = np.ascontiguousarray(data, np.float32)
+    ntr, ns = data.shape
+    SX, SY, DSR = (np.ascontiguousarray(a, np.float32) for a in (SX, SY, DSR))
+    _check(lib().rtm_segy_write_image(str(template).encode(), str(out_path).encode(), _f(data), ntr, ns,
+                                      int(dt_value), _f(SX), _f(SY), RX, RY, _f(DSR)))
 
 
 # ------------------------------------------------------------------ engine

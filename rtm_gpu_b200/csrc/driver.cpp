@@ -8,6 +8,7 @@
 #include "host/rtm_host.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -120,7 +121,25 @@ extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int ver
     if (c.nrec < 1) return rtm_fail(RTM_ERR_ARG, "nrec = %d", c.nrec);
 
     std::vector<float> vraw;
-    if (!rtm::read_velocity(c.OutNameVp.c_str(), c.mod_NZ, c.mod_NX, vraw, err)) return rtm_fail(RTM_ERR_IO, "%s", err.c_str());
+    auto ends_with = [](const std::string& a, const char* suf) {
+        const size_t n = std::strlen(suf);
+        if (a.size() < n) return false;
+        for (size_t i = 0; i < n; ++i)
+            if (std::tolower((unsigned char)a[a.size() - n + i]) != suf[i]) return false;
+        return true;
+    };
+    if (ends_with(c.OutNameVp, ".sgy") || ends_with(c.OutNameVp, ".segy")) {
+        // SEG-Y velocity model: one trace per x position, samples along depth (segy2trace semantics)
+        int ns = 0, ntr = 0, fmt = 0;
+        float dt = 0;
+        if (!rtm::segy_read_info(c.OutNameVp.c_str(), ns, ntr, fmt, dt, err)) return rtm_fail(RTM_ERR_IO, "%s", err.c_str());
+        if (ns != c.mod_NZ || ntr < c.mod_NX)
+            return rtm_fail(RTM_ERR_IO, "SEG-Y model %s is %d traces x %d samples, expected %d x %d", c.OutNameVp.c_str(), ntr, ns, c.mod_NX, c.mod_NZ);
+        vraw.resize((size_t)c.mod_NX * c.mod_NZ);
+        if (!rtm::segy_read_traces(c.OutNameVp.c_str(), vraw.data(), ns, c.mod_NX, err)) return rtm_fail(RTM_ERR_IO, "%s", err.c_str());
+    } else if (!rtm::read_velocity(c.OutNameVp.c_str(), c.mod_NZ, c.mod_NX, vraw, err)) {
+        return rtm_fail(RTM_ERR_IO, "%s", err.c_str());
+    }
     job.v.resize((size_t)g.NZ * g.NX);
     rtm::pad_velocity(vraw.data(), c.mod_NZ, c.mod_NX, c.N2, c.ifv, job.v.data());
     job.bins = rtm::velocity_bins(job.v.data(), (long)job.v.size(), c.dv);
@@ -197,5 +216,18 @@ extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int ver
     if (!write_floats(c.Result + "RVSP_Migration_Real_new2.dat", win.data(), win.size()) ||
         !write_floats(c.Result + "vnew.dat", vwin.data(), vwin.size()))
         return rtm_fail(RTM_ERR_IO, "cannot write the stacked image under %s", c.Result.c_str());
+
+    // SEG-Y export of the windowed image (kernel.cu:1181-1209, WriteSGY) when the header template
+    // the reference requires is present in the working directory
+    if (std::FILE* t = std::fopen("SGY_Model.sgy", "rb")) {
+        std::fclose(t);
+        const int ntr = c.NX_ED - c.NX_BG, ns = c.NZ_ED - c.NZ_BG;
+        std::vector<float> SX(ntr), SY(ntr), DSR(ntr);
+        for (int i = 0; i < ntr; ++i) { SX[i] = 1.0 * i * 10; SY[i] = -1.0 * i * 10; DSR[i] = 1000 - i; }
+        const std::string name = c.Result + "RVSP_migration_Real.sgy";
+        if (!rtm::segy_write_image("SGY_Model.sgy", name.c_str(), win.data(), ntr, ns, (int)c.hz, SX.data(), SY.data(), 1.0f, 1.0f,
+                                   DSR.data(), err))
+            return rtm_fail(RTM_ERR_IO, "%s", err.c_str());
+    }
     return RTM_OK;
 }

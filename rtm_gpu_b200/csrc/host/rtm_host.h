@@ -1,6 +1,7 @@
 // Host-side (C++) pieces of the RTM engine: everything the reference does on the CPU
 // before and after the device time loop that the hot path depends on.
 #pragma once
+#include <cstdint>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -75,5 +76,18 @@ void taylor_operator(int M, float* c);
 void resample_trace(int nxin, float dxin, const float* yin, int nxout, float dxout, float* yout);
 // the 513 x 8 interpolation table (for the device version of the same interpolation)
 const float* sinc_table(int* nshifts, int* ntaps);
+
+// ---------------------------------------------------------------- SEG-Y (segy.cpp, SGYWrite.cpp)
+float    ibm_to_float(uint32_t word);
+uint32_t float_to_ibm(float y);
+void segy_decode_samples(const unsigned char* buf, float* out, int ns, int format);   // segy2trace :653
+void segy_encode_samples(unsigned char* buf, const float* in, int ns, int format);    // trace2segy :675
+void segy_unpack_header(const unsigned char* buf, int* words91);                      // segy2head :697
+void segy_pack_header(unsigned char* buf, const int* words91);                        // head2segy :746
+bool segy_read_info(const char* path, int& ns, int& ntr, int& format, float& dt, std::string& err);
+bool segy_read_traces(const char* path, float* out, int ns, int ntr, std::string& err);
+bool segy_write_image(const char* template_path, const char* out_path, const float* data, int ntr, int ns,
+                      int dt_value, const float* SX, const float* SY, float RX, float RY, const float* DSR,
+                      std::string& err);                                              // WriteSGY
 
 }  // namespace rtm

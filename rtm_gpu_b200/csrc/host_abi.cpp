@@ -70,3 +70,39 @@ extern "C" void rtm_resample(int nxin, float dxin, const float* yin, int nxout, 
 {
     rtm::resample_trace(nxin, dxin, yin, nxout, dxout, yout);
 }
+
+// ---- SEG-Y
+int rtm_fail(int code, const char* fmt, ...);
+
+extern "C" void rtm_segy_decode(const unsigned char* buf, float* out, int ns, int format) { rtm::segy_decode_samples(buf, out, ns, format); }
+extern "C" void rtm_segy_encode(unsigned char* buf, const float* in, int ns, int format) { rtm::segy_encode_samples(buf, in, ns, format); }
+
+extern "C" int rtm_segy_info(const char* path, int* ns, int* ntr, int* format, float* dt)
+{
+    std::string err;
+    int a, b, c;
+    float d;
+    if (!rtm::segy_read_info(path, a, b, c, d, err)) return rtm_fail(RTM_ERR_IO, "%s", err.c_str());
+    if (ns) *ns = a;
+    if (ntr) *ntr = b;
+    if (format) *format = c;
+    if (dt) *dt = d;
+    return RTM_OK;
+}
+
+extern "C" int rtm_segy_read(const char* path, float* out, int ns, int ntr)
+{
+    std::string err;
+    if (!rtm::segy_read_traces(path, out, ns, ntr, err)) return rtm_fail(RTM_ERR_IO, "%s", err.c_str());
+    return RTM_OK;
+}
+
+extern "C" int rtm_segy_write_image(const char* template_path, const char* out_path, const float* data, int ntr,
+                                    int ns, int dt_value, const float* SX, const float* SY, float RX, float RY,
+                                    const float* DSR)
+{
+    std::string err;
+    if (!rtm::segy_write_image(template_path, out_path, data, ntr, ns, dt_value, SX, SY, RX, RY, DSR, err))
+        return rtm_fail(RTM_ERR_IO, "%s", err.c_str());
+    return RTM_OK;
+}

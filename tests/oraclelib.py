@@ -172,6 +172,11 @@ def refhost():
         L.ref_velocity.argtypes = [C.c_char_p, fp, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int,
                                    C.c_float, C.c_float, C.c_int]
         L.ref_resample.argtypes = [C.c_int, C.c_float, fp, C.c_int, C.c_float, fp]
+        L.ref_segy2trace.argtypes = [C.c_char_p, fp, C.c_int, C.c_int]
+        L.ref_trace2segy.argtypes = [C.c_char_p, fp, C.c_int, C.c_int]
+        L.ref_segy2head.argtypes = [C.c_char_p, ip, C.c_int]
+        L.ref_head2segy.argtypes = [C.c_char_p, ip, C.c_int]
+        L.ref_WriteSGY.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp, fp, C.c_float, C.c_float, fp, C.c_char_p]
         _refhost = L
     return _refhost
 

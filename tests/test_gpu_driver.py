@@ -36,6 +36,7 @@ def test_driver_outputs_match_reference(name):
         stdout = run_driver(wd, "--gpus", "1")
         ups, downs = read_shot_images(case, out)
         final = read_final_image(case, out)
+        sgy = (out / "RVSP_migration_Real.sgy").read_bytes()
         assert "vmin=%f" % g["vrange"][0] in stdout and "nvel=%d" % g["vrange"][2] in stdout
         for m in range(case.nrec):
             assert rel_l2(ups[m], g[f"up_{m}"]) < 2e-3 and rel_l2(downs[m], g[f"down_{m}"]) < 2e-4
@@ -49,6 +50,7 @@ def test_driver_outputs_match_reference(name):
                 assert np.array_equal(ups[m], rups[m]) and np.array_equal(downs[m], rdowns[m])
             if case.ifv == 0:
                 assert np.array_equal(final, read_final_image(case, out), equal_nan=True)
+                assert sgy == (out / "RVSP_migration_Real.sgy").read_bytes()  # WriteSGY, byte for byte
     finally:
         shutil.rmtree(wd, ignore_errors=True)
 
@@ -82,3 +84,29 @@ def test_driver_reports_missing_inputs():
         assert p.returncode != 0 and "cannot open run file" in p.stderr
     finally:
         shutil.rmtree(wd, ignore_errors=True)
+
+
+def test_driver_reads_segy_velocity_model():
+    """The velocity model as a SEG-Y file (IBM floats, one trace per x position) gives the same images
+    as the raw [x][z] float file holding the decoded values."""
+    import struct
+    case = dataclasses.replace(GOLDEN_CASES["tiny_te_compen"], NT1=80, nrec=1, depths=[300.0])
+    vel = velocity_tiny(case)
+    outs = []
+    for as_segy in (False, True):
+        wd = Path(tempfile.mkdtemp(prefix="rtm_drv_"))
+        try:
+            data = {d: data_tiny(case, d) for d in case.depths}
+            out = write_inputs(case, wd, vel, data)
+            if as_segy:
+                bh = bytearray(400)
+                struct.pack_into(">h", bh, 16, 1000); struct.pack_into(">h", bh, 20, case.mod_NZ); struct.pack_into(">h", bh, 24, 1)
+                body = b"".join(bytes(240) + R.segy_encode(vel[i], 1) for i in range(case.mod_NX))
+                (wd / "in" / "vel.sgy").write_bytes(b" " * 3200 + bytes(bh) + body)
+                txt = (wd / "2D_Real_RVSP_RTM.txt").read_text().replace("vel.dat", "vel.sgy")
+                (wd / "2D_Real_RVSP_RTM.txt").write_text(txt)
+            run_driver(wd, "--quiet")
+            outs.append(read_shot_images(case, out))
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+    assert np.array_equal(outs[0][0][0], outs[1][0][0]) and np.array_equal(outs[0][1][0], outs[1][1][0])

@@ -94,7 +94,36 @@ def build_resample(outpath: Path):
     print(f"resample: wrote {outpath}")
 
 
+def segy_test_values():
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.standard_normal(200) * 10.0 ** rng.integers(-30, 30, 200), [0.0, -0.0, 1.0, -1.0, 0.1, 3.4e38,
+                        -3.4e38, 1e-40, 7.2e75 % 1e38, 16.0, 15.999999, 1.0 / 16, 255.5, -4096.25]])
+    return x.astype(np.float32)
+
+
+def build_segy(outpath: Path):
+    """trace2segy / segy2trace (segy.cpp:653-695) for the four sample formats."""
+    import ctypes as C
+    x = segy_test_values()
+    res = {"x": x}
+    for fmt in (1, 2, 3, 5):
+        xin = x if fmt in (1, 5) else np.clip(x, -3e4, 3e4).astype(np.float32)
+        nb = 2 if fmt == 3 else 4
+        buf = C.create_string_buffer(len(xin) * nb)
+        O.refhost().ref_trace2segy(buf, xin.ctypes.data_as(O.fp), len(xin), fmt)
+        back = np.zeros(len(xin), np.float32)
+        O.refhost().ref_segy2trace(buf.raw, back.ctypes.data_as(O.fp), len(xin), fmt)
+        res[f"in_{fmt}"] = xin
+        res[f"bytes_{fmt}"] = np.frombuffer(buf.raw, np.uint8).copy()
+        res[f"back_{fmt}"] = back
+    np.savez_compressed(outpath, **res)
+    print(f"segy: wrote {outpath}")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["segy"]:
+        build_segy(ROOT / "tests" / "golden" / "segy.npz")
+        sys.exit(0)
     if sys.argv[1:] == ["resample"]:
         build_resample(ROOT / "tests" / "golden" / "resample.npz")
         sys.exit(0)
