@@ -182,6 +182,14 @@ int  rtm_segy_write_image(const char *template_path, const char *out_path, const
                           int ns, int dt_value, const float *SX, const float *SY, float RX, float RY,
                           const float *DSR);
 
+/* Post-stack chain (kernel.cu:1110-1179; host-only): D2T / T2D (DisToTimeAndTimeToDis1D.cpp:115, :31)
+ * and phase_correction (phase_correction_ricker_decon.cpp:153).  V, D are [Nx][Nz] (x outer); the
+ * converters return the samples per output trace and write at most cap floats (call with NULL to size). */
+int  rtm_depth_to_time(const float *V, const float *D, int Nx, int Nz, float dz, float dt, float *T, int cap);
+int  rtm_time_to_depth(const float *V, const float *D, int Nx, int Nt, int Nz_V, float dtime, float ddepth,
+                       float *Z, int cap);
+void rtm_phase_rotate(const float *din, float *dout, int ntr, int nt, float angle_deg);
+
 /* Drop-in driver: everything main() does up to the stacked image (kernel.cu:525-1108),
  * reading the reference's input files and writing its output files.
  *   run_file  path of 2D_Real_RVSP_RTM.txt

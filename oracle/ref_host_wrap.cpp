@@ -74,4 +74,14 @@ void ref_WriteSGY(float *Data, int NX, int NT, int tao3, float *SX, float *SY, f
     WriteSGY(Data, NX, NT, tao3, SX, SY, RX, RY, DSR, name);
 }
 
+int ref_D2T(const char *file, float *V, float *D, int Nx, int Nz, int st, int en, float dx, float dz, float dt)
+{
+    return D2T(file, V, D, Nx, Nz, st, en, dx, dz, dt);
+}
+int ref_T2D(const char *file, float *V, float *D, int Nx, int Nz, int Nz_V, int st, int en, float dx, float dz, float dt)
+{
+    return T2D(file, V, D, Nx, Nz, Nz_V, st, en, dx, dz, dt);
+}
+void ref_phase_correction(float *din, float *dout, int ntr, int nt, float angle) { phase_correction(din, dout, ntr, nt, angle); }
+
 } /* extern "C" */

@@ -52,7 +52,8 @@ ABI_SYMBOLS = [
     "rtm_reset_stats", "rtm_device_count", "rtm_store_all_active", "rtm_ricker", "rtm_source_row", "rtm_derived",
     "rtm_pad_velocity", "rtm_velocity_bins", "rtm_taylor_operator", "rtm_ls_operator",
     "rtm_ls_coefficients", "rtm_resample", "rtm_segy_decode", "rtm_segy_encode", "rtm_segy_info",
-    "rtm_segy_read", "rtm_segy_write_image", "rtm_run_driver",
+    "rtm_segy_read", "rtm_segy_write_image", "rtm_depth_to_time", "rtm_time_to_depth", "rtm_phase_rotate",
+    "rtm_run_driver",
 ]
 
 _lib = None
@@ -113,6 +114,10 @@ def lib():
     L.rtm_segy_read.argtypes = [C.c_char_p, _fp, C.c_int, C.c_int]
     L.rtm_segy_write_image.argtypes = [C.c_char_p, C.c_char_p, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp,
                                        C.c_float, C.c_float, _fp]
+    L.rtm_depth_to_time.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, _fp, C.c_int]
+    L.rtm_time_to_depth.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp, C.c_int]
+    L.rtm_phase_rotate.restype = None
+    L.rtm_phase_rotate.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_float]
     L.rtm_run_driver.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
     _lib = L
     return L
@@ -224,6 +229,33 @@ def segy_write_image(template, out_path, data, dt_value, SX, SY, RX, RY, DSR):
     SX, SY, DSR = (np.ascontiguousarray(a, np.float32) for a in (SX, SY, DSR))
     _check(lib().rtm_segy_write_image(str(template).encode(), str(out_path).encode(), _f(data), ntr, ns,
                                       int(dt_value), _f(SX), _f(SY), RX, RY, _f(DSR)))
+
+
+def depth_to_time(V, D, dz, dt):
+    V = np.ascontiguousarray(V, np.float32)
+    D = np.ascontiguousarray(D, np.float32)
+    Nx, Nz = D.shape
+    nt = lib().rtm_depth_to_time(_f(V), _f(D), Nx, Nz, dz, dt, None, 0)
+    T = np.zeros((Nx, max(nt, 0)), np.float32)
+    lib().rtm_depth_to_time(_f(V), _f(D), Nx, Nz, dz, dt, _f(T), T.size)
+    return T
+
+
+def time_to_depth(V, D, Nz_V, dtime, ddepth):
+    V = np.ascontiguousarray(V, np.float32)
+    D = np.ascontiguousarray(D, np.float32)
+    Nx, Nt = D.shape
+    nz = lib().rtm_time_to_depth(_f(V), _f(D), Nx, Nt, Nz_V, dtime, ddepth, None, 0)
+    Z = np.zeros((Nx, max(nz, 0)), np.float32)
+    lib().rtm_time_to_depth(_f(V), _f(D), Nx, Nt, Nz_V, dtime, ddepth, _f(Z), Z.size)
+    return Z
+
+
+def phase_rotate(d, angle_deg):
+    d = np.ascontiguousarray(d, np.float32)
+    out = np.zeros_like(d)
+    lib().rtm_phase_rotate(_f(d), _f(out), d.shape[0], d.shape[1], angle_deg)
+    return out
 
 
 # ------------------------------------------------------------------ engine

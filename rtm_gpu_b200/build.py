@@ -17,7 +17,7 @@ EXE = PKG / "rtm_b200"
 
 CU_SOURCES = ["rtm_engine.cu"]
 CXX_SOURCES = ["host_abi.cpp", "rtm_nccl.cpp", "driver.cpp", "host/fd_operator.cpp", "host/model.cpp",
-               "host/config.cpp", "host/resample.cpp", "host/segy_io.cpp"]
+               "host/config.cpp", "host/resample.cpp", "host/segy_io.cpp", "host/poststack.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-pthread", "--threads", "4"]
 

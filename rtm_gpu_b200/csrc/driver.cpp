@@ -2,8 +2,8 @@
 // windowed image (kernel.cu:525-1108), on the reference's own file surface, with the serial
 // shot loop (kernel.cu:791) replaced by one host thread per GPU, each migrating batches of
 // shots through the C ABI, and the file-based stack (:992-1040) replaced by on-device stacks
-// plus one NCCL reduce.  The post-stack cosmetics (D2T, phase rotation, T2D, SEG-Y export,
-// kernel.cu:1110-1209) are outside the hot path and are not produced (DESIGN.md "Scope").
+// plus one NCCL reduce.  The post-stack stage (D2T, phase rotation, T2D, kernel.cu:1110-1179) and the
+// SEG-Y export (:1181-1209) run on the host after the reduce, as in the reference.
 #include "../../include/rtm_b200.h"
 #include "host/rtm_host.h"
 
@@ -216,6 +216,31 @@ extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int ver
     if (!write_floats(c.Result + "RVSP_Migration_Real_new2.dat", win.data(), win.size()) ||
         !write_floats(c.Result + "vnew.dat", vwin.data(), vwin.size()))
         return rtm_fail(RTM_ERR_IO, "cannot write the stacked image under %s", c.Result.c_str());
+
+    // Post-stack stage (kernel.cu:1110-1179): depth -> time, phase rotation, time -> depth.  The
+    // reference re-reads the two files just written as mod_NX' x mod_NZ arrays (mod_NX' = window
+    // width), whatever was written; the same streams are used here.
+    {
+        const int nxw = c.NX_ED - c.NX_BG;
+        const size_t need = (size_t)nxw * c.mod_NZ;
+        if (win.size() >= need && vwin.size() >= need) {
+            std::vector<float> T, Tp, Z;
+            const int nt = rtm::depth_to_time(vwin.data(), win.data(), nxw, c.mod_NZ, c.hz, c.tao, T);
+            if (verbose) std::printf("nt=%d\n", nt);
+            if (nt > 0) {
+                Tp.resize(T.size());
+                rtm::phase_rotate(T.data(), Tp.data(), nxw, nt, c.angle);
+                const int nz = rtm::time_to_depth(vwin.data(), Tp.data(), nxw, nt, c.mod_NZ, c.tao, c.hz, Z);
+                if (verbose) std::printf("nt=%d\n", nz);
+                if (!write_floats(c.Result + "RVSP_Migration_Real_T.dat", T.data(), T.size()) ||
+                    !write_floats(c.Result + "RVSP_Migration_Real_T_phase.dat", Tp.data(), Tp.size()) ||
+                    !write_floats(c.Result + "RVSP_Migration_Real_D.dat", Z.data(), Z.size()))
+                    return rtm_fail(RTM_ERR_IO, "cannot write the post-stack files under %s", c.Result.c_str());
+            }
+        } else if (verbose) {
+            std::printf("post-stack stage skipped: the output window is shallower than the model\n");
+        }
+    }
 
     // SEG-Y export of the windowed image (kernel.cu:1181-1209, WriteSGY) when the header template
     // the reference requires is present in the working directory

@@ -90,4 +90,11 @@ bool segy_write_image(const char* template_path, const char* out_path, const flo
                       int dt_value, const float* SX, const float* SY, float RX, float RY, const float* DSR,
                       std::string& err);                                              // WriteSGY
 
+// ---------------------------------------------------------------- post-stack chain (kernel.cu:1110-1179)
+// V, D: [Nx][Nz] (x outer).  Return the number of output samples per trace; T/Z: [Nx][n].
+int  depth_to_time(const float* V, const float* D, int Nx, int Nz, float dz, float dt, std::vector<float>& T);   // D2T
+int  time_to_depth(const float* V, const float* D, int Nx, int Nt_in, int Nz_V, float dtime, float ddepth,
+                   std::vector<float>& Z);                                                                      // T2D
+void phase_rotate(const float* din, float* dout, int ntr, int nt, float angle_deg);                             // phase_correction
+
 }  // namespace rtm

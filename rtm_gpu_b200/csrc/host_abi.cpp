@@ -106,3 +106,24 @@ extern "C" int rtm_segy_write_image(const char* template_path, const char* out_p
         return rtm_fail(RTM_ERR_IO, "%s", err.c_str());
     return RTM_OK;
 }
+
+// ---- post-stack chain
+extern "C" int rtm_depth_to_time(const float* V, const float* D, int Nx, int Nz, float dz, float dt, float* T, int cap)
+{
+    std::vector<float> out;
+    const int nt = rtm::depth_to_time(V, D, Nx, Nz, dz, dt, out);
+    if (T) for (size_t i = 0; i < out.size() && i < (size_t)cap; ++i) T[i] = out[i];
+    return nt;
+}
+extern "C" int rtm_time_to_depth(const float* V, const float* D, int Nx, int Nt, int Nz_V, float dtime, float ddepth,
+                                 float* Z, int cap)
+{
+    std::vector<float> out;
+    const int nz = rtm::time_to_depth(V, D, Nx, Nt, Nz_V, dtime, ddepth, out);
+    if (Z) for (size_t i = 0; i < out.size() && i < (size_t)cap; ++i) Z[i] = out[i];
+    return nz;
+}
+extern "C" void rtm_phase_rotate(const float* din, float* dout, int ntr, int nt, float angle_deg)
+{
+    rtm::phase_rotate(din, dout, ntr, nt, angle_deg);
+}

@@ -177,6 +177,9 @@ def refhost():
         L.ref_segy2head.argtypes = [C.c_char_p, ip, C.c_int]
         L.ref_head2segy.argtypes = [C.c_char_p, ip, C.c_int]
         L.ref_WriteSGY.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp, fp, C.c_float, C.c_float, fp, C.c_char_p]
+        L.ref_D2T.argtypes = [C.c_char_p, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+        L.ref_T2D.argtypes = [C.c_char_p, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+        L.ref_phase_correction.argtypes = [fp, fp, C.c_int, C.c_int, C.c_float]
         _refhost = L
     return _refhost
 
