@@ -10,12 +10,28 @@
 // by the reference's own code, tests/test_host_operator.py).
 #include "rtm_host.h"
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <thread>
 #include <vector>
 
 namespace rtm {
 namespace {
+
+// Independent work items on all host cores.  Every item is computed exactly as in the serial
+// code, so results do not depend on the number of threads.
+template <class F> void parallel_for(int n, F f)
+{
+    const int nt = std::max(1, std::min<int>(n, (int)std::thread::hardware_concurrency()));
+    if (nt == 1) { for (int i = 0; i < n; ++i) f(i); return; }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t)
+        pool.emplace_back([&] { for (int i = next++; i < n; i = next++) f(i); });
+    for (auto& th : pool) th.join();
+}
 
 constexpr double kPi = 3.1415926535898;  // the reference's literal (LSMOrCon_rec_2D.cpp:4)
 
@@ -146,8 +162,13 @@ int operator_length(const OperatorSearch& q, double vel, int start_len, std::FIL
     int len = 0, j;
     for (j = start_len; j <= q.nfdmax; ++j) {
         ls_coefficients(c.data(), r, b, j, q.hzx);
-        int k;
-        for (k = 1; k < nfre; ++k) {
+        // the serial loop stops at the first frequency whose error exceeds eps at some angle
+        // n < nthita; whether such a frequency exists does not depend on the order, so all
+        // frequencies are tested concurrently
+        std::atomic<bool> failed(false);
+        parallel_for(nfre - 1, [&](int kk) {
+            if (failed.load(std::memory_order_relaxed)) return;
+            const int k = kk + 1;
             const double rat = 2 / (r * hk[k]);
             int n;
             for (n = 0; n <= q.nthita; ++n) {
@@ -162,10 +183,10 @@ int operator_length(const OperatorSearch& q, double vel, int start_len, std::FIL
                 err        = std::fabs(ra * (1.0 / err - 1.0));
                 if (err > q.eps) break;
             }
-            if (n < q.nthita) break;  // (a failure at exactly n == nthita is not caught, as in the reference)
-        }
+            if (n < q.nthita) failed = true;  // (a failure at exactly n == nthita is not caught, as in the reference)
+        });
         len = j;
-        if (k == nfre) break;
+        if (!failed) break;
     }
     if (j == q.nfdmax + 1 && log) std::fprintf(log, "M=%d is not enough", j);
     return len;
@@ -260,16 +281,16 @@ int build_ls_operator(const OperatorSearch& q, int nvel, double vmin, double dv,
     for (int i = 1; i <= nvel; ++i) Index[i] = Index[i - 1] + M[i - 1] + 1;
     const int NC = Index[nvel];
     c.assign(NC, 0.0f);
-    std::vector<double> cd(q.nfdmax + 1);
     const double rat = q.tao / q.h;
     const double ra  = 2.0 * kPi * q.fmax * q.tao;
-    for (int i = 0; i < nvel; ++i) {
-        if (need[i] != 1) continue;
+    parallel_for(nvel, [&](int i) {  // one least-squares system per used velocity bin
+        if (need[i] != 1) return;
+        std::vector<double> cd(q.nfdmax + 1);
         const double r = (vmin + i) * rat;  // (the reference assumes dv == 1 here, :58)
         const double b = ra / r;
         ls_coefficients(cd.data(), r, b, M[i], q.hzx);
         for (int l = 0; l <= M[i]; ++l) c[l + Index[i]] = (float)cd[l];
-    }
+    });
     return NC;
 }
 
