@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -303,6 +304,11 @@ struct rtm_ctx {
     size_t field_floats = 0;
     size_t smem_fwd = 0, smem_bwd = 0;
     float  last_forward_ms = 0;
+    // The launches of a whole time loop depend only on (loop kind, shots in the batch): they are
+    // captured once into a CUDA graph and replayed for every later batch (one graph launch per
+    // loop instead of NT-2 kernel launches).  Invalidated when the model/operator changes.
+    std::map<long long, cudaGraphExec_t> graphs;
+    bool   use_graphs = true;
     rtm_stats stats{};
 };
 
@@ -347,6 +353,7 @@ extern "C" void rtm_destroy(rtm_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
     cudaFree(c->store);
     for (auto& f : c->field) cudaFree(f);
     for (auto& f : c->acc) cudaFree(f);
@@ -413,6 +420,7 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     G.ntz_f = (G.mod_NZ + kWarps * RTM_NR_F - 1) / (kWarps * RTM_NR_F);
     G.ntz_b = (G.mod_NZ + kWarps * RTM_NR_B - 1) / (kWarps * RTM_NR_B);
     G.nband = (G.NX + kRingTX - 1) / kRingTX; G.nside = (G.mod_NZ + kRingTX - 1) / kRingTX;
+    if (const char* e = std::getenv("RTM_NO_GRAPH")) c->use_graphs = std::atoi(e) == 0;
     G.lead = 0;  // L2 look-ahead prefetch: measured slower on B200 for this access mix (profiles/)
     if (const char* e = std::getenv("RTM_PREFETCH_LEAD")) G.lead = std::atoi(e);
     for (int i = 0; i <= p->N2; ++i) G.w[i] = (float)((1.0 * i) / (1.0 * p->N2));  // :688-691
@@ -488,6 +496,8 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     return RTM_OK;
 }
 
+static void drop_graphs(rtm_ctx* c);
+
 // Side arrays of the adaptive operator (need both the model and the operator table).
 static int prepare_ls(rtm_ctx* c)
 {
@@ -522,6 +532,7 @@ extern "C" int rtm_set_model(rtm_ctx* c, const float* v, float vmin, float vmax,
         CK(cudaStreamSynchronize(c->stream));
     }
     c->have_model = true;
+    drop_graphs(c);
     return prepare_ls(c);
 }
 
@@ -560,6 +571,7 @@ extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const fl
     }
     c->have_op = true;
     c->nvel = nvel;
+    drop_graphs(c);
     return prepare_ls(c);
 }
 
@@ -625,6 +637,33 @@ static int dispatch_bwd(rtm_ctx* c, int ns, int s1, int r1, const BwdArgs& a)
     return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", c->RP);
 }
 
+static void drop_graphs(rtm_ctx* c)
+{
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
+    c->graphs.clear();
+}
+
+// Replay (or capture, the first time) the launches issued by `body` as one CUDA graph.
+template <class Body> static int run_as_graph(rtm_ctx* c, long long key, Body body)
+{
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = body();
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return rtm_fail(RTM_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e2 != cudaSuccess) return rtm_fail(RTM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e2));
+        it = c->graphs.emplace(key, exec).first;
+    }
+    CK(cudaGraphLaunch(it->second, c->stream));
+    return RTM_OK;
+}
+
 static int ensure_strips(rtm_ctx* c)
 {
     if (c->st.up) return RTM_OK;
@@ -688,16 +727,28 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
     if (nsnap) { if (int rc = snapshot(0)) return rc; if (int rc = snapshot(1)) return rc; }
     int NT2;
     rtm_derived(c->p.h, c->p.hz, c->p.tao, c->p.tao, c->p.f0, 2, nullptr, &NT2, nullptr, nullptr, nullptr, nullptr, nullptr);
-    CK(cudaEventRecord(c->ev0, c->stream));
-    for (int k = 2; k < G.NT; ++k) {
+    auto step = [&](int k) -> int {
         FwdArgs a;
         a.P1 = slot(k - 1); a.P0 = slot(k - 2); a.P2 = slot(k);
         a.src = c->d_src;
         a.wavelet = (k < NT2) ? rtm::ricker((k - 1) * c->p.tao, c->p.f0) : 0.0f;  // :812-813
         a.k = k; a.nshots = ns; a.st = st; a.gather = gather;
         a.tma_s0 = use_store ? (k - 1) * c->S : 0;
-        if (int rc = dispatch_fwd(c, ns, use_store ? c->tmap_store : c->tmap_f[(k - 1) % 3], a)) return rc;
-        if (nsnap) if (int rc = snapshot(k)) return rc;
+        return dispatch_fwd(c, ns, use_store ? c->tmap_store : c->tmap_f[(k - 1) % 3], a);
+    };
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (c->use_graphs && nsnap == 0 && G.NT > 3) {
+        if (int rc = step(2)) return rc;  // (also sets the kernel's shared-memory attribute before capture)
+        const long long key = 1 + 2 * (st.up ? 1 : 0) + 4 * (gather ? 1 : 0) + 8 * (use_store ? 1 : 0) + 16LL * ns;
+        if (int rc = run_as_graph(c, key, [&]() -> int {
+                for (int k = 3; k < G.NT; ++k) if (int r = step(k)) return r;
+                return RTM_OK;
+            })) return rc;
+    } else {
+        for (int k = 2; k < G.NT; ++k) {
+            if (int rc = step(k)) return rc;
+            if (nsnap) if (int rc = snapshot(k)) return rc;
+        }
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaGetLastError());
@@ -768,8 +819,7 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
     rtm_derived(c->p.h, c->p.hz, c->p.tao, c->p.tao, c->p.f0, 2, nullptr, &NT2, nullptr, nullptr, nullptr, nullptr, nullptr);
     int r0 = rb[0], r1 = rb[1], r2 = rb[2];
     const size_t slab = (size_t)c->S * G.shot_stride;
-    CK(cudaEventRecord(c->ev0, c->stream));
-    for (int k = G.NT - 3; k >= 0; --k) {
+    auto bstep = [&](int k) -> int {
         BwdArgs a;
         a.Sk = store ? c->store + (size_t)k * slab : nullptr;
         a.S1 = store ? nullptr : c->field[sy]; a.S02 = store ? nullptr : c->field[sx];
@@ -781,6 +831,17 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
         if (int rc = dispatch_bwd(c, ns, store ? r1 : sy, r1, a)) return rc;
         std::swap(sx, sy);
         const int t = r0; r0 = r1; r1 = r2; r2 = t;
+        return RTM_OK;
+    };
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (c->use_graphs && G.NT > 3) {
+        if (int rc = bstep(G.NT - 3)) return rc;
+        if (int rc = run_as_graph(c, 2 + 8 * (store ? 1 : 0) + 16LL * ns, [&]() -> int {
+                for (int k = G.NT - 4; k >= 0; --k) if (int r = bstep(k)) return r;
+                return RTM_OK;
+            })) return rc;
+    } else {
+        for (int k = G.NT - 3; k >= 0; --k) if (int rc = bstep(k)) return rc;
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     // per-shot image post-processing and stacking
