@@ -405,7 +405,7 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     if (G.padL + p->N2 < c->RP) G.padL += 32;  // the TMA box may start left of the first interior column
     G.pitch = (G.padL + G.NX + 4 + 31) / 32 * 32;
     G.shot_stride = (long long)G.NZ * G.pitch;
-    G.nfdmax = p->nfdmax; G.NT = p->NT; G.iLSTE = p->iLSTE; G.iCompen = p->iCompen;
+    G.nfdmax = p->nfdmax; G.mmax = p->nfdmax; G.NT = p->NT; G.iLSTE = p->iLSTE; G.iCompen = p->iCompen;
     G.tao = p->tao; G.h = p->h;
     // derived scalars exactly as kernel.cu:614-626
     G.taoh  = p->tao / p->h;
@@ -469,11 +469,6 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     CKC(cudaMalloc(&c->d_tile_bins_b, sizeof(int2) * G.ntx * G.ntz_b));
     G.bins = c->d_bins; G.tile_bins_f = c->d_tile_bins_f; G.tile_bins_b = c->d_tile_bins_b;
     G.slice_cap = 6144;  // 24 KB of shared memory per CTA for the tile's slice of Index/c
-    for (int i = 0; i < 5; ++i) {
-        int rc = encode_tmap(c, &c->tmap_f[i], c->field[i], kWarps * RTM_NR_F);
-        if (!rc) rc = encode_tmap(c, &c->tmap_b[i], c->field[i], kWarps * RTM_NR_B);
-        if (rc) return fail(rc);
-    }
     if (p->flags & RTM_FLAG_STORE_ALL) {
         // keep the whole forward wavefield when it fits (with 4 GB of head-room for the strips-free
         // rest); otherwise fall back to boundary saving + reverse-time reconstruction
@@ -483,8 +478,6 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
         if (bytes + (4ull << 30) < free_b && (size_t)G.NT * c->S < (1ull << 31)) {
             CKC(cudaMalloc(&c->store, bytes));
             CKC(cudaMemset(c->store, 0, bytes));
-            int rc = encode_tmap(c, &c->tmap_store, c->store, kWarps * RTM_NR_F, (long long)G.NT * c->S);
-            if (rc) return fail(rc);
             c->store_mode = true;
         }
     }
@@ -569,6 +562,22 @@ extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const fl
         G.cc0f = (float)G.cc0TE;
         G.cc0_exact = ((double)G.cc0f == G.cc0TE) ? 1 : 0;
     }
+    // The stencil halo (shared-memory tile, TMA box) is sized by the longest operator that is
+    // actually present, which can be far below nfdmax (e.g. fast models need length 2-3 only).
+    G.mmax = G.nfdmax;
+    if (G.iLSTE == 0) {
+        G.mmax = 1;
+        for (int i = 0; i < nvel; ++i) G.mmax = std::max(G.mmax, Index[i + 1] - Index[i] - 1);
+    }
+    c->RP = (G.mmax + 3) / 4 * 4;
+    for (int i = 0; i < 5; ++i) {
+        int rc = encode_tmap(c, &c->tmap_f[i], c->field[i], kWarps * RTM_NR_F);
+        if (!rc) rc = encode_tmap(c, &c->tmap_b[i], c->field[i], kWarps * RTM_NR_B);
+        if (rc) return rc;
+    }
+    if (c->store_mode)
+        if (int rc = encode_tmap(c, &c->tmap_store, c->store, kWarps * RTM_NR_F, (long long)G.NT * c->S)) return rc;
+    c->smem_fwd = c->smem_bwd = 0;
     c->have_op = true;
     c->nvel = nvel;
     drop_graphs(c);
@@ -580,7 +589,7 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, int ns, const CUten
 {
     const Geo& G = c->G;
     const int nring = 2 * G.nband + 2 * G.nside;
-    size_t smem = std::max((size_t)Tile<RP, RTM_NR_F>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
+    size_t smem = std::max((size_t)Tile<RP, RTM_NR_F>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.mmax) * 4);
     if (smem > c->smem_fwd) {  // per device, once
         CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS, RTM_NR_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->smem_fwd = smem;
@@ -594,7 +603,7 @@ template <int RP, bool LS> static int launch_bwd(rtm_ctx* c, int ns, int s1, int
     if (c->store_mode) {
         const Geo& G = c->G;
         const int nring = 2 * G.nband + 2 * G.nside;
-        size_t smem = std::max((size_t)Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
+        size_t smem = std::max((size_t)Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.mmax) * 4);
         if (smem > c->smem_bwd) {
             CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             c->smem_bwd = smem;
@@ -605,7 +614,7 @@ template <int RP, bool LS> static int launch_bwd(rtm_ctx* c, int ns, int s1, int
     }
     const Geo& G = c->G;
     const int nring = 2 * G.nband + 2 * G.nside;
-    size_t smem = std::max((size_t)2 * Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.nfdmax) * 4);
+    size_t smem = std::max((size_t)2 * Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.mmax) * 4);
     if (smem > c->smem_bwd) {
         CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->smem_bwd = smem;

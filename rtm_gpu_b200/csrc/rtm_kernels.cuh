@@ -46,6 +46,7 @@ struct Geo {
     int   pitch, padL;       // internal row pitch (floats) and left pad: cell (z,x) at z*pitch+padL+x
     long long shot_stride;   // floats between shots of one field buffer
     int   nfdmax;            // strip width; Taylor radius
+    int   mmax;              // longest operator actually present in the model (<= nfdmax): stencil halo
     int   NT;
     int   iLSTE, iCompen;
     float tao2, h2, taoh, taoh2, hzx2_1, vmin, dv;
@@ -268,7 +269,7 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
                                           const float* __restrict__ seis_row, float* smem, Emit emit)
 {
     const RingRect o  = ring_rect(G, tile);
-    const int      NZ = G.NZ, NX = G.NX, N2 = G.N2, R = G.nfdmax, pitch = G.pitch;
+    const int      NZ = G.NZ, NX = G.NX, N2 = G.N2, R = G.mmax, pitch = G.pitch;
     const float*   V  = G.v + G.padL;  // cell (z,x) of the model at V[z*pitch+x]
     // compute rectangle = output grown by 1, clipped
     const int cza = max(o.za - 1, 0), czb = min(o.zb + 1, NZ);
