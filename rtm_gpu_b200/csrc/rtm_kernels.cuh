@@ -151,15 +151,6 @@ __device__ __forceinline__ float vel_factor(const Geo& G, float v)
 {
     return __fmul_rn(__fmul_rn(__fmul_rn(v, v), G.tao2), G.h2);
 }
-// velocity bin of the adaptive operator: (int)((v-vmin)/dv+0.5), (int)(...+1.5)
-__device__ __forceinline__ void ls_lookup(const Geo& G, float v, int& top, int& M)
-{
-    const float  q  = __fdiv_rn(__fsub_rn(v, G.vmin), G.dv);
-    const double qd = (double)q;
-    top             = __ldg(G.Index + __double2int_rz(__dadd_rn(qd, 0.5)));
-    M               = __ldg(G.Index + __double2int_rz(__dadd_rn(qd, 1.5))) - top - 1;
-}
-
 // first term of the stencil sum, w1 = (float)(((1.0+hzx2_1)*c0)*P1) evaluated in double by the
 // reference.  When (1+hzx2_1)*c0 is exactly a float the double product is exact, so a single
 // float multiply rounds identically (no conversions needed).
@@ -177,13 +168,12 @@ __device__ __forceinline__ float w1_first_ls(const Geo& G, float c0, float p1)
 // Two-way update of the cell whose current-field value is *sc in a shared tile of pitch SP.
 template <bool LS>
 __device__ __forceinline__ float two_way_generic(const Geo& G, const float* sc, int SP, float p0,
-                                                 float vv, int sum_kind)
+                                                 float vv, int bin, int sum_kind)
 {
     const float p1 = sc[0];
     float       w1;
     if (LS) {
-        int top, M;
-        ls_lookup(G, vv, top, M);
+        const int top = __ldg(G.Index + bin), M = __ldg(G.Index + bin + 1) - top - 1;  // bin precomputed per cell
         const float* cp = G.c + top;
         w1 = w1_first_ls(G, __ldg(cp), p1);
         for (int l = 1; l <= M; ++l) {
@@ -300,8 +290,9 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
         if (j >= 0 && d != 0.0f) {
             val = d;  // replacement (BKAdd :349-353)
         } else {
-            const float vv = __ldg(V + (size_t)z * pitch + x);
-            val = two_way_generic<LS>(G, s1 + (lz + R) * SP + lx + R, SP, s0[i], vv, sum_kind);
+            const float vv  = __ldg(V + (size_t)z * pitch + x);
+            const int   bin = LS ? (int)__ldg(G.bins + G.padL + (size_t)z * pitch + x) : 0;
+            val = two_way_generic<LS>(G, s1 + (lz + R) * SP + lx + R, SP, s0[i], vv, bin, sum_kind);
         }
         if (inject && z == r_u && x == r_x) val = __fadd_rn(val, wavelet);
         s2[i] = val;
@@ -538,6 +529,12 @@ struct FwdArgs {
 #ifndef RTM_BWD_MINB
 #define RTM_BWD_MINB 3
 #endif
+#ifndef RTM_FWD_MINB_R12
+#define RTM_FWD_MINB_R12 3
+#endif
+#ifndef RTM_BWD_MINB_R12
+#define RTM_BWD_MINB_R12 2
+#endif
 #ifndef RTM_FWD_MINB_LS
 #define RTM_FWD_MINB_LS 3
 #endif
@@ -545,7 +542,7 @@ struct FwdArgs {
 #define RTM_BWD_MINB_LS 2
 #endif
 template <int RP, bool LS, int NR>
-__global__ void __launch_bounds__(kThreads, (RP <= 4 ? (LS ? RTM_FWD_MINB_LS : RTM_FWD_MINB) : (RP <= 8 ? 3 : 2)))
+__global__ void __launch_bounds__(kThreads, (RP <= 4 ? (LS ? RTM_FWD_MINB_LS : RTM_FWD_MINB) : (RP <= 8 ? 3 : RTM_FWD_MINB_R12)))
 fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ Geo G,
                 const FwdArgs a)
 {
@@ -713,7 +710,7 @@ struct BwdArgs {
 // STORE: the source field of slot k is read from the stored forward wavefield instead of being
 // reconstructed (RTM_FLAG_STORE_ALL; not a reference mode).
 template <int RP, bool LS, int NR, bool STORE>
-__global__ void __launch_bounds__(kThreads, (RP <= 4 ? (LS ? RTM_BWD_MINB_LS : RTM_BWD_MINB) : 2))
+__global__ void __launch_bounds__(kThreads, (RP <= 4 ? (LS ? RTM_BWD_MINB_LS : RTM_BWD_MINB) : ((RP <= 8 && !LS) ? 3 : RTM_BWD_MINB_R12)))
 bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmR1,
                 const __grid_constant__ Geo G, const BwdArgs a)
 {

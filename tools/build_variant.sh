@@ -7,7 +7,7 @@ cd rtm_gpu_b200/csrc
 F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-O2,-pthread $defs"
 nvcc $F -c rtm_engine.cu -o /tmp/rtmv_$name/e.o 2>&1 | grep -v warning || true
 objs=/tmp/rtmv_$name/e.o
-for f in host_abi.cpp rtm_nccl.cpp driver.cpp host/fd_operator.cpp host/model.cpp host/config.cpp host/resample.cpp; do
+for f in host_abi.cpp rtm_nccl.cpp driver.cpp host/fd_operator.cpp host/model.cpp host/config.cpp host/resample.cpp host/segy_io.cpp host/poststack.cpp; do
   o=/tmp/rtmv_$name/$(basename $f).o
   [ -f ../build/$(basename $f).o ] && objs="$objs ../build/$(basename $f).o" && continue
   nvcc $F -c $f -o $o; objs="$objs $o"
