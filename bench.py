@@ -151,13 +151,15 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ reference arm (CPU)
-def run_reference_cpu(w: Workload, nproc: int, nt_sample: int):
+def run_reference_cpu(w: Workload, nproc: int, nt_sample: int, binary: str = "ref_cpu_fast"):
     """The reference's own kernels on the host (oracle/_ref/ref_cpu_fast, built from
     /root/reference by oracle/Makefile): one process per shot, `nproc` processes at once,
-    each migrating one shot of the workload's grid with NT = nt_sample time slots."""
+    each migrating one shot of the workload's grid with NT = nt_sample time slots.
+    With binary="ref_cuda" the same procedure times the reference's own CUDA build (one process,
+    one GPU: it is single-GPU and serial over shots)."""
     import dataclasses
     from refcase import REF_DIR, Case, write_inputs
-    exe = REF_DIR / "ref_cpu_fast"
+    exe = REF_DIR / binary
     kind = "reference"
     if not exe.exists():
         return None
@@ -199,6 +201,10 @@ def run_reference_cpu(w: Workload, nproc: int, nt_sample: int):
         return None
     dt = max(dt_full - dt_fixed, 1e-3)
     cu = nproc * (nt_sample - 2) * (2.0 * w.NZ * w.NX + w.mod_NZ * w.mod_NX)
+    if binary == "ref_cuda":
+        return {"value": cu / dt / 1e6, "unit": "Mcell-updates/s", "kind": "reference CUDA build (unmodified kernel.cu, nvcc sm_100a)",
+                "seconds": dt, "sample": f"1 shot, full {w.mod_NX}x{w.mod_NZ} grid, NT={nt_sample} of {w.NT} time slots, whole main(); "
+                                         f"{dt_full:.2f} s minus {dt_fixed:.2f} s fixed cost measured with an empty time loop"}
     return {"value": cu / dt / 1e6, "unit": "Mcell-updates/s", "cores": nproc, "kind": kind, "seconds": dt,
             "sample": f"{nproc} concurrent processes x 1 shot each, full {w.mod_NX}x{w.mod_NZ} grid, NT={nt_sample} of {w.NT} "
                       f"time slots; the reference's own kernels and main() run on the host through oracle/shim "
@@ -407,6 +413,14 @@ def main():
                 "clocks": clocks, "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches)}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_cpu_baseline:
+            try:  # second reported baseline: the reference's own CUDA build on this GPU (after our run)
+                eng.close()
+                rc = run_reference_cpu(w, 1, w.NT, binary="ref_cuda")  # one whole shot of the workload
+                if rc is not None:
+                    line["ref_cuda_baseline"] = rc
+            except Exception as ex:  # noqa: BLE001
+                line["ref_cuda_baseline"] = {"value": None, "unavailable": str(ex)[:200]}
         print(json.dumps(line))
     eng.close()
     if world > 1:
