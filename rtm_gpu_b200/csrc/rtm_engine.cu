@@ -275,14 +275,26 @@ struct rtm_ctx {
     bool       have_model = false, have_op = false;
     float      vmax = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // the tile classes of one time step run concurrently
+    cudaEvent_t  fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
     // device memory
     float* field[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float* acc[4]   = {nullptr, nullptr, nullptr, nullptr};
-    CUtensorMap tmap_f[5], tmap_b[5];  // halo boxes of the forward / backward tile shapes
+    // Interior tiles grouped by the operator length they need (rounded up to 4): every class runs
+    // the kernel template, halo box and register budget of its own radius.  The Taylor operator
+    // has one class holding all tiles (tile lists null).
+    struct TileClass {
+        int  RP = 4;
+        int  n_f = 0, n_b = 0;              // tiles per shot in the forward / backward tiling
+        int *d_tiles_f = nullptr, *d_tiles_b = nullptr;
+        CUtensorMap tmap_f[5], tmap_b[5], tmap_store;
+        size_t smem_f = 0, smem_b = 0;      // dynamic shared memory already granted to the kernels
+    };
+    std::vector<TileClass> classes;
+    std::vector<int> h_M;                   // operator length per velocity bin (adaptive operator)
     // store-all mode (RTM_FLAG_STORE_ALL): every forward time slot stays in HBM, [NT][S][NZ][pitch]
     float* store = nullptr;
-    CUtensorMap tmap_store;
     bool   store_mode = false;
     float* d_v = nullptr;
     float* d_avel = nullptr;
@@ -302,7 +314,6 @@ struct rtm_ctx {
     int*   d_maxbits = nullptr;
     int    stack_shots = 0;
     size_t field_floats = 0;
-    size_t smem_fwd = 0, smem_bwd = 0;
     float  last_forward_ms = 0;
     // The launches of a whole time loop depend only on (loop kind, shots in the batch): they are
     // captured once into a CUDA graph and replayed for every later batch (one graph launch per
@@ -312,7 +323,7 @@ struct rtm_ctx {
     rtm_stats stats{};
 };
 
-static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int tile_rows, long long nslab = 0)
+static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int RP, int tile_rows, long long nslab = 0)
 {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -330,7 +341,7 @@ static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int tile_rows, l
     const Geo& G = c->G;
     cuuint64_t dims[3]    = {(cuuint64_t)G.pitch, (cuuint64_t)G.NZ, (cuuint64_t)(nslab ? nslab : c->S)};
     cuuint64_t strides[2] = {(cuuint64_t)G.pitch * 4, (cuuint64_t)G.shot_stride * 4};
-    cuuint32_t box[3]     = {(cuuint32_t)(kTX + 2 * c->RP), (cuuint32_t)(tile_rows + 2 * c->RP), 1};
+    cuuint32_t box[3]     = {(cuuint32_t)(kTX + 2 * RP), (cuuint32_t)(tile_rows + 2 * RP), 1};
     cuuint32_t estr[3]    = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -354,6 +365,7 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
+    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); }
     cudaFree(c->store);
     for (auto& f : c->field) cudaFree(f);
     for (auto& f : c->acc) cudaFree(f);
@@ -366,6 +378,9 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evA) cudaEventDestroy(c->evA);
     if (c->evB) cudaEventDestroy(c->evB);
+    for (auto& a : c->aux) if (a) cudaStreamDestroy(a);
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+    for (auto& e : c->join_ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -421,8 +436,6 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     G.ntz_b = (G.mod_NZ + kWarps * RTM_NR_B - 1) / (kWarps * RTM_NR_B);
     G.nband = (G.NX + kRingTX - 1) / kRingTX; G.nside = (G.mod_NZ + kRingTX - 1) / kRingTX;
     if (const char* e = std::getenv("RTM_NO_GRAPH")) c->use_graphs = std::atoi(e) == 0;
-    G.lead = 0;  // L2 look-ahead prefetch: measured slower on B200 for this access mix (profiles/)
-    if (const char* e = std::getenv("RTM_PREFETCH_LEAD")) G.lead = std::atoi(e);
     for (int i = 0; i <= p->N2; ++i) G.w[i] = (float)((1.0 * i) / (1.0 * p->N2));  // :688-691
 
     auto fail = [&](int rc) { rtm_destroy(c); return rc; };
@@ -434,6 +447,9 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
                                  cudaGetErrorString(e_), __FILE__, __LINE__));                 \
     } while (0)
     CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& a : c->aux) CKC(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+    for (auto& e : c->join_ev) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CKC(cudaEventCreate(&c->ev0));
     CKC(cudaEventCreate(&c->ev1));
     CKC(cudaEventCreate(&c->evA));
@@ -492,9 +508,12 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
 static void drop_graphs(rtm_ctx* c);
 
 // Side arrays of the adaptive operator (need both the model and the operator table).
+static int prepare_classes(rtm_ctx* c);
+
 static int prepare_ls(rtm_ctx* c)
 {
-    if (c->G.iLSTE != 0 || !c->have_model || !c->have_op) return RTM_OK;
+    if (c->G.iLSTE != 0) return c->have_op ? prepare_classes(c) : RTM_OK;
+    if (!c->have_model || !c->have_op) return RTM_OK;
     const Geo& G = c->G;
     if (c->nvel > 65535)
         return rtm_fail(RTM_ERR_ARG, "adaptive operator with %d velocity bins: the per-cell bin array is 16-bit, use a larger dv", c->nvel);
@@ -504,6 +523,52 @@ static int prepare_ls(rtm_ctx* c)
     tile_bins_kernel<<<G.ntx * G.ntz_b, 256, 0, c->stream>>>(c->d_bins, G, kWarps * RTM_NR_B, G.ntx, c->d_tile_bins_b);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
+    return prepare_classes(c);
+}
+
+// Group the interior tiles by the radius class they need and encode the TMA boxes per class.
+static int prepare_classes(rtm_ctx* c)
+{
+    const Geo& G = c->G;
+    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); }
+    c->classes.clear();
+    const int nf = G.ntx * G.ntz_f, nb = G.ntx * G.ntz_b;
+    std::map<int, std::pair<std::vector<int>, std::vector<int>>> lists;  // RP -> (forward tiles, backward tiles)
+    if (G.iLSTE != 0) {
+        lists[c->RP];  // one class, all tiles
+    } else {
+        std::vector<int2> tb(std::max(nf, nb));
+        for (int pass = 0; pass < 2; ++pass) {
+            const int n = pass ? nb : nf;
+            CK(cudaMemcpy(tb.data(), pass ? c->d_tile_bins_b : c->d_tile_bins_f, sizeof(int2) * n, cudaMemcpyDeviceToHost));
+            for (int t = 0; t < n; ++t) {
+                int m = 1;
+                for (int b = std::max(tb[t].x, 0); b <= tb[t].y && b < (int)c->h_M.size(); ++b) m = std::max(m, c->h_M[b]);
+                auto& l = lists[(m + 3) / 4 * 4];
+                (pass ? l.second : l.first).push_back(t);
+            }
+        }
+    }
+    for (auto it = lists.rbegin(); it != lists.rend(); ++it) {  // longest operators first
+        rtm_ctx::TileClass k;
+        k.RP = it->first;
+        if (G.iLSTE != 0) { k.n_f = nf; k.n_b = nb; }
+        else {
+            k.n_f = (int)it->second.first.size(); k.n_b = (int)it->second.second.size();
+            // (a class that holds every tile needs no list: the kernel then uses the tile number itself)
+            if (k.n_f && k.n_f < nf) { CK(cudaMalloc(&k.d_tiles_f, sizeof(int) * k.n_f)); CK(cudaMemcpy(k.d_tiles_f, it->second.first.data(), sizeof(int) * k.n_f, cudaMemcpyHostToDevice)); }
+            if (k.n_b && k.n_b < nb) { CK(cudaMalloc(&k.d_tiles_b, sizeof(int) * k.n_b)); CK(cudaMemcpy(k.d_tiles_b, it->second.second.data(), sizeof(int) * k.n_b, cudaMemcpyHostToDevice)); }
+        }
+        for (int i = 0; i < 5; ++i) {
+            int rc = encode_tmap(c, &k.tmap_f[i], c->field[i], k.RP, kWarps * RTM_NR_F);
+            if (!rc) rc = encode_tmap(c, &k.tmap_b[i], c->field[i], k.RP, kWarps * RTM_NR_B);
+            if (rc) return rc;
+        }
+        if (c->store_mode)
+            if (int rc = encode_tmap(c, &k.tmap_store, c->store, k.RP, kWarps * RTM_NR_F, (long long)G.NT * c->S)) return rc;
+        c->classes.push_back(k);
+    }
+    CK(cudaDeviceSynchronize());
     return RTM_OK;
 }
 
@@ -570,14 +635,11 @@ extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const fl
         for (int i = 0; i < nvel; ++i) G.mmax = std::max(G.mmax, Index[i + 1] - Index[i] - 1);
     }
     c->RP = (G.mmax + 3) / 4 * 4;
-    for (int i = 0; i < 5; ++i) {
-        int rc = encode_tmap(c, &c->tmap_f[i], c->field[i], kWarps * RTM_NR_F);
-        if (!rc) rc = encode_tmap(c, &c->tmap_b[i], c->field[i], kWarps * RTM_NR_B);
-        if (rc) return rc;
+    c->h_M.clear();
+    if (G.iLSTE == 0) {
+        c->h_M.resize(nvel);
+        for (int i = 0; i < nvel; ++i) c->h_M[i] = Index[i + 1] - Index[i] - 1;
     }
-    if (c->store_mode)
-        if (int rc = encode_tmap(c, &c->tmap_store, c->store, kWarps * RTM_NR_F, (long long)G.NT * c->S)) return rc;
-    c->smem_fwd = c->smem_bwd = 0;
     c->have_op = true;
     c->nvel = nvel;
     drop_graphs(c);
@@ -585,65 +647,90 @@ extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const fl
 }
 
 // ------------------------------------------------------------------------------------ launches
-template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, int ns, const CUtensorMap& tm, const FwdArgs& a)
+// One launch = the interior tiles of one class (+ the ring tiles when do_ring).
+template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int buf, FwdArgs a)
 {
     const Geo& G = c->G;
-    const int nring = 2 * G.nband + 2 * G.nside;
-    size_t smem = std::max((size_t)Tile<RP, RTM_NR_F>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.mmax) * 4);
-    if (smem > c->smem_fwd) {  // per device, once
+    const int nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0;
+    size_t smem = (size_t)Tile<RP, RTM_NR_F>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0);
+    if (a.do_ring) smem = std::max(smem, (size_t)ring_smem_floats(G.N2, G.mmax) * 4);
+    if (smem > k.smem_f) {  // per device, once
         CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS, RTM_NR_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c->smem_fwd = smem;
+        k.smem_f = smem;
     }
-    dim3 grid((unsigned)((nring + G.ntx * G.ntz_f) * ns));
-    fwd_step_kernel<RP, LS, RTM_NR_F><<<grid, kThreads, smem, c->stream>>>(tm, G, a);
+    a.tiles = k.d_tiles_f; a.ntiles = k.n_f;
+    dim3 grid((unsigned)((nring + k.n_f) * ns));
+    if (grid.x == 0) return RTM_OK;
+    fwd_step_kernel<RP, LS, RTM_NR_F><<<grid, kThreads, smem, st>>>(buf < 0 ? k.tmap_store : k.tmap_f[buf], G, a);
     return RTM_OK;
 }
-template <int RP, bool LS> static int launch_bwd(rtm_ctx* c, int ns, int s1, int r1, const BwdArgs& a)
+template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, BwdArgs a)
 {
-    if (c->store_mode) {
-        const Geo& G = c->G;
-        const int nring = 2 * G.nband + 2 * G.nside;
-        size_t smem = std::max((size_t)Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.mmax) * 4);
-        if (smem > c->smem_bwd) {
-            CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            c->smem_bwd = smem;
-        }
-        dim3 grid((unsigned)((nring + G.ntx * G.ntz_b) * ns));
-        bwd_step_kernel<RP, LS, RTM_NR_B, true><<<grid, kThreads, smem, c->stream>>>(c->tmap_b[r1], c->tmap_b[r1], G, a);
-        return RTM_OK;
-    }
     const Geo& G = c->G;
-    const int nring = 2 * G.nband + 2 * G.nside;
-    size_t smem = std::max((size_t)2 * Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0), (size_t)ring_smem_floats(G.N2, G.mmax) * 4);
-    if (smem > c->smem_bwd) {
-        CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c->smem_bwd = smem;
+    const int nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0;
+    size_t smem = (size_t)(STORE ? 1 : 2) * Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0);
+    if (a.do_ring) smem = std::max(smem, (size_t)ring_smem_floats(G.N2, G.mmax) * 4);
+    if (smem > k.smem_b) {
+        CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k.smem_b = smem;
     }
-    dim3 grid((unsigned)((nring + G.ntx * G.ntz_b) * ns));
-    bwd_step_kernel<RP, LS, RTM_NR_B, false><<<grid, kThreads, smem, c->stream>>>(c->tmap_b[s1], c->tmap_b[r1], G, a);
+    a.tiles = k.d_tiles_b; a.ntiles = k.n_b;
+    dim3 grid((unsigned)((nring + k.n_b) * ns));
+    if (grid.x == 0) return RTM_OK;
+    bwd_step_kernel<RP, LS, RTM_NR_B, STORE><<<grid, kThreads, smem, st>>>(k.tmap_b[STORE ? r1 : s1], k.tmap_b[r1], G, a);
     return RTM_OK;
 }
-static int dispatch_fwd(rtm_ctx* c, int ns, const CUtensorMap& cur, const FwdArgs& a)
+// The classes of one time step touch disjoint cells: they are forked onto side streams so that
+// small classes share the GPU with the large ones, and joined before the next step.
+template <class Launch> static int fork_join(rtm_ctx* c, Launch launch)
+{
+    const int n = (int)c->classes.size();
+    if (n > 1) {
+        CK(cudaEventRecord(c->fork_ev, c->stream));
+        for (int i = 1; i < n && i <= 3; ++i) CK(cudaStreamWaitEvent(c->aux[i - 1], c->fork_ev, 0));
+    }
+    for (int i = 0; i < n; ++i) {
+        cudaStream_t st = (i >= 1 && i <= 3) ? c->aux[i - 1] : c->stream;
+        if (int rc = launch(c->classes[i], st, i == 0)) return rc;
+    }
+    for (int i = 1; i < n && i <= 3; ++i) {
+        CK(cudaEventRecord(c->join_ev[i - 1], c->aux[i - 1]));
+        CK(cudaStreamWaitEvent(c->stream, c->join_ev[i - 1], 0));
+    }
+    return RTM_OK;
+}
+// buf: index of the field buffer holding slot k-1, or -1 for the store-all slab
+static int dispatch_fwd(rtm_ctx* c, int ns, int buf, FwdArgs a)
 {
     const bool ls = c->G.iLSTE == 0;
-    switch (c->RP) {
-    case 4:  return ls ? launch_fwd<4, true>(c, ns, cur, a) : launch_fwd<4, false>(c, ns, cur, a);
-    case 8:  return ls ? launch_fwd<8, true>(c, ns, cur, a) : launch_fwd<8, false>(c, ns, cur, a);
-    case 12: return ls ? launch_fwd<12, true>(c, ns, cur, a) : launch_fwd<12, false>(c, ns, cur, a);
-    case 16: return ls ? launch_fwd<16, true>(c, ns, cur, a) : launch_fwd<16, false>(c, ns, cur, a);
-    }
-    return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", c->RP);
+    return fork_join(c, [&](rtm_ctx::TileClass& k, cudaStream_t st, bool first) -> int {
+        a.do_ring = first ? 1 : 0;
+        switch (k.RP) {
+        case 4:  return ls ? launch_fwd<4, true>(c, k, st, ns, buf, a) : launch_fwd<4, false>(c, k, st, ns, buf, a);
+        case 8:  return ls ? launch_fwd<8, true>(c, k, st, ns, buf, a) : launch_fwd<8, false>(c, k, st, ns, buf, a);
+        case 12: return ls ? launch_fwd<12, true>(c, k, st, ns, buf, a) : launch_fwd<12, false>(c, k, st, ns, buf, a);
+        case 16: return ls ? launch_fwd<16, true>(c, k, st, ns, buf, a) : launch_fwd<16, false>(c, k, st, ns, buf, a);
+        }
+        return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", k.RP);
+    });
+}
+template <bool STORE> static int dispatch_bwd_t(rtm_ctx* c, int ns, int s1, int r1, BwdArgs a)
+{
+    const bool ls = c->G.iLSTE == 0;
+    return fork_join(c, [&](rtm_ctx::TileClass& k, cudaStream_t st, bool first) -> int {
+        a.do_ring = first ? 1 : 0;
+        switch (k.RP) {
+        case 4:  return ls ? launch_bwd<4, true, STORE>(c, k, st, ns, s1, r1, a) : launch_bwd<4, false, STORE>(c, k, st, ns, s1, r1, a);
+        case 8:  return ls ? launch_bwd<8, true, STORE>(c, k, st, ns, s1, r1, a) : launch_bwd<8, false, STORE>(c, k, st, ns, s1, r1, a);
+        case 12: return ls ? launch_bwd<12, true, STORE>(c, k, st, ns, s1, r1, a) : launch_bwd<12, false, STORE>(c, k, st, ns, s1, r1, a);
+        case 16: return ls ? launch_bwd<16, true, STORE>(c, k, st, ns, s1, r1, a) : launch_bwd<16, false, STORE>(c, k, st, ns, s1, r1, a);
+        }
+        return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", k.RP);
+    });
 }
 static int dispatch_bwd(rtm_ctx* c, int ns, int s1, int r1, const BwdArgs& a)
 {
-    const bool ls = c->G.iLSTE == 0;
-    switch (c->RP) {
-    case 4:  return ls ? launch_bwd<4, true>(c, ns, s1, r1, a) : launch_bwd<4, false>(c, ns, s1, r1, a);
-    case 8:  return ls ? launch_bwd<8, true>(c, ns, s1, r1, a) : launch_bwd<8, false>(c, ns, s1, r1, a);
-    case 12: return ls ? launch_bwd<12, true>(c, ns, s1, r1, a) : launch_bwd<12, false>(c, ns, s1, r1, a);
-    case 16: return ls ? launch_bwd<16, true>(c, ns, s1, r1, a) : launch_bwd<16, false>(c, ns, s1, r1, a);
-    }
-    return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", c->RP);
+    return c->store_mode ? dispatch_bwd_t<true>(c, ns, s1, r1, a) : dispatch_bwd_t<false>(c, ns, s1, r1, a);
 }
 
 static void drop_graphs(rtm_ctx* c)
@@ -743,7 +830,7 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
         a.wavelet = (k < NT2) ? rtm::ricker((k - 1) * c->p.tao, c->p.f0) : 0.0f;  // :812-813
         a.k = k; a.nshots = ns; a.st = st; a.gather = gather;
         a.tma_s0 = use_store ? (k - 1) * c->S : 0;
-        return dispatch_fwd(c, ns, use_store ? c->tmap_store : c->tmap_f[(k - 1) % 3], a);
+        return dispatch_fwd(c, ns, use_store ? -1 : (k - 1) % 3, a);
     };
     CK(cudaEventRecord(c->ev0, c->stream));
     if (c->use_graphs && nsnap == 0 && G.NT > 3) {
@@ -768,7 +855,7 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
     c->stats.cell_updates += cu;
     c->stats.algorithmic_bytes += cu * 16.0;
     c->stats.forward_seconds += ms * 1e-3;
-    c->stats.kernel_launches += G.NT - 2 + 3;
+    c->stats.kernel_launches += (long)(G.NT - 2) * (long)c->classes.size() + 3;
     c->last_forward_ms = ms;
     *last1 = slot(G.NT - 1); *last0 = slot(G.NT - 2);
     return RTM_OK;
@@ -876,7 +963,7 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
     c->stats.backward_seconds += ms * 1e-3;
     CK(cudaEventElapsedTime(&ms, c->evA, c->evB));
     c->stats.device_seconds += ms * 1e-3;  // whole batch: init, both loops, image post, stack
-    c->stats.kernel_launches += G.NT - 2 + 4;
+    c->stats.kernel_launches += (long)(G.NT - 2) * (long)c->classes.size() + 4;
     c->stats.shots += ns;
     c->stack_shots += ns;
     return RTM_OK;

@@ -56,7 +56,6 @@ struct Geo {
     // tiling
     int   ntx, ntz_f, ntz_b; // interior tiles (forward / backward kernels use different tile heights)
     int   nband, nside;      // ring tiles per band (top/bottom) and per side (left/right)
-    int   lead;              // interior tiles of look-ahead for the L2 prefetch (0 = off)
     // operator
     const float* c;          // LS: packed table; TE: unused
     const int*   Index;
@@ -120,18 +119,6 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
         "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(x), "r"(z), "r"(s)
         : "memory");
-}
-
-// L2 prefetch of data a later CTA will need (no SM resources are held while it is in flight)
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, int z, int s)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"((uint64_t)map),
-                 "r"(x), "r"(z), "r"(s)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // ------------------------------------------------------------------ exact arithmetic
@@ -519,6 +506,9 @@ struct FwdArgs {
     int          k;    // time slot being produced
     int          nshots;
     int          tma_s0;  // offset of shot 0 along the tensor map's 3rd dimension (store-all: slot*S)
+    const int*   tiles;   // interior tiles of this launch (null: all tiles 0..ntiles-1)
+    int          ntiles;  // interior tiles per shot in this launch
+    int          do_ring; // this launch also carries the ring tiles
     Strips       st;   // may hold nulls when strips are not wanted (pure modelling)
     float*       gather;  // [S][NT][n] time-major, or null
 };
@@ -549,7 +539,9 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // 1-D grid: the ring tiles of ALL shots first (they are the longest-running CTAs and would
     // otherwise form the tail of the launch), then the interior tiles shot by shot.
-    const int  nring = 2 * G.nband + 2 * G.nside, nint = G.ntx * G.ntz_f;
+    // A time step may be split into several launches, one per operator-length class of the
+    // interior tiles (adaptive operator): each carries its own tile list; one of them the ring.
+    const int  nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0, nint = a.ntiles;
     const bool is_ring = (int)blockIdx.x < a.nshots * nring;
     const int  bi   = is_ring ? blockIdx.x : blockIdx.x - a.nshots * nring;
     const int  shot = is_ring ? bi / nring : bi / nint;
@@ -586,7 +578,7 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
     }
 
     // ---- interior tile
-    const int t   = bi % nint;
+    const int t   = a.tiles ? a.tiles[bi % nint] : bi % nint;
     const int tz  = t / G.ntx, tx = t % G.ntx;
     const int z0  = G.N2 + tz * (kWarps * NR), x0 = G.N2 + tx * kTX;  // first interior cell of the tile
     float*    sP  = reinterpret_cast<float*>(smem_raw);
@@ -600,23 +592,6 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
         tma_load_3d(sP, &tmP1, bar, G.padL + x0 - RP, z0 - RP, a.tma_s0 + shot);
     }
     const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
-    if (G.lead > 0) {
-        // Pull the inputs of the interior tile that runs `lead` tiles after this one into L2:
-        // its DRAM latency is then paid by nobody (the SM holds no registers or smem for it).
-        const int ntile = G.ntx * G.ntz_f;
-        const int L2i = shot * ntile + t + G.lead;
-        if (L2i < a.nshots * ntile) {
-            const int ps = L2i / ntile, pt = L2i % ntile;
-            const int pz0 = G.N2 + (pt / G.ntx) * (kWarps * NR), px0 = G.N2 + (pt % G.ntx) * kTX;
-            if (tid == 32) tma_prefetch_3d(&tmP1, G.padL + px0 - RP, pz0 - RP, a.tma_s0 + ps);
-            if (tid >= 64 && tid < 64 + kWarps * NR && pz0 + tid - 64 < zend) {
-                const size_t po = (long long)ps * G.shot_stride + (size_t)(pz0 + tid - 64) * G.pitch + G.padL + px0;
-                const uint32_t bytes = 4u * (uint32_t)min(kTX, G.pitch - G.padL - px0);
-                bulk_prefetch_l2(a.P0 + po, bytes);
-            }
-        }
-    }
-
     LsTable T{};
     if (LS) {  // this tile's slice of the operator table -> shared memory (behind the halo tile)
         T = ls_stage_slice(G, G.tile_bins_f[t], reinterpret_cast<int*>(smem_raw + Tile<RP, NR>::BYTES + 16));
@@ -702,6 +677,9 @@ struct BwdArgs {
     float        wavelet;
     int          k;
     int          nshots;
+    const int*   tiles;   // interior tiles of this launch (null: all tiles 0..ntiles-1)
+    int          ntiles;
+    int          do_ring;
     Strips       st;
     const float* seis;  // [S][NT][n] time-major; row k+1 is imposed
     float *sumS, *sumR, *rel1, *rel2;  // accumulators, field layout
@@ -715,7 +693,7 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
                 const __grid_constant__ Geo G, const BwdArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int  nring = 2 * G.nband + 2 * G.nside, nint = G.ntx * G.ntz_b;
+    const int  nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0, nint = a.ntiles;
     const bool is_ring = (int)blockIdx.x < a.nshots * nring;
     const int  bi   = is_ring ? blockIdx.x : blockIdx.x - a.nshots * nring;
     const int  shot = is_ring ? bi / nring : bi / nint;
@@ -747,7 +725,7 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
         return;
     }
 
-    const int t   = bi % nint;
+    const int t   = a.tiles ? a.tiles[bi % nint] : bi % nint;
     const int tz  = t / G.ntx, tx = t % G.ntx;
     const int z0  = G.N2 + tz * (kWarps * NR), x0 = G.N2 + tx * kTX;
     constexpr int NTILE = STORE ? 1 : 2;  // halo tiles in shared memory
@@ -764,25 +742,6 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
         tma_load_3d(sR, &tmR1, bar, G.padL + x0 - RP, z0 - RP, shot);
     }
     const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
-    if (G.lead > 0) {  // L2 prefetch for the interior tile `lead` tiles ahead (see fwd_step_kernel)
-        const int ntile = G.ntx * G.ntz_b;
-        const int L2i = shot * ntile + t + G.lead;
-        if (L2i < a.nshots * ntile) {
-            const int ps = L2i / ntile, pt = L2i % ntile;
-            const int pz0 = G.N2 + (pt / G.ntx) * (kWarps * NR), px0 = G.N2 + (pt % G.ntx) * kTX;
-            if (tid == 0) tma_prefetch_3d(&tmS1, G.padL + px0 - RP, pz0 - RP, ps);
-            if (tid == 1) tma_prefetch_3d(&tmR1, G.padL + px0 - RP, pz0 - RP, ps);
-            const int row = tid & 31, stream = tid >> 5;  // 8 warps: 6 plain streams (+2 idle)
-            if (row < kWarps * NR && pz0 + row < zend && stream < (G.iCompen == 1 ? 6 : 4)) {
-                const size_t po = (long long)ps * G.shot_stride + (size_t)(pz0 + row) * G.pitch + G.padL + px0;
-                const uint32_t bytes = 4u * (uint32_t)min(kTX, G.pitch - G.padL - px0);
-                const float* base = stream == 0 ? a.S02 : stream == 1 ? a.R0 : stream == 2 ? a.rel1
-                                  : stream == 3 ? a.rel2 : stream == 4 ? a.sumS : a.sumR;
-                bulk_prefetch_l2(base + po, bytes);
-            }
-        }
-    }
-
     LsTable T{};
     if (LS) {
         T = ls_stage_slice(G, G.tile_bins_b[t], reinterpret_cast<int*>(smem_raw + NTILE * Tile<RP, NR>::BYTES + 16));
