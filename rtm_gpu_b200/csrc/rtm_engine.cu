@@ -484,7 +484,6 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     CKC(cudaMalloc(&c->d_tile_bins_f, sizeof(int2) * G.ntx * G.ntz_f));
     CKC(cudaMalloc(&c->d_tile_bins_b, sizeof(int2) * G.ntx * G.ntz_b));
     G.bins = c->d_bins; G.tile_bins_f = c->d_tile_bins_f; G.tile_bins_b = c->d_tile_bins_b;
-    G.slice_cap = 6144;  // 24 KB of shared memory per CTA for the tile's slice of Index/c
     if (p->flags & RTM_FLAG_STORE_ALL) {
         // keep the whole forward wavefield when it fits (with 4 GB of head-room for the strips-free
         // rest); otherwise fall back to boundary saving + reverse-time reconstruction
@@ -652,7 +651,7 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass&
 {
     const Geo& G = c->G;
     const int nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0;
-    size_t smem = (size_t)Tile<RP, RTM_NR_F>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0);
+    size_t smem = (size_t)Tile<RP, RTM_NR_F>::BYTES + 16 + (LS ? (size_t)slice_bytes(RP) : 0);
     if (a.do_ring) smem = std::max(smem, (size_t)ring_smem_floats(G.N2, G.mmax) * 4);
     if (smem > k.smem_f) {  // per device, once
         CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS, RTM_NR_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -668,7 +667,7 @@ template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx
 {
     const Geo& G = c->G;
     const int nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0;
-    size_t smem = (size_t)(STORE ? 1 : 2) * Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)G.slice_cap * 4 : 0);
+    size_t smem = (size_t)(STORE ? 1 : 2) * Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)slice_bytes(RP) : 0);
     if (a.do_ring) smem = std::max(smem, (size_t)ring_smem_floats(G.N2, G.mmax) * 4);
     if (smem > k.smem_b) {
         CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

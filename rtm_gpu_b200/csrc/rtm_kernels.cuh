@@ -38,6 +38,8 @@ constexpr int kTX      = 128;  // interior tile width  (32 lanes x float4)
 constexpr int kWarps   = kThreads / 32;
 constexpr int kRingTX  = 128;  // ring tile extent along the band
 constexpr int kMaxR    = 16;
+constexpr int kSliceBins = 768;  // velocity bins whose coefficient rows a tile can stage in shared memory
+__host__ __device__ constexpr int slice_bytes(int RP) { return RP >= 8 ? 24576 : kSliceBins * (RP + 5) * 4; }
 
 enum SumKind { SUM_FLOAT = 0, SUM_DOUBLE = 1 };
 
@@ -70,7 +72,6 @@ struct Geo {
     const unsigned short* bins;   // [NZ][pitch]
     const int2* tile_bins_f;      // [ntz_f*ntx] (min bin, max bin) of each forward interior tile
     const int2* tile_bins_b;      // [ntz_b*ntx]
-    int    slice_cap;             // words of shared memory available for the Index/c slice
     const float* v;          // [NZ][pitch], shared by all shots
     float  w[65];            // blend weights l/N2
 };
@@ -367,41 +368,65 @@ __device__ __forceinline__ void unpack(const float4& a, float (&o)[4])
     o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
 }
 
-// Stencil sums w1 of four x-adjacent cells of one row.  `sc` points at the first of the four
-// cells inside the shared tile.  x neighbours: the row segment [x-RP, x+3+RP] as float4 shared
-// loads; z neighbours: one float4 shared load per row offset (all four cells share it), which
-// keeps the register footprint small enough for 3-4 resident CTAs per SM.
-// M <= RP is the uniform length of the Taylor operator; the adaptive operator brings a length
-// and table offset per cell.
-// Operator-table access of the adaptive path for one interior tile: `ip[bin]` is the packed
-// offset of a bin, `cp[offset]` a coefficient.  Both point either at the tile's slice staged in
-// shared memory (biased so that global bin numbers / offsets index them directly) or at the
-// global tables when the slice does not fit.
+// Operator table of the adaptive path for one interior tile.  Normal case ("rows"): the
+// coefficient rows of the tile's bins [bmin,bmax] are staged in shared memory, zero-padded to a
+// fixed stride of RP+4 floats (16-byte aligned, so a cell fetches its coefficients with float4
+// loads and no Index lookups), next to one length per bin.  Fallback (slice larger than the
+// shared-memory budget, e.g. a salt flank crossing the tile): the packed global tables.
 struct LsTable {
-    const int*   ip;
-    const float* cp;
+    const float* rows;   // shared: [(bmax-bmin+1)][RP+4]
+    const int*   len;    // shared: [(bmax-bmin+1)]
+    const int*   ip;     // fallback: global Index
+    const float* cp;     // fallback: global c
     int bmin, bmax;
+    bool staged;
 };
 
-// Stage Index[bmin..bmax+1] and c[Index[bmin]..Index[bmax+1]) of this tile into shared memory.
 // Called by all threads of the CTA; the caller synchronises afterwards.
-__device__ __forceinline__ LsTable ls_stage_slice(const Geo& G, int2 tb, int* smem_words)
+template <int RP>
+__device__ __forceinline__ LsTable ls_stage_slice(const Geo& G, int2 tb, float* smem_words)
 {
+    constexpr int STRIDE = RP + 4;
     LsTable T;
     T.bmin = tb.x; T.bmax = tb.y;
-    const int nI = tb.y - tb.x + 2;
-    const int cBeg = __ldg(G.Index + tb.x), cEnd = __ldg(G.Index + tb.y + 1);
-    const int nC = cEnd - cBeg;
-    if (nI + nC <= G.slice_cap) {
-        int*   sI = smem_words;
-        float* sC = reinterpret_cast<float*>(smem_words + nI);
-        for (int i = threadIdx.x; i < nI; i += kThreads) sI[i] = __ldg(G.Index + tb.x + i);
-        for (int i = threadIdx.x; i < nC; i += kThreads) sC[i] = __ldg(G.c + cBeg + i);
-        T.ip = sI - tb.x;
-        T.cp = sC - cBeg;
-    } else {
-        T.ip = G.Index;
-        T.cp = G.c;
+    T.ip = G.Index; T.cp = G.c;
+    const int nb = tb.y - tb.x + 1;
+    T.rows = smem_words;
+    T.len  = nullptr;
+    T.staged = false;
+    if (RP >= 8) {
+        // long operators: padded rows would mostly hold zeros; stage the packed slice instead
+        // (Index[bmin..bmax+1] and c[Index[bmin]..Index[bmax+1])), addressed like the global tables
+        const int nI = nb + 1;
+        const int cBeg = __ldg(G.Index + tb.x), nC = __ldg(G.Index + tb.y + 1) - cBeg;
+        if (nI + nC <= slice_bytes(RP) / 4) {
+            int*   sI = reinterpret_cast<int*>(smem_words);
+            float* sC = smem_words + nI;
+            for (int i = threadIdx.x; i < nI; i += kThreads) sI[i] = __ldg(G.Index + tb.x + i);
+            for (int i = threadIdx.x; i < nC; i += kThreads) sC[i] = __ldg(G.c + cBeg + i);
+            T.ip = sI - tb.x;
+            T.cp = sC - cBeg;
+        }
+        return T;
+    }
+    T.staged = nb <= kSliceBins;
+    T.len  = reinterpret_cast<const int*>(smem_words + nb * STRIDE);
+    if (T.staged) {
+        int* sl = reinterpret_cast<int*>(smem_words + nb * STRIDE);
+        for (int r = threadIdx.x; r < nb; r += kThreads) {  // one bin (row) per thread
+            const int top = __ldg(G.Index + tb.x + r), M = __ldg(G.Index + tb.x + r + 1) - top - 1;
+            float* row = smem_words + r * STRIDE;
+#pragma unroll
+            for (int g = 0; g < STRIDE / 4; ++g) {
+                float4 v4;
+                v4.x = (4 * g + 0 <= M) ? __ldg(G.c + top + 4 * g + 0) : 0.0f;
+                v4.y = (4 * g + 1 <= M) ? __ldg(G.c + top + 4 * g + 1) : 0.0f;
+                v4.z = (4 * g + 2 <= M) ? __ldg(G.c + top + 4 * g + 2) : 0.0f;
+                v4.w = (4 * g + 3 <= M) ? __ldg(G.c + top + 4 * g + 3) : 0.0f;
+                *reinterpret_cast<float4*>(row + 4 * g) = v4;
+            }
+            sl[r] = M;
+        }
     }
     return T;
 }
@@ -428,30 +453,71 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
 
     if (LS) {
         const int b4[4] = {(int)(bins4.x & 0xffffu), (int)(bins4.x >> 16), (int)(bins4.y & 0xffffu), (int)(bins4.y >> 16)};
-        const float* cq[4];
         int Mc[4], Mx = 0;
+        if (T.staged) {
+            constexpr int STRIDE = RP + 4;
+            const float* row[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int b   = min(max(b4[q], T.bmin), T.bmax);  // (cells of a partial group past the interior)
-            const int top = T.ip[b];
-            Mc[q] = T.ip[b + 1] - top - 1;
-            cq[q] = T.cp + top;
-            Mx    = max(Mx, Mc[q]);
-            w1[q] = w1_first_ls(G, cq[q][0], p1[q]);
-        }
+            for (int q = 0; q < 4; ++q) {
+                const int r = min(max(b4[q], T.bmin), T.bmax) - T.bmin;  // (cells of a partial group past the interior)
+                row[q] = T.rows + r * STRIDE;
+                Mc[q]  = T.len[r];
+                Mx     = max(Mx, Mc[q]);
+            }
 #pragma unroll
-        for (int l = 1; l <= RP; ++l) {
-            if (l <= Mx) {
-                float zm[4], zp[4];
-                unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
-                unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
+            for (int g = 0; g <= RP / 4; ++g) {  // coefficients 4g .. 4g+3 of the four cells
+                if (4 * g > Mx) break;
+                float cg[4][4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (l <= Mc[q]) {
-                        const float s = __fadd_rn(zm[q], zp[q]);
-                        const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
-                        const float u = __fadd_rn(t, xr[RP + q + l]);
-                        w1[q]         = __fmaf_rn(cq[q][l], u, w1[q]);
+                for (int q = 0; q < 4; ++q) unpack(*reinterpret_cast<const float4*>(row[q] + 4 * g), cg[q]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int l = 4 * g + j;
+                    if (l > RP) break;
+                    if (l == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) w1[q] = w1_first_ls(G, cg[q][0], p1[q]);
+                    } else if (l <= Mx) {
+                        float zm[4], zp[4];
+                        unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
+                        unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (l <= Mc[q]) {
+                                const float s = __fadd_rn(zm[q], zp[q]);
+                                const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
+                                const float u = __fadd_rn(t, xr[RP + q + l]);
+                                w1[q]         = __fmaf_rn(cg[q][j], u, w1[q]);
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            const float* cq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int b   = min(max(b4[q], T.bmin), T.bmax);
+                const int top = T.ip[b];
+                Mc[q] = T.ip[b + 1] - top - 1;
+                cq[q] = T.cp + top;
+                Mx    = max(Mx, Mc[q]);
+                w1[q] = w1_first_ls(G, cq[q][0], p1[q]);
+            }
+#pragma unroll
+            for (int l = 1; l <= RP; ++l) {
+                if (l <= Mx) {
+                    float zm[4], zp[4];
+                    unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
+                    unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (l <= Mc[q]) {
+                            const float s = __fadd_rn(zm[q], zp[q]);
+                            const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
+                            const float u = __fadd_rn(t, xr[RP + q + l]);
+                            w1[q]         = __fmaf_rn(cq[q][l], u, w1[q]);
+                        }
                     }
                 }
             }
@@ -519,6 +585,9 @@ struct FwdArgs {
 #ifndef RTM_BWD_MINB
 #define RTM_BWD_MINB 3
 #endif
+#ifndef RTM_FWD_MINB_LS_BIG
+#define RTM_FWD_MINB_LS_BIG 3
+#endif
 #ifndef RTM_FWD_MINB_R12
 #define RTM_FWD_MINB_R12 3
 #endif
@@ -532,7 +601,7 @@ struct FwdArgs {
 #define RTM_BWD_MINB_LS 2
 #endif
 template <int RP, bool LS, int NR>
-__global__ void __launch_bounds__(kThreads, (RP <= 4 ? (LS ? RTM_FWD_MINB_LS : RTM_FWD_MINB) : (RP <= 8 ? 3 : RTM_FWD_MINB_R12)))
+__global__ void __launch_bounds__(kThreads, (RP <= 4 ? (LS ? RTM_FWD_MINB_LS : RTM_FWD_MINB) : (LS ? RTM_FWD_MINB_LS_BIG : (RP <= 8 ? 3 : RTM_FWD_MINB_R12))))
 fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ Geo G,
                 const FwdArgs a)
 {
@@ -594,7 +663,7 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
     const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
     LsTable T{};
     if (LS) {  // this tile's slice of the operator table -> shared memory (behind the halo tile)
-        T = ls_stage_slice(G, G.tile_bins_f[t], reinterpret_cast<int*>(smem_raw + Tile<RP, NR>::BYTES + 16));
+        T = ls_stage_slice<RP>(G, G.tile_bins_f[t], reinterpret_cast<float*>(smem_raw + Tile<RP, NR>::BYTES + 16));
         __syncthreads();
     }
     const int lz0 = warp * NR, lx0 = lane * 4;
@@ -744,7 +813,7 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
     const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
     LsTable T{};
     if (LS) {
-        T = ls_stage_slice(G, G.tile_bins_b[t], reinterpret_cast<int*>(smem_raw + NTILE * Tile<RP, NR>::BYTES + 16));
+        T = ls_stage_slice<RP>(G, G.tile_bins_b[t], reinterpret_cast<float*>(smem_raw + NTILE * Tile<RP, NR>::BYTES + 16));
         __syncthreads();
     }
     const int lz0 = warp * NR, lx0 = lane * 4;
