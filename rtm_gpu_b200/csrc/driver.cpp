@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cctype>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -36,6 +37,7 @@ struct Worker {
     int rc = 0;
     std::string err;
     std::vector<std::string> log;  // one entry per shot, reference wording
+    double t_create = 0, t_io = 0, t_migrate = 0;
 };
 
 bool write_floats(const std::string& path, const float* p, size_t n)
@@ -57,17 +59,22 @@ void run_worker(const Job& job, Worker& w)
     p.iLSTE = c.iLSTE; p.iCompen = c.iCompen; p.h = c.h; p.hz = c.hz; p.tao = c.tao; p.f0 = c.f0;
     p.whitecoe = c.whitecoe; p.s_l = g.s_l; p.s_z = g.s_z; p.n = c.n; p.ds = c.ds;
     p.max_batch = std::max(1, std::min(job.batch, w.count));
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto tc0 = now();
     if (rtm_create(w.device, &p, &w.ctx)) return fail(RTM_ERR_CUDA, rtm_last_error());
     if (rtm_set_model(w.ctx, job.v.data(), job.bins.vmin, job.bins.vmax, c.dv)) return fail(RTM_ERR_CUDA, rtm_last_error());
     if (rtm_set_operator(w.ctx, c.iLSTE == 0 ? job.Index.data() : nullptr, job.bins.nvel, job.c.data(), (int)job.c.size()))
         return fail(RTM_ERR_ARG, rtm_last_error());
 
+    w.t_create = secs(tc0, now());
     const size_t ncell = (size_t)c.mod_NX * c.mod_NZ, ntr = (size_t)c.n * c.NT1;
     std::vector<float> seis((size_t)p.max_batch * ntr), up((size_t)p.max_batch * ncell),
         down((size_t)p.max_batch * ncell), stable(p.max_batch);
     std::vector<int> r_u(p.max_batch), r_x(p.max_batch);
     for (int b0 = 0; b0 < w.count; b0 += p.max_batch) {
         const int ns = std::min(p.max_batch, w.count - b0);
+        const auto ti0 = now();
         for (int s = 0; s < ns; ++s) {
             const int m = w.first + b0 + s;
             const int N = (int)c.INRE[m];
@@ -84,9 +91,12 @@ void run_worker(const Job& job, Worker& w)
         }
         // traces go up at their recording rate; resampling to the modelling rate (:839-845) and the
         // transpose to the engine's layout happen on the device
+        const auto tm0 = now();
+        w.t_io += secs(ti0, tm0);
         if (rtm_migrate_raw(w.ctx, ns, r_u.data(), r_x.data(), seis.data(), c.NT1, c.tao1, up.data(), down.data(),
                             stable.data()))
             return fail(RTM_ERR_CUDA, rtm_last_error());
+        w.t_migrate += secs(tm0, now());
         for (int s = 0; s < ns; ++s) {
             const int m = w.first + b0 + s;
             char buf[512];
@@ -112,6 +122,10 @@ extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int ver
     Job job;
     std::string err;
     rtm::RunConfig& c = job.cfg;
+    const auto T0 = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
+    const bool timing = (verbose & 2) != 0;
+    verbose &= 1;
     if (!rtm::parse_run_file(run_file, c, err) || !rtm::parse_parameter_file(c.OutPara.c_str(), c, err) ||
         !rtm::parse_depth_file(c.OutNameDPR.c_str(), c, err))
         return rtm_fail(RTM_ERR_IO, "%s", err.c_str());
@@ -170,6 +184,8 @@ extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int ver
     }
     job.batch = batch;
 
+    const double t_setup = since(T0);
+    const auto T1 = std::chrono::steady_clock::now();
     std::vector<Worker> workers(ngpu);
     std::vector<std::thread> threads;
     for (int i = 0, first = 0; i < ngpu; ++i) {  // contiguous blocks of shots per GPU
@@ -185,6 +201,8 @@ extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int ver
         if (verbose) for (auto& s : w.log) std::fputs(s.c_str(), stdout);
         if (w.rc && !rc) { rc = w.rc; err = w.err; }
     }
+    const double t_shots = since(T1);
+    const auto T2 = std::chrono::steady_clock::now();
     const size_t ncell = (size_t)c.mod_NX * c.mod_NZ;
     std::vector<float> up_sum(ncell), down_sum(ncell), img(ncell), ill(ncell);
     if (!rc) {
@@ -195,6 +213,8 @@ extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int ver
         if (rc) err = rtm_last_error();
         else if (nshots != c.nrec) { rc = RTM_ERR_STATE; err = "stack holds a different number of shots than nrec"; }
     }
+    const double t_reduce = since(T2);
+    const auto T3 = std::chrono::steady_clock::now();
     for (auto& w : workers) rtm_destroy(w.ctx);
     if (rc) return rtm_fail(rc, "%s", err.c_str());
     rtm_stack_finalize(up_sum.data(), down_sum.data(), c.nrec, c.iNorm, ncell, img.data(), ill.data());
@@ -254,5 +274,12 @@ extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int ver
                                    DSR.data(), err))
             return rtm_fail(RTM_ERR_IO, "%s", err.c_str());
     }
+    if (timing)
+        std::printf("rtm_b200 timing (GPU 0 thread): context+model+operator upload %.2f s | reading traces %.2f s | rtm_migrate_raw %.2f s\n",
+                    workers[0].t_create, workers[0].t_io, workers[0].t_migrate);
+    if (timing)
+        std::printf("rtm_b200 timing: setup (files, model, operator) %.2f s | %d shots on %d GPU(s), batch %d: %.2f s | "
+                    "stack reduce (%s) %.2f s | teardown + post-stack + SEG-Y %.2f s\n",
+                    t_setup, c.nrec, ngpu, batch, t_shots, rtm_stack_reduce_backend(), t_reduce, since(T3));
     return RTM_OK;
 }

@@ -1,6 +1,6 @@
 // rtm_b200: drop-in replacement of the reference's RTM executable for the hot path.
 // Run in the directory that holds 2D_Real_RVSP_RTM.txt (kernel.cu:542), like the reference.
-//   rtm_b200 [run-file] [--gpus N] [--batch B] [--quiet]
+//   rtm_b200 [run-file] [--gpus N] [--batch B] [--quiet] [--timing]
 #include "../../include/rtm_b200.h"
 
 #include <chrono>
@@ -15,7 +15,8 @@ int main(int argc, char** argv)
     for (int i = 1; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--batch") && i + 1 < argc) batch = std::atoi(argv[++i]);
-        else if (!std::strcmp(argv[i], "--quiet")) verbose = 0;
+        else if (!std::strcmp(argv[i], "--quiet")) verbose &= ~1;
+        else if (!std::strcmp(argv[i], "--timing")) verbose |= 2;
         else run = argv[i];
     }
     const auto t0 = std::chrono::steady_clock::now();
