@@ -1,11 +1,12 @@
 // rtm_engine.cu -- context, memory layout, time loops and the C ABI (include/rtm_b200.h).
 //
 // HBM layout (per context = per GPU), S = max_batch shots advanced together:
-//   field buffers  5 x [S][NZ][pitch] f32   pitch = multiple of 32 floats, the interior's first
+//   field buffers  8 x [S][NZ][pitch] f32   pitch = multiple of 32 floats, the interior's first
 //                                           column sits on a 128-byte boundary (padL)
-//                  forward pass: 3 rotate (slots k-2,k-1,k).  backward pass: the two buffers that
-//                  hold slots NT-1/NT-2 become the reconstructed source field (updated in place),
-//                  the other three rotate as the receiver field.
+//                  forward pass: 3 rotate (slots k-2,k-1,k).  backward pass: four buffers per
+//                  field (source / receiver): slots k+2,k+1 are read, slots k,k-1 written by one
+//                  PAIR of steps (two-step kernel on the inner tiles, single-step kernel on the
+//                  ring and the frame of tiles next to it), then the roles swap.
 //   accumulators   4 x [S][NZ][pitch]       sumS, sumR, rel1, rel2 (only the interior is used)
 //   velocity       [NZ][pitch]              shared by all shots
 //   strips         up/dw [S][NT][nfdmax][mod_NX], lf/rt [S][NT][mod_NZ][nfdmax]   (64-bit sizes)
@@ -81,16 +82,18 @@ __global__ void bins_kernel(const float* v, unsigned short* bins, Geo G, size_t 
 }
 
 // (min bin, max bin) over the interior cells of every interior tile of height tile_rows
-__global__ void tile_bins_kernel(const unsigned short* bins, Geo G, int tile_rows, int ntx, int2* out)
+// (grow > 0: the tile grown by `grow` cells on every side, clipped to the interior)
+__global__ void tile_bins_kernel(const unsigned short* bins, Geo G, int tile_rows, int ntx, int grow, int2* out)
 {
     __shared__ int smin, smax;
     if (threadIdx.x == 0) { smin = 0x7fffffff; smax = 0; }
     __syncthreads();
-    const int t = blockIdx.x, z0 = G.N2 + (t / ntx) * tile_rows, x0 = G.N2 + (t % ntx) * kTX;
+    const int t = blockIdx.x, z0 = G.N2 + (t / ntx) * tile_rows - grow, x0 = G.N2 + (t % ntx) * kTX - grow;
+    const int w = kTX + 2 * grow;
     int lo = 0x7fffffff, hi = 0;
-    for (int i = threadIdx.x; i < tile_rows * kTX; i += blockDim.x) {
-        const int z = z0 + i / kTX, x = x0 + i % kTX;
-        if (z < G.NZ - G.N2 && x < G.NX - G.N2) {
+    for (int i = threadIdx.x; i < (tile_rows + 2 * grow) * w; i += blockDim.x) {
+        const int z = z0 + i / w, x = x0 + i % w;
+        if (z >= G.N2 && x >= G.N2 && z < G.NZ - G.N2 && x < G.NX - G.N2) {
             const int b = bins[(size_t)z * G.pitch + G.padL + x];
             lo = min(lo, b); hi = max(hi, b);
         }
@@ -279,7 +282,8 @@ struct rtm_ctx {
     cudaEvent_t  fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
     // device memory
-    float* field[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    static constexpr int kFields = 8;
+    float* field[kFields] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float* acc[4]   = {nullptr, nullptr, nullptr, nullptr};
     // Interior tiles grouped by the operator length they need (rounded up to 4): every class runs
     // the kernel template, halo box and register budget of its own radius.  The Taylor operator
@@ -288,9 +292,18 @@ struct rtm_ctx {
         int  RP = 4;
         int  n_f = 0, n_b = 0;              // tiles per shot in the forward / backward tiling
         int *d_tiles_f = nullptr, *d_tiles_b = nullptr;
-        CUtensorMap tmap_f[5], tmap_b[5], tmap_store;
-        size_t smem_f = 0, smem_b = 0;      // dynamic shared memory already granted to the kernels
+        // pair stepping: inner tiles advanced two steps per pass (classified by the operator of the
+        // tile grown by one radius), frame tiles (next to the ring, or too long an operator) stepped singly
+        int  n_b2 = 0, n_bf = 0;
+        int *d_tiles_b2 = nullptr, *d_tiles_bf = nullptr;
+        CUtensorMap tmap_f[kFields], tmap_b[kFields], tmap_b2[kFields], tmap_store;
+        size_t smem_f = 0, smem_b = 0, smem_b2 = 0;  // dynamic shared memory already granted to the kernels
     };
+    bool   fuse2 = true;                    // two backward steps per pass on the inner tiles
+    int    fuse2_maxrp = 4;                 // ... for operator classes up to this radius
+    bool   dry = false;                     // launch helpers only set kernel attributes
+    long   nlaunch = 0;                     // kernels launched (graph replays included)
+    std::map<long long, long> graph_launches;
     std::vector<TileClass> classes;
     std::vector<int> h_M;                   // operator length per velocity bin (adaptive operator)
     // store-all mode (RTM_FLAG_STORE_ALL): every forward time slot stays in HBM, [NT][S][NZ][pitch]
@@ -299,7 +312,7 @@ struct rtm_ctx {
     float* d_v = nullptr;
     float* d_avel = nullptr;
     unsigned short* d_bins = nullptr;
-    int2 *d_tile_bins_f = nullptr, *d_tile_bins_b = nullptr;
+    int2 *d_tile_bins_f = nullptr, *d_tile_bins_b = nullptr, *d_tile_bins_b2 = nullptr;
     int    nvel = 0;
     float* d_c = nullptr;
     int*   d_Index = nullptr;
@@ -365,11 +378,11 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
-    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); }
+    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_b2); cudaFree(k.d_tiles_bf); }
     cudaFree(c->store);
     for (auto& f : c->field) cudaFree(f);
     for (auto& f : c->acc) cudaFree(f);
-    cudaFree(c->d_v); cudaFree(c->d_avel); cudaFree(c->d_bins); cudaFree(c->d_tile_bins_f); cudaFree(c->d_tile_bins_b); cudaFree(c->d_c); cudaFree(c->d_Index);
+    cudaFree(c->d_v); cudaFree(c->d_avel); cudaFree(c->d_bins); cudaFree(c->d_tile_bins_f); cudaFree(c->d_tile_bins_b); cudaFree(c->d_tile_bins_b2); cudaFree(c->d_c); cudaFree(c->d_Index);
     cudaFree(c->st.up); cudaFree(c->st.dw); cudaFree(c->st.lf); cudaFree(c->st.rt);
     cudaFree(c->d_traces); cudaFree(c->d_stage); cudaFree(c->d_raw); cudaFree(c->d_sinc); cudaFree(c->d_src);
     cudaFree(c->d_up); cudaFree(c->d_down); cudaFree(c->d_stack); cudaFree(c->d_stable);
@@ -436,6 +449,9 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     G.ntz_b = (G.mod_NZ + kWarps * RTM_NR_B - 1) / (kWarps * RTM_NR_B);
     G.nband = (G.NX + kRingTX - 1) / kRingTX; G.nside = (G.mod_NZ + kRingTX - 1) / kRingTX;
     if (const char* e = std::getenv("RTM_NO_GRAPH")) c->use_graphs = std::atoi(e) == 0;
+    if (const char* e = std::getenv("RTM_FUSE2")) c->fuse2 = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RTM_FUSE2_MAXRP")) c->fuse2_maxrp = std::atoi(e);
+    if (p->flags & RTM_FLAG_STORE_ALL) c->fuse2 = false;
     for (int i = 0; i <= p->N2; ++i) G.w[i] = (float)((1.0 * i) / (1.0 * p->N2));  // :688-691
 
     auto fail = [&](int rc) { rtm_destroy(c); return rc; };
@@ -456,7 +472,7 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     CKC(cudaEventCreate(&c->evB));
     c->field_floats = (size_t)c->S * G.shot_stride + 64;  // slack for float4 loads past the last row
     const size_t ncell = (size_t)G.mod_NX * G.mod_NZ;
-    size_t need = (5 + 4) * c->field_floats * 4 + (size_t)G.shot_stride * 4 +
+    size_t need = (rtm_ctx::kFields + 4) * c->field_floats * 4 + (size_t)G.shot_stride * 4 +
                   2 * (size_t)c->S * G.NT * G.n * 4 + 2 * c->S * ncell * 4;
     size_t free_b = 0, total_b = 0;
     CKC(cudaMemGetInfo(&free_b, &total_b));
@@ -483,7 +499,8 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     CKC(cudaMemset(c->d_bins, 0, ((size_t)G.shot_stride + 64) * sizeof(unsigned short)));
     CKC(cudaMalloc(&c->d_tile_bins_f, sizeof(int2) * G.ntx * G.ntz_f));
     CKC(cudaMalloc(&c->d_tile_bins_b, sizeof(int2) * G.ntx * G.ntz_b));
-    G.bins = c->d_bins; G.tile_bins_f = c->d_tile_bins_f; G.tile_bins_b = c->d_tile_bins_b;
+    CKC(cudaMalloc(&c->d_tile_bins_b2, sizeof(int2) * G.ntx * G.ntz_b));
+    G.bins = c->d_bins; G.tile_bins_f = c->d_tile_bins_f; G.tile_bins_b = c->d_tile_bins_b; G.tile_bins_b2 = c->d_tile_bins_b2;
     if (p->flags & RTM_FLAG_STORE_ALL) {
         // keep the whole forward wavefield when it fits (with 4 GB of head-room for the strips-free
         // rest); otherwise fall back to boundary saving + reverse-time reconstruction
@@ -518,8 +535,9 @@ static int prepare_ls(rtm_ctx* c)
         return rtm_fail(RTM_ERR_ARG, "adaptive operator with %d velocity bins: the per-cell bin array is 16-bit, use a larger dv", c->nvel);
     const size_t n = (size_t)G.shot_stride;
     bins_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_v, c->d_bins, G, n, c->nvel);
-    tile_bins_kernel<<<G.ntx * G.ntz_f, 256, 0, c->stream>>>(c->d_bins, G, kWarps * RTM_NR_F, G.ntx, c->d_tile_bins_f);
-    tile_bins_kernel<<<G.ntx * G.ntz_b, 256, 0, c->stream>>>(c->d_bins, G, kWarps * RTM_NR_B, G.ntx, c->d_tile_bins_b);
+    tile_bins_kernel<<<G.ntx * G.ntz_f, 256, 0, c->stream>>>(c->d_bins, G, kWarps * RTM_NR_F, G.ntx, 0, c->d_tile_bins_f);
+    tile_bins_kernel<<<G.ntx * G.ntz_b, 256, 0, c->stream>>>(c->d_bins, G, kWarps * RTM_NR_B, G.ntx, 0, c->d_tile_bins_b);
+    tile_bins_kernel<<<G.ntx * G.ntz_b, 256, 0, c->stream>>>(c->d_bins, G, kWarps * RTM_NR_B, G.ntx, c->RP, c->d_tile_bins_b2);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     return prepare_classes(c);
@@ -529,38 +547,58 @@ static int prepare_ls(rtm_ctx* c)
 static int prepare_classes(rtm_ctx* c)
 {
     const Geo& G = c->G;
-    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); }
+    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_b2); cudaFree(k.d_tiles_bf); }
     c->classes.clear();
     const int nf = G.ntx * G.ntz_f, nb = G.ntx * G.ntz_b;
-    std::map<int, std::pair<std::vector<int>, std::vector<int>>> lists;  // RP -> (forward tiles, backward tiles)
-    if (G.iLSTE != 0) {
-        lists[c->RP];  // one class, all tiles
-    } else {
-        std::vector<int2> tb(std::max(nf, nb));
-        for (int pass = 0; pass < 2; ++pass) {
-            const int n = pass ? nb : nf;
-            CK(cudaMemcpy(tb.data(), pass ? c->d_tile_bins_b : c->d_tile_bins_f, sizeof(int2) * n, cudaMemcpyDeviceToHost));
-            for (int t = 0; t < n; ++t) {
-                int m = 1;
-                for (int b = std::max(tb[t].x, 0); b <= tb[t].y && b < (int)c->h_M.size(); ++b) m = std::max(m, c->h_M[b]);
-                auto& l = lists[(m + 3) / 4 * 4];
-                (pass ? l.second : l.first).push_back(t);
-            }
+    struct Lists { std::vector<int> fwd, bwd, bwd2, frame; };
+    std::map<int, Lists> lists;  // RP -> tile lists
+    const bool ls = G.iLSTE == 0;
+    // an inner tile: full, and grown by one (rounded) radius it still lies in the interior
+    const int TZb = kWarps * RTM_NR_B;
+    auto inner = [&](int t) {
+        const int z0 = G.N2 + (t / G.ntx) * TZb, x0 = G.N2 + (t % G.ntx) * kTX;
+        return z0 - c->RP >= G.N2 && x0 - c->RP >= G.N2 && z0 + TZb + c->RP <= G.NZ - G.N2 &&
+               x0 + kTX + c->RP <= G.NX - G.N2;
+    };
+    std::vector<int2> tb(std::max(nf, nb)), tb2(nb);
+    if (ls) CK(cudaMemcpy(tb2.data(), c->d_tile_bins_b2, sizeof(int2) * nb, cudaMemcpyDeviceToHost));
+    auto radius_class = [&](int2 r) {
+        int m = 1;
+        for (int b = std::max(r.x, 0); b <= r.y && b < (int)c->h_M.size(); ++b) m = std::max(m, c->h_M[b]);
+        return (m + 3) / 4 * 4;
+    };
+    for (int pass = 0; pass < 2; ++pass) {
+        const int n = pass ? nb : nf;
+        if (ls) CK(cudaMemcpy(tb.data(), pass ? c->d_tile_bins_b : c->d_tile_bins_f, sizeof(int2) * n, cudaMemcpyDeviceToHost));
+        for (int t = 0; t < n; ++t) {
+            const int rp = ls ? radius_class(tb[t]) : c->RP;
+            if (!pass) { lists[rp].fwd.push_back(t); continue; }
+            lists[rp].bwd.push_back(t);
+            const int rp2 = ls ? radius_class(tb2[t]) : c->RP;
+            if (c->fuse2 && inner(t) && rp2 <= c->fuse2_maxrp && rp2 <= 8) lists[rp2].bwd2.push_back(t);
+            else lists[rp].frame.push_back(t);
         }
     }
+    auto upload = [&](const std::vector<int>& v, int** d) -> int {
+        if (v.empty()) return RTM_OK;
+        CK(cudaMalloc(d, sizeof(int) * v.size()));
+        CK(cudaMemcpy(*d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice));
+        return RTM_OK;
+    };
     for (auto it = lists.rbegin(); it != lists.rend(); ++it) {  // longest operators first
         rtm_ctx::TileClass k;
         k.RP = it->first;
-        if (G.iLSTE != 0) { k.n_f = nf; k.n_b = nb; }
-        else {
-            k.n_f = (int)it->second.first.size(); k.n_b = (int)it->second.second.size();
-            // (a class that holds every tile needs no list: the kernel then uses the tile number itself)
-            if (k.n_f && k.n_f < nf) { CK(cudaMalloc(&k.d_tiles_f, sizeof(int) * k.n_f)); CK(cudaMemcpy(k.d_tiles_f, it->second.first.data(), sizeof(int) * k.n_f, cudaMemcpyHostToDevice)); }
-            if (k.n_b && k.n_b < nb) { CK(cudaMalloc(&k.d_tiles_b, sizeof(int) * k.n_b)); CK(cudaMemcpy(k.d_tiles_b, it->second.second.data(), sizeof(int) * k.n_b, cudaMemcpyHostToDevice)); }
-        }
-        for (int i = 0; i < 5; ++i) {
+        const Lists& L = it->second;
+        k.n_f = (int)L.fwd.size(); k.n_b = (int)L.bwd.size(); k.n_b2 = (int)L.bwd2.size(); k.n_bf = (int)L.frame.size();
+        // (a class that holds every tile needs no list: the kernel then uses the tile number itself)
+        if (k.n_f < nf) if (int rc = upload(L.fwd, &k.d_tiles_f)) return rc;
+        if (k.n_b < nb) if (int rc = upload(L.bwd, &k.d_tiles_b)) return rc;
+        if (int rc = upload(L.bwd2, &k.d_tiles_b2)) return rc;
+        if (int rc = upload(L.frame, &k.d_tiles_bf)) return rc;
+        for (int i = 0; i < rtm_ctx::kFields; ++i) {
             int rc = encode_tmap(c, &k.tmap_f[i], c->field[i], k.RP, kWarps * RTM_NR_F);
             if (!rc) rc = encode_tmap(c, &k.tmap_b[i], c->field[i], k.RP, kWarps * RTM_NR_B);
+            if (!rc && k.n_b2) rc = encode_tmap(c, &k.tmap_b2[i], c->field[i], 2 * k.RP, kWarps * RTM_NR_B);
             if (rc) return rc;
         }
         if (c->store_mode)
@@ -659,11 +697,13 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass&
     }
     a.tiles = k.d_tiles_f; a.ntiles = k.n_f;
     dim3 grid((unsigned)((nring + k.n_f) * ns));
-    if (grid.x == 0) return RTM_OK;
+    if (grid.x == 0 || c->dry) return RTM_OK;
+    ++c->nlaunch;
     fwd_step_kernel<RP, LS, RTM_NR_F><<<grid, kThreads, smem, st>>>(buf < 0 ? k.tmap_store : k.tmap_f[buf], G, a);
     return RTM_OK;
 }
-template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, BwdArgs a)
+// frame: only the tiles that the two-step kernel does not cover
+template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, BwdArgs a, bool frame)
 {
     const Geo& G = c->G;
     const int nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0;
@@ -673,17 +713,46 @@ template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx
         CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k.smem_b = smem;
     }
-    a.tiles = k.d_tiles_b; a.ntiles = k.n_b;
-    dim3 grid((unsigned)((nring + k.n_b) * ns));
-    if (grid.x == 0) return RTM_OK;
+    a.tiles = frame ? k.d_tiles_bf : k.d_tiles_b; a.ntiles = frame ? k.n_bf : k.n_b;
+    dim3 grid((unsigned)((nring + a.ntiles) * ns));
+    if (grid.x == 0 || c->dry) return RTM_OK;
+    ++c->nlaunch;
     bwd_step_kernel<RP, LS, RTM_NR_B, STORE><<<grid, kThreads, smem, st>>>(k.tmap_b[STORE ? r1 : s1], k.tmap_b[r1], G, a);
     return RTM_OK;
 }
+template <int RP, bool LS> static int launch_bwd2(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, Bwd2Args a)
+{
+    if (k.n_b2 == 0) return RTM_OK;
+    const size_t smem = (size_t)Tile2<RP>::BYTES + 16 + (LS ? (size_t)slice_bytes(RP) : 0);
+    if (smem > k.smem_b2) {
+        CK(cudaFuncSetAttribute(bwd2_step_kernel<RP, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k.smem_b2 = smem;
+    }
+    a.tiles = k.d_tiles_b2; a.ntiles = k.n_b2;
+    if (c->dry) return RTM_OK;
+    ++c->nlaunch;
+    bwd2_step_kernel<RP, LS><<<(unsigned)(k.n_b2 * ns), kThreads, smem, st>>>(k.tmap_b2[s1], k.tmap_b2[r1], c->G, a);
+    return RTM_OK;
+}
+static int dispatch_bwd2_class(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, const Bwd2Args& a)
+{
+    const bool ls = c->G.iLSTE == 0;
+    switch (k.RP) {
+    case 4: return ls ? launch_bwd2<4, true>(c, k, st, ns, s1, r1, a) : launch_bwd2<4, false>(c, k, st, ns, s1, r1, a);
+    case 8: return ls ? launch_bwd2<8, true>(c, k, st, ns, s1, r1, a) : launch_bwd2<8, false>(c, k, st, ns, s1, r1, a);
+    }
+    return rtm_fail(RTM_ERR_ARG, "two-step kernel: unsupported operator radius %d", k.RP);
+}
 // The classes of one time step touch disjoint cells: they are forked onto side streams so that
 // small classes share the GPU with the large ones, and joined before the next step.
-template <class Launch> static int fork_join(rtm_ctx* c, Launch launch)
+template <class Launch> static int fork_join(rtm_ctx* c, Launch launch, cudaStream_t serial = nullptr)
 {
     const int n = (int)c->classes.size();
+    if (serial) {  // all classes one after the other on the given stream
+        for (int i = 0; i < n; ++i)
+            if (int rc = launch(c->classes[i], serial, i == 0)) return rc;
+        return RTM_OK;
+    }
     if (n > 1) {
         CK(cudaEventRecord(c->fork_ev, c->stream));
         for (int i = 1; i < n && i <= 3; ++i) CK(cudaStreamWaitEvent(c->aux[i - 1], c->fork_ev, 0));
@@ -713,29 +782,30 @@ static int dispatch_fwd(rtm_ctx* c, int ns, int buf, FwdArgs a)
         return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", k.RP);
     });
 }
-template <bool STORE> static int dispatch_bwd_t(rtm_ctx* c, int ns, int s1, int r1, BwdArgs a)
+template <bool STORE> static int dispatch_bwd_t(rtm_ctx* c, int ns, int s1, int r1, BwdArgs a, bool frame, cudaStream_t serial)
 {
     const bool ls = c->G.iLSTE == 0;
     return fork_join(c, [&](rtm_ctx::TileClass& k, cudaStream_t st, bool first) -> int {
         a.do_ring = first ? 1 : 0;
         switch (k.RP) {
-        case 4:  return ls ? launch_bwd<4, true, STORE>(c, k, st, ns, s1, r1, a) : launch_bwd<4, false, STORE>(c, k, st, ns, s1, r1, a);
-        case 8:  return ls ? launch_bwd<8, true, STORE>(c, k, st, ns, s1, r1, a) : launch_bwd<8, false, STORE>(c, k, st, ns, s1, r1, a);
-        case 12: return ls ? launch_bwd<12, true, STORE>(c, k, st, ns, s1, r1, a) : launch_bwd<12, false, STORE>(c, k, st, ns, s1, r1, a);
-        case 16: return ls ? launch_bwd<16, true, STORE>(c, k, st, ns, s1, r1, a) : launch_bwd<16, false, STORE>(c, k, st, ns, s1, r1, a);
+        case 4:  return ls ? launch_bwd<4, true, STORE>(c, k, st, ns, s1, r1, a, frame) : launch_bwd<4, false, STORE>(c, k, st, ns, s1, r1, a, frame);
+        case 8:  return ls ? launch_bwd<8, true, STORE>(c, k, st, ns, s1, r1, a, frame) : launch_bwd<8, false, STORE>(c, k, st, ns, s1, r1, a, frame);
+        case 12: return ls ? launch_bwd<12, true, STORE>(c, k, st, ns, s1, r1, a, frame) : launch_bwd<12, false, STORE>(c, k, st, ns, s1, r1, a, frame);
+        case 16: return ls ? launch_bwd<16, true, STORE>(c, k, st, ns, s1, r1, a, frame) : launch_bwd<16, false, STORE>(c, k, st, ns, s1, r1, a, frame);
         }
         return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", k.RP);
-    });
+    }, serial);
 }
-static int dispatch_bwd(rtm_ctx* c, int ns, int s1, int r1, const BwdArgs& a)
+static int dispatch_bwd(rtm_ctx* c, int ns, int s1, int r1, const BwdArgs& a, bool frame = false, cudaStream_t serial = nullptr)
 {
-    return c->store_mode ? dispatch_bwd_t<true>(c, ns, s1, r1, a) : dispatch_bwd_t<false>(c, ns, s1, r1, a);
+    return c->store_mode ? dispatch_bwd_t<true>(c, ns, s1, r1, a, frame, serial) : dispatch_bwd_t<false>(c, ns, s1, r1, a, frame, serial);
 }
 
 static void drop_graphs(rtm_ctx* c)
 {
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
     c->graphs.clear();
+    c->graph_launches.clear();
 }
 
 // Replay (or capture, the first time) the launches issued by `body` as one CUDA graph.
@@ -744,9 +814,12 @@ template <class Body> static int run_as_graph(rtm_ctx* c, long long key, Body bo
     auto it = c->graphs.find(key);
     if (it == c->graphs.end()) {
         cudaGraph_t graph = nullptr;
+        const long n0 = c->nlaunch;
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         const int rc = body();
         const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        c->graph_launches[key] = c->nlaunch - n0;
+        c->nlaunch = n0;
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return rtm_fail(RTM_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
         cudaGraphExec_t exec = nullptr;
@@ -756,6 +829,7 @@ template <class Body> static int run_as_graph(rtm_ctx* c, long long key, Body bo
         it = c->graphs.emplace(key, exec).first;
     }
     CK(cudaGraphLaunch(it->second, c->stream));
+    c->nlaunch += c->graph_launches[key];
     return RTM_OK;
 }
 
@@ -831,6 +905,7 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
         a.tma_s0 = use_store ? (k - 1) * c->S : 0;
         return dispatch_fwd(c, ns, use_store ? -1 : (k - 1) % 3, a);
     };
+    const long nl0 = c->nlaunch;
     CK(cudaEventRecord(c->ev0, c->stream));
     if (c->use_graphs && nsnap == 0 && G.NT > 3) {
         if (int rc = step(2)) return rc;  // (also sets the kernel's shared-memory attribute before capture)
@@ -854,7 +929,7 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
     c->stats.cell_updates += cu;
     c->stats.algorithmic_bytes += cu * 16.0;
     c->stats.forward_seconds += ms * 1e-3;
-    c->stats.kernel_launches += (long)(G.NT - 2) * (long)c->classes.size() + 3;
+    c->stats.kernel_launches += (c->nlaunch - nl0) + 3;
     c->last_forward_ms = ms;
     *last1 = slot(G.NT - 1); *last0 = slot(G.NT - 2);
     return RTM_OK;
@@ -896,15 +971,23 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
     float *l1, *l0;
     CK(cudaEventRecord(c->evA, c->stream));
     if (int rc = run_forward(c, ns, r_u, r_x, true, nullptr, 0, nullptr, nullptr, store, &l1, &l0)) return rc;
-    // source field: l1 = slot NT-1 ("previous", updated in place), l0 = slot NT-2 ("current");
-    // the receiver field rotates through the remaining buffers (store-all: all of field[0..2])
-    int sx = -1, sy = -1, rb[3], nrb = 0;
-    for (int b = 0; b < 5; ++b) {
-        if (c->field[b] == l1) sx = b;
-        else if (c->field[b] == l0) sy = b;
-        else if (nrb < 3) rb[nrb++] = b;
+    // Backward pass.  Source field: Sa = slot k+2 (starts as slot NT-1), Sb = slot k+1 (NT-2), Sc/Sd
+    // receive slots k / k-1; receiver field Ra..Rd likewise, starting from zero (store-all: only
+    // the receiver buffers are used).
+    int Sa = -1, Sb = -1, Sc = -1, Sd = -1, Ra = -1, Rb = -1, Rc = -1, Rd = -1;
+    {
+        int rest[rtm_ctx::kFields], n = 0;
+        for (int b = 0; b < rtm_ctx::kFields; ++b) {
+            if (c->field[b] == l1) Sa = b;
+            else if (c->field[b] == l0) Sb = b;
+            else rest[n++] = b;
+        }
+        if (store) { Ra = rest[0]; Rb = rest[1]; Rc = rest[2]; Rd = rest[3]; }
+        else { Sc = rest[0]; Sd = rest[1]; Ra = rest[2]; Rb = rest[3]; Rc = rest[4]; Rd = rest[5]; }
     }
-    for (int i = 0; i < 3; ++i) CK(cudaMemsetAsync(c->field[rb[i]], 0, c->field_floats * 4, c->stream));
+    CK(cudaMemsetAsync(c->field[Ra], 0, c->field_floats * 4, c->stream));
+    CK(cudaMemsetAsync(c->field[Rb], 0, c->field_floats * 4, c->stream));
+    CK(cudaMemsetAsync(c->field[Rc], 0, c->field_floats * 4, c->stream));
     const float fw1 = (float)(rtm::ricker(0.0f, c->p.f0) / 2.0);
     {
         dim3 grid((G.NX + 127) / 128, G.NZ, ns);
@@ -912,31 +995,86 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
     }
     int NT2;
     rtm_derived(c->p.h, c->p.hz, c->p.tao, c->p.tao, c->p.f0, 2, nullptr, &NT2, nullptr, nullptr, nullptr, nullptr, nullptr);
-    int r0 = rb[0], r1 = rb[1], r2 = rb[2];
     const size_t slab = (size_t)c->S * G.shot_stride;
-    auto bstep = [&](int k) -> int {
-        BwdArgs a;
+    auto wavelet = [&](int k) { return (k < NT2) ? rtm::ricker((k + 1) * c->p.tao, c->p.f0) : 0.0f; };  // :889-890
+    // arguments of one single-step launch for slot k: source prev/out buffers, receiver prev/out
+    auto args1 = [&](int k, int s0, int s2, int r0, int r1, int r2) {
+        BwdArgs a{};
         a.Sk = store ? c->store + (size_t)k * slab : nullptr;
-        a.S1 = store ? nullptr : c->field[sy]; a.S02 = store ? nullptr : c->field[sx];
+        a.S1 = nullptr; a.S02 = store ? nullptr : c->field[s0]; a.S2 = store ? nullptr : c->field[s2];
         a.R1 = c->field[r1]; a.R0 = c->field[r0]; a.R2 = c->field[r2];
         a.src = c->d_src;
-        a.wavelet = (k < NT2) ? rtm::ricker((k + 1) * c->p.tao, c->p.f0) : 0.0f;  // :889-890
+        a.wavelet = wavelet(k);
         a.k = k; a.nshots = ns; a.st = c->st; a.seis = c->d_traces;
         a.sumS = c->acc[0]; a.sumR = c->acc[1]; a.rel1 = c->acc[2]; a.rel2 = c->acc[3];
-        if (int rc = dispatch_bwd(c, ns, store ? r1 : sy, r1, a)) return rc;
-        std::swap(sx, sy);
-        const int t = r0; r0 = r1; r1 = r2; r2 = t;
+        return a;
+    };
+    // one step, all tiles; the source slot k replaces slot k+2 in place
+    auto bstep = [&](int k) -> int {
+        if (int rc = dispatch_bwd(c, ns, store ? Rb : Sb, Rb, args1(k, Sa, Sa, Ra, Rb, Rc))) return rc;
+        std::swap(Sa, Sb);
+        const int t = Ra; Ra = Rb; Rb = Rc; Rc = t;
         return RTM_OK;
     };
+    // steps k and k-1: inner tiles by the two-step kernel, concurrently ring + frame tiles for slot k
+    // on a side stream, then ring + frame tiles for slot k-1
+    auto bstep2 = [&](int k) -> int {
+        CK(cudaEventRecord(c->fork_ev, c->stream));
+        for (auto& a : c->aux) CK(cudaStreamWaitEvent(a, c->fork_ev, 0));
+        Bwd2Args a2{};
+        a2.S0 = c->field[Sa]; a2.Sk = c->field[Sc]; a2.Skm = c->field[Sd];
+        a2.R0 = c->field[Ra]; a2.Rk = c->field[Rc]; a2.Rkm = c->field[Rd];
+        a2.src = c->d_src; a2.wavelet_k = wavelet(k); a2.wavelet_km = wavelet(k - 1);
+        a2.k = k; a2.nshots = ns; a2.seis = c->d_traces;
+        a2.sumS = c->acc[0]; a2.sumR = c->acc[1]; a2.rel1 = c->acc[2]; a2.rel2 = c->acc[3];
+        int nside = 0;
+        for (auto& kc : c->classes) {
+            if (!kc.n_b2) continue;
+            cudaStream_t st = nside == 0 ? c->stream : c->aux[(nside - 1) % 2];
+            ++nside;
+            if (int rc = dispatch_bwd2_class(c, kc, st, ns, Sb, Rb, a2)) return rc;
+        }
+        if (int rc = dispatch_bwd(c, ns, Sb, Rb, args1(k, Sa, Sc, Ra, Rb, Rc), true, c->aux[2])) return rc;
+        for (int i = 0; i < 3; ++i) {
+            CK(cudaEventRecord(c->join_ev[i], c->aux[i]));
+            CK(cudaStreamWaitEvent(c->stream, c->join_ev[i], 0));
+        }
+        if (int rc = dispatch_bwd(c, ns, Sc, Rc, args1(k - 1, Sb, Sd, Rb, Rc, Rd), true)) return rc;
+        std::swap(Sa, Sc); std::swap(Sb, Sd);
+        std::swap(Ra, Rc); std::swap(Rb, Rd);
+        return RTM_OK;
+    };
+    bool pairs = c->fuse2 && !store;
+    if (pairs) {
+        pairs = false;
+        for (auto& kc : c->classes) pairs = pairs || kc.n_b2 > 0;
+    }
+    auto loop = [&](int kfirst) -> int {  // slots kfirst .. 0
+        int k = kfirst;
+        if (pairs) {
+            if ((k + 1) % 2) { if (int rc = bstep(k)) return rc; --k; }
+            for (; k >= 1; k -= 2) if (int rc = bstep2(k)) return rc;
+        } else {
+            for (; k >= 0; --k) if (int rc = bstep(k)) return rc;
+        }
+        return RTM_OK;
+    };
+    const long nl0 = c->nlaunch;
     CK(cudaEventRecord(c->ev0, c->stream));
     if (c->use_graphs && G.NT > 3) {
-        if (int rc = bstep(G.NT - 3)) return rc;
-        if (int rc = run_as_graph(c, 2 + 8 * (store ? 1 : 0) + 16LL * ns, [&]() -> int {
-                for (int k = G.NT - 4; k >= 0; --k) if (int r = bstep(k)) return r;
-                return RTM_OK;
-            })) return rc;
+        {   // kernel attributes cannot be set during capture: a dry pass over both kinds of step
+            const int sv[8] = {Sa, Sb, Sc, Sd, Ra, Rb, Rc, Rd};
+            c->dry = true;
+            int rc = bstep(G.NT - 3);
+            if (!rc && pairs) rc = bstep2(G.NT - 3);
+            c->dry = false;
+            Sa = sv[0]; Sb = sv[1]; Sc = sv[2]; Sd = sv[3]; Ra = sv[4]; Rb = sv[5]; Rc = sv[6]; Rd = sv[7];
+            if (rc) return rc;
+        }
+        if (int rc = run_as_graph(c, 2 + 4 * (pairs ? 1 : 0) + 8 * (store ? 1 : 0) + 16LL * ns, [&]() -> int { return loop(G.NT - 3); }))
+            return rc;
     } else {
-        for (int k = G.NT - 3; k >= 0; --k) if (int rc = bstep(k)) return rc;
+        if (int rc = loop(G.NT - 3)) return rc;
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     // per-shot image post-processing and stacking
@@ -962,7 +1100,7 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
     c->stats.backward_seconds += ms * 1e-3;
     CK(cudaEventElapsedTime(&ms, c->evA, c->evB));
     c->stats.device_seconds += ms * 1e-3;  // whole batch: init, both loops, image post, stack
-    c->stats.kernel_launches += (long)(G.NT - 2) * (long)c->classes.size() + 4;
+    c->stats.kernel_launches += (c->nlaunch - nl0) + 4;
     c->stats.shots += ns;
     c->stack_shots += ns;
     return RTM_OK;

@@ -72,6 +72,7 @@ struct Geo {
     const unsigned short* bins;   // [NZ][pitch]
     const int2* tile_bins_f;      // [ntz_f*ntx] (min bin, max bin) of each forward interior tile
     const int2* tile_bins_b;      // [ntz_b*ntx]
+    const int2* tile_bins_b2;     // [ntz_b*ntx] same tiles grown by the operator radius (two-step kernel)
     const float* v;          // [NZ][pitch], shared by all shots
     float  w[65];            // blend weights l/N2
 };
@@ -437,11 +438,10 @@ __device__ __forceinline__ LsTable ls_stage_slice(const Geo& G, int2 tb, float* 
 // keeps the register footprint small enough for 3-4 resident CTAs per SM.
 // M <= RP is the uniform length of the Taylor operator; the adaptive operator brings a length
 // and table offset per cell (from the cell's velocity bin).
-template <int RP, bool LS>
+template <int RP, bool LS, int SP = kTX + 2 * RP>
 __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M, const LsTable& T,
                                             uint2 bins4, float (&w1)[4], float (&p1)[4])
 {
-    constexpr int SP = kTX + 2 * RP;
     float xr[4 + 2 * RP];  // columns x-RP .. x+3+RP of this row
 #pragma unroll
     for (int g = 0; g < (4 + 2 * RP) / 4; ++g) {
@@ -738,7 +738,8 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
 struct BwdArgs {
     const float* Sk;   // store-all mode: the stored forward field of slot k (S1/S02/strips unused)
     const float* S1;   // source slot k+1 (ring = strips of slot k+1)
-    float*       S02;  // in: source slot k+2, out: source slot k (interior), ring := strips of slot k
+    const float* S02;  // source slot k+2
+    float*       S2;   // out: source slot k (interior), ring := strips of slot k.  May alias S02 (in place)
     const float* R1;   // receiver, current
     const float* R0;   // receiver, previous
     float*       R2;   // receiver, new
@@ -772,7 +773,7 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
 
     if (is_ring) {
         float* R2 = a.R2 + so;
-        float* SX = a.S02 + so;
+        float* SX = a.S2 + so;
         const int N2 = G.N2, nf = G.nfdmax, NZ = G.NZ, NX = G.NX, k = a.k;
         const Strips st = a.st;
         ring_tile<LS>(G, bi % nring, a.R1 + so, a.R0 + so, SUM_FLOAT, false, 0, 0, 0.0f, seis_row,
@@ -919,7 +920,7 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
                 r2v[q] = __fmaf_rn(S2[q], S2[q], r2v[q]);
             }
         }
-        if (!STORE) put(a.S02, S2);
+        if (!STORE) put(a.S2, S2);
         put(a.R2, R2);
         put(a.rel1, r1v);
         put(a.rel2, r2v);
@@ -928,6 +929,261 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
             put(a.sumR, sRv);
         }
         o += G.pitch; vp += G.pitch; bp += G.pitch; spS += Tile<RP, NR>::SP; spR += Tile<RP, NR>::SP;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------
+// Two backward steps (k and k-1) of one INNER interior tile in a single pass.
+//
+// Slots k and k-1 depend on slots k+1/k+2 only through a neighbourhood of 2 operator radii, so a
+// tile whose neighbourhood holds no absorbing-ring cell can advance two steps while its fields
+// and imaging accumulators cross HBM once: per grid cell and PAIR of steps 68 B (S,R of slots
+// k+1,k+2 in, S,R of slots k,k-1 out, v, four accumulators read-modify-write) instead of 2 x 60 B.
+//   phase A: slot k of both fields on the tile grown by RP cells -> shared memory ("mid" tiles);
+//            the current fields (slot k+1) arrive as TMA boxes with a 2*RP halo;
+//   phase B: slot k-1 on the tile itself from the mid tiles (P0 = centre of the TMA boxes), both
+//            imaging updates in time order, all stores.
+// Every cell value is produced by exactly the operations of the single-step kernel, so results
+// are bit-identical to stepping twice.  Ring tiles and the frame of interior tiles next to the
+// ring run the single-step kernel for slot k (concurrently) and for slot k-1 (afterwards).
+// Buffers: slots k+2,k+1 are only read, slots k,k-1 go to two other buffers (4 per field).
+// ------------------------------------------------------------------------------------
+struct Bwd2Args {
+    const float* S0;   // source slot k+2 (slot k+1 comes through the tensor map)
+    float*       Sk;   // out: source slot k
+    float*       Skm;  // out: source slot k-1
+    const float* R0;   // receiver slot k+2
+    float*       Rk;
+    float*       Rkm;
+    const int2*  src;
+    float        wavelet_k, wavelet_km;  // source term of steps k and k-1
+    int          k;
+    int          nshots;
+    const int*   tiles;   // inner tiles of this launch
+    int          ntiles;
+    const float* seis;    // [S][NT][n]; row k+1 is imposed in step k, row k in step k-1
+    float *sumS, *sumR, *rel1, *rel2;
+};
+
+template <int RP> struct Tile2 {
+    static constexpr int NR   = RTM_NR_B;
+    static constexpr int TZ   = kWarps * NR;
+    static constexpr int SPA  = kTX + 4 * RP, ROWSA = TZ + 4 * RP;  // slot k+1 boxes (halo 2*RP)
+    static constexpr int SPB  = kTX + 2 * RP, ROWSB = TZ + 2 * RP;  // slot k mid tiles (halo RP)
+    static constexpr int CUR_BYTES = SPA * ROWSA * 4, MID_BYTES = SPB * ROWSB * 4;
+    static constexpr int BYTES = 2 * CUR_BYTES + 2 * MID_BYTES;
+};
+
+#ifndef RTM_BWD2_MINB
+#define RTM_BWD2_MINB 3
+#endif
+template <int RP, bool LS>
+__global__ void __launch_bounds__(kThreads, (RP <= 4 ? RTM_BWD2_MINB : (RP <= 8 ? 2 : 1)))
+bwd2_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmR1,
+                 const __grid_constant__ Geo G, const Bwd2Args a)
+{
+    using T2 = Tile2<RP>;
+    constexpr int NR = T2::NR, SPA = T2::SPA, SPB = T2::SPB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int  shot = blockIdx.x / a.ntiles;
+    const int  t    = a.tiles[blockIdx.x % a.ntiles];
+    const long long so = (long long)shot * G.shot_stride + G.padL;
+    const int2 src = a.src[shot];
+    const int  tz  = t / G.ntx, tx = t % G.ntx;
+    const int  z0  = G.N2 + tz * T2::TZ, x0 = G.N2 + tx * kTX;
+    float*    sS1 = reinterpret_cast<float*>(smem_raw);
+    float*    sR1 = reinterpret_cast<float*>(smem_raw + T2::CUR_BYTES);
+    float*    mS  = reinterpret_cast<float*>(smem_raw + 2 * T2::CUR_BYTES);
+    float*    mR  = reinterpret_cast<float*>(smem_raw + 2 * T2::CUR_BYTES + T2::MID_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + T2::BYTES);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, 2 * T2::CUR_BYTES);
+        tma_load_3d(sS1, &tmS1, bar, G.padL + x0 - 2 * RP, z0 - 2 * RP, shot);
+        tma_load_3d(sR1, &tmR1, bar, G.padL + x0 - 2 * RP, z0 - 2 * RP, shot);
+    }
+    LsTable T{};
+    if (LS) {
+        T = ls_stage_slice<RP>(G, G.tile_bins_b2[t], reinterpret_cast<float*>(smem_raw + T2::BYTES + 16));
+        __syncthreads();
+    }
+    const float* AV = G.avel + G.padL;
+    const unsigned short* BN = G.bins + G.padL;
+    const float* S0 = a.S0 + so;
+    const float* R0 = a.R0 + so;
+
+    // ---- phase A: slot k on rows [z0-RP, z0+TZ+RP), columns [x0-RP, x0+kTX+RP)
+    {
+        constexpr int NRA = T2::ROWSB / kWarps;  // grown rows per warp
+        constexpr int GH  = RP / 4;              // halo float4 groups per side
+        const float* seisA = a.seis + ((size_t)shot * G.NT + (a.k + 1)) * G.n;
+        // one float4 group (4 x-adjacent cells) of grown row rg, both fields
+        auto item = [&](int rg, int g, const float4& s0v, const float4& r0v, const float4& avv, const uint2& b2) {
+            const int z = z0 - RP + rg, x = x0 - RP + 4 * g;
+            float av[4], p0[4], w1[4], p1[4], o[4];
+            unpack(avv, av);
+            stencil_row<RP, LS, SPA>(G, sS1 + (rg + RP) * SPA + 4 * g + RP, G.nfdmax, T, b2, w1, p1);
+            unpack(s0v, p0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = finish_double(av[q], w1[q], p1[q], p0[q]);
+            if (z == src.x && src.y >= x && src.y < x + 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (x + q == src.y) o[q] = __fadd_rn(o[q], a.wavelet_k);
+            }
+            *reinterpret_cast<float4*>(mS + rg * SPB + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
+            stencil_row<RP, LS, SPA>(G, sR1 + (rg + RP) * SPA + 4 * g + RP, G.nfdmax, T, b2, w1, p1);
+            unpack(r0v, p0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = finish_float(av[q], w1[q], p1[q], p0[q]);
+            if (z == G.s_z) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = data_index(G, z, x + q);
+                    if (j >= 0) {
+                        const float d = seisA[j];
+                        if (d != 0.0f) o[q] = d;
+                    }
+                }
+            }
+            *reinterpret_cast<float4*>(mR + rg * SPB + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
+        };
+        // main part: lane -> group GH+lane (the tile's own columns), warp -> NRA consecutive rows
+        const int rg0 = warp * NRA;
+        size_t    cell = (size_t)(z0 - RP + rg0) * G.pitch + x0 + 4 * lane;
+        float4 s0n = __ldg(reinterpret_cast<const float4*>(S0 + cell));
+        float4 r0n = __ldg(reinterpret_cast<const float4*>(R0 + cell));
+        float4 avn = __ldg(reinterpret_cast<const float4*>(AV + cell));
+        uint2  bn  = make_uint2(0u, 0u);
+        if (LS) bn = __ldg(reinterpret_cast<const uint2*>(BN + cell));
+        mbar_wait(bar, 0);
+#pragma unroll
+        for (int r = 0; r < NRA; ++r) {
+            const float4 s0c = s0n, r0c = r0n, avc = avn;
+            const uint2  bc  = bn;
+            if (r + 1 < NRA) {
+                cell += G.pitch;
+                s0n = __ldg(reinterpret_cast<const float4*>(S0 + cell));
+                r0n = __ldg(reinterpret_cast<const float4*>(R0 + cell));
+                avn = __ldg(reinterpret_cast<const float4*>(AV + cell));
+                if (LS) bn = __ldg(reinterpret_cast<const uint2*>(BN + cell));
+            }
+            item(rg0 + r, GH + lane, s0c, r0c, avc, bc);
+        }
+        // the 2*GH halo groups of every grown row, flattened over the CTA
+        for (int i = tid; i < T2::ROWSB * 2 * GH; i += kThreads) {
+            const int rg = i / (2 * GH), j = i % (2 * GH);
+            const int g  = j < GH ? j : SPB / 4 - 2 * GH + j;
+            const size_t ce = (size_t)(z0 - RP + rg) * G.pitch + x0 - RP + 4 * g;
+            const float4 s0c = __ldg(reinterpret_cast<const float4*>(S0 + ce));
+            const float4 r0c = __ldg(reinterpret_cast<const float4*>(R0 + ce));
+            const float4 avc = __ldg(reinterpret_cast<const float4*>(AV + ce));
+            uint2 bc = make_uint2(0u, 0u);
+            if (LS) bc = __ldg(reinterpret_cast<const uint2*>(BN + ce));
+            item(rg, g, s0c, r0c, avc, bc);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: slot k-1 on the tile (always a full tile), imaging updates of both steps
+    {
+        const int lz0 = warp * NR, lx0 = lane * 4;
+        const int z = z0 + lz0, x = x0 + lx0;
+        const bool compen = G.iCompen == 1;
+        const float* seisB = a.seis + ((size_t)shot * G.NT + a.k) * G.n;
+        size_t cell = (size_t)z * G.pitch + x;
+        size_t o    = so + cell;
+        float4 avn = __ldg(reinterpret_cast<const float4*>(AV + cell));
+        uint2  bn  = make_uint2(0u, 0u);
+        if (LS) bn = __ldg(reinterpret_cast<const uint2*>(BN + cell));
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const float4 a1 = *reinterpret_cast<const float4*>(a.rel1 + o);
+            const float4 a2 = *reinterpret_cast<const float4*>(a.rel2 + o);
+            float4 aS = make_float4(0.f, 0.f, 0.f, 0.f), aR = aS;
+            if (compen) {
+                aS = *reinterpret_cast<const float4*>(a.sumS + o);
+                aR = *reinterpret_cast<const float4*>(a.sumR + o);
+            }
+            float av[4];
+            unpack(avn, av);
+            const uint2 bc = bn;
+            if (r + 1 < NR) {
+                avn = __ldg(reinterpret_cast<const float4*>(AV + cell + G.pitch));
+                if (LS) bn = __ldg(reinterpret_cast<const uint2*>(BN + cell + G.pitch));
+            }
+            float w1[4], sk[4], rk[4], p0[4], skm[4], rkm[4];
+            // source field, slot k-1
+            stencil_row<RP, LS, SPB>(G, mS + (lz0 + r + RP) * SPB + lx0 + RP, G.nfdmax, T, bc, w1, sk);
+            unpack(*reinterpret_cast<const float4*>(sS1 + (lz0 + r + 2 * RP) * SPA + lx0 + 2 * RP), p0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) skm[q] = finish_double(av[q], w1[q], sk[q], p0[q]);
+            if (z + r == src.x && src.y >= x && src.y < x + 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (x + q == src.y) skm[q] = __fadd_rn(skm[q], a.wavelet_km);
+            }
+            // receiver field, slot k-1
+            stencil_row<RP, LS, SPB>(G, mR + (lz0 + r + RP) * SPB + lx0 + RP, G.nfdmax, T, bc, w1, rk);
+            unpack(*reinterpret_cast<const float4*>(sR1 + (lz0 + r + 2 * RP) * SPA + lx0 + 2 * RP), p0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rkm[q] = finish_float(av[q], w1[q], rk[q], p0[q]);
+            if (z + r == G.s_z) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = data_index(G, z + r, x + q);
+                    if (j >= 0) {
+                        const float d = seisB[j];
+                        if (d != 0.0f) rkm[q] = d;
+                    }
+                }
+            }
+            // imaging, step k then step k-1 (Rel_Compen :503-517 / Rel_NonCompen :489-501)
+            float r1v[4], r2v[4], sSv[4], sRv[4];
+            unpack(a1, r1v);
+            unpack(a2, r2v);
+            unpack(aS, sSv);
+            unpack(aR, sRv);
+            if (compen) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    sSv[q] = __fadd_rn(sk[q], sSv[q]);
+                    sRv[q] = __fadd_rn(rk[q], sRv[q]);
+                    r1v[q] = __fmaf_rn(sRv[q], sSv[q], r1v[q]);
+                    r2v[q] = __fmaf_rn(sk[q], sk[q], r2v[q]);
+                    sSv[q] = __fadd_rn(skm[q], sSv[q]);
+                    sRv[q] = __fadd_rn(rkm[q], sRv[q]);
+                    r1v[q] = __fmaf_rn(sRv[q], sSv[q], r1v[q]);
+                    r2v[q] = __fmaf_rn(skm[q], skm[q], r2v[q]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    r1v[q] = __fmaf_rn(rk[q], sk[q], r1v[q]);
+                    r2v[q] = __fmaf_rn(sk[q], sk[q], r2v[q]);
+                    r1v[q] = __fmaf_rn(rkm[q], skm[q], r1v[q]);
+                    r2v[q] = __fmaf_rn(skm[q], skm[q], r2v[q]);
+                }
+            }
+            auto put = [&](float* base, const float (&val)[4]) {
+                *reinterpret_cast<float4*>(base + o) = make_float4(val[0], val[1], val[2], val[3]);
+            };
+            put(a.Sk, sk);
+            put(a.Skm, skm);
+            put(a.Rk, rk);
+            put(a.Rkm, rkm);
+            put(a.rel1, r1v);
+            put(a.rel2, r2v);
+            if (compen) {
+                put(a.sumS, sSv);
+                put(a.sumR, sRv);
+            }
+            o += G.pitch; cell += G.pitch;
+        }
     }
 }
 
