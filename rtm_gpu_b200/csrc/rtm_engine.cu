@@ -281,6 +281,7 @@ struct rtm_ctx {
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // the tile classes of one time step run concurrently
     cudaEvent_t  fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    cudaEvent_t  ev_ii[2] = {nullptr, nullptr}, ev_ib[2] = {nullptr, nullptr};  // pair stepping, alternating
     // device memory
     static constexpr int kFields = 8;
     float* field[kFields] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -294,13 +295,22 @@ struct rtm_ctx {
         int *d_tiles_f = nullptr, *d_tiles_b = nullptr;
         // pair stepping: inner tiles advanced two steps per pass (classified by the operator of the
         // tile grown by one radius), frame tiles (next to the ring, or too long an operator) stepped singly
-        int  n_b2 = 0, n_bf = 0;
-        int *d_tiles_b2 = nullptr, *d_tiles_bf = nullptr;
+        // (inner tiles: "ii" = all eight neighbours are inner tiles too, "ib" = next to a frame tile)
+        int  n_b2 = 0, n_ii = 0, n_ib = 0, n_bf = 0;
+        int  ii_rect[3] = {0, 0, 0};        // first tile, width, row stride when the ii tiles form a rectangle
+        int *d_tiles_ii = nullptr, *d_tiles_ib = nullptr, *d_tiles_bf = nullptr;
         CUtensorMap tmap_f[kFields], tmap_b[kFields], tmap_b2[kFields], tmap_store;
         size_t smem_f = 0, smem_b = 0, smem_b2 = 0;  // dynamic shared memory already granted to the kernels
     };
-    bool   fuse2 = true;                    // two backward steps per pass on the inner tiles
-    int    fuse2_maxrp = 4;                 // ... for operator classes up to this radius
+    // Pair stepping of the backward pass (two-step kernel on the inner tiles).  Measured on the
+    // B200 (profiles/README.md) it pays for the Taylor operator up to radius 4 once a launch holds a
+    // few waves of inner tiles; for longer operators and the adaptive operator it is opt-in:
+    //   RTM_FUSE2=0 off, =1 forced (any operator, any size), unset: automatic;
+    //   RTM_FUSE2_MAXRP=4|8 longest (rounded) radius stepped in pairs.
+    bool   fuse2 = true;
+    bool   fuse2_forced = false;
+    int    fuse2_maxrp = 4;
+    static constexpr int kFuse2MinCtas = 1500;  // automatic mode: inner-inner tiles x shots per launch
     bool   dry = false;                     // launch helpers only set kernel attributes
     long   nlaunch = 0;                     // kernels launched (graph replays included)
     std::map<long long, long> graph_launches;
@@ -378,7 +388,7 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
-    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_b2); cudaFree(k.d_tiles_bf); }
+    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); }
     cudaFree(c->store);
     for (auto& f : c->field) cudaFree(f);
     for (auto& f : c->acc) cudaFree(f);
@@ -394,6 +404,8 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     for (auto& a : c->aux) if (a) cudaStreamDestroy(a);
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     for (auto& e : c->join_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_ii) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_ib) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -449,7 +461,8 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     G.ntz_b = (G.mod_NZ + kWarps * RTM_NR_B - 1) / (kWarps * RTM_NR_B);
     G.nband = (G.NX + kRingTX - 1) / kRingTX; G.nside = (G.mod_NZ + kRingTX - 1) / kRingTX;
     if (const char* e = std::getenv("RTM_NO_GRAPH")) c->use_graphs = std::atoi(e) == 0;
-    if (const char* e = std::getenv("RTM_FUSE2")) c->fuse2 = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RTM_FUSE2")) { c->fuse2 = std::atoi(e) != 0; c->fuse2_forced = c->fuse2; }
+    if (!c->fuse2_forced && p->iLSTE == 0) c->fuse2 = false;
     if (const char* e = std::getenv("RTM_FUSE2_MAXRP")) c->fuse2_maxrp = std::atoi(e);
     if (p->flags & RTM_FLAG_STORE_ALL) c->fuse2 = false;
     for (int i = 0; i <= p->N2; ++i) G.w[i] = (float)((1.0 * i) / (1.0 * p->N2));  // :688-691
@@ -463,7 +476,13 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
                                  cudaGetErrorString(e_), __FILE__, __LINE__));                 \
     } while (0)
     CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (auto& a : c->aux) CKC(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    {   // aux[2] carries the ring/frame chain of the pair stepping: small launches, served first
+        int lo = 0, hi = 0;
+        CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (int i = 0; i < 3; ++i) CKC(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, i == 2 ? hi : lo));
+    }
+    for (auto& e : c->ev_ii) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : c->ev_ib) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
     for (auto& e : c->join_ev) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CKC(cudaEventCreate(&c->ev0));
@@ -547,10 +566,10 @@ static int prepare_ls(rtm_ctx* c)
 static int prepare_classes(rtm_ctx* c)
 {
     const Geo& G = c->G;
-    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_b2); cudaFree(k.d_tiles_bf); }
+    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); }
     c->classes.clear();
     const int nf = G.ntx * G.ntz_f, nb = G.ntx * G.ntz_b;
-    struct Lists { std::vector<int> fwd, bwd, bwd2, frame; };
+    struct Lists { std::vector<int> fwd, bwd, ii, ib, frame; };
     std::map<int, Lists> lists;  // RP -> tile lists
     const bool ls = G.iLSTE == 0;
     // an inner tile: full, and grown by one (rounded) radius it still lies in the interior
@@ -567,6 +586,31 @@ static int prepare_classes(rtm_ctx* c)
         for (int b = std::max(r.x, 0); b <= r.y && b < (int)c->h_M.size(); ++b) m = std::max(m, c->h_M[b]);
         return (m + 3) / 4 * 4;
     };
+    // Tiles advanced by the two-step kernel: vertical pairs (32 rows) of inner tiles whose grown
+    // operator is short enough.  covered[t]: tile t belongs to such a pair; head[t]: it is the upper one.
+    std::vector<int> rp2(nb, 0);
+    std::vector<char> ok(nb, 0), covered(nb, 0), head(nb, 0);
+    for (int t = 0; t < nb; ++t) {
+        rp2[t] = ls ? radius_class(tb2[t]) : c->RP;
+        ok[t]  = c->fuse2 && inner(t) && rp2[t] <= c->fuse2_maxrp && rp2[t] <= 8;
+    }
+    constexpr int gsz = Tile2<4>::TZ / (kWarps * RTM_NR_B);  // single-step tiles stacked in one two-step tile
+    for (int tx = 0; tx < G.ntx; ++tx)
+        for (int tz = 0; tz + gsz <= G.ntz_b;) {
+            const int t = tz * G.ntx + tx;
+            bool all = true;
+            for (int i = 0; i < gsz; ++i) all = all && ok[t + i * G.ntx];
+            if (!all) { ++tz; continue; }
+            head[t] = 1;
+            for (int i = 0; i < gsz; ++i) {
+                const int u = t + i * G.ntx;
+                covered[u] = 1;
+                rp2[t] = std::max(rp2[t], rp2[u]);
+                if (ls) tb2[t] = make_int2(std::min(tb2[t].x, tb2[u].x), std::max(tb2[t].y, tb2[u].y));
+            }
+            tz += gsz;
+        }
+    if (ls) CK(cudaMemcpy(c->d_tile_bins_b2, tb2.data(), sizeof(int2) * nb, cudaMemcpyHostToDevice));
     for (int pass = 0; pass < 2; ++pass) {
         const int n = pass ? nb : nf;
         if (ls) CK(cudaMemcpy(tb.data(), pass ? c->d_tile_bins_b : c->d_tile_bins_f, sizeof(int2) * n, cudaMemcpyDeviceToHost));
@@ -574,9 +618,12 @@ static int prepare_classes(rtm_ctx* c)
             const int rp = ls ? radius_class(tb[t]) : c->RP;
             if (!pass) { lists[rp].fwd.push_back(t); continue; }
             lists[rp].bwd.push_back(t);
-            const int rp2 = ls ? radius_class(tb2[t]) : c->RP;
-            if (c->fuse2 && inner(t) && rp2 <= c->fuse2_maxrp && rp2 <= 8) lists[rp2].bwd2.push_back(t);
-            else lists[rp].frame.push_back(t);
+            if (!covered[t]) { lists[rp].frame.push_back(t); continue; }
+            if (!head[t]) continue;
+            bool all = true;  // every tile around the pair is advanced by the two-step kernel as well
+            for (int dz = -1; dz <= gsz; ++dz)
+                for (int dx = -1; dx <= 1; ++dx) all = all && covered[t + dz * G.ntx + dx];
+            (all ? lists[rp2[t]].ii : lists[rp2[t]].ib).push_back(t);
         }
     }
     auto upload = [&](const std::vector<int>& v, int** d) -> int {
@@ -589,16 +636,27 @@ static int prepare_classes(rtm_ctx* c)
         rtm_ctx::TileClass k;
         k.RP = it->first;
         const Lists& L = it->second;
-        k.n_f = (int)L.fwd.size(); k.n_b = (int)L.bwd.size(); k.n_b2 = (int)L.bwd2.size(); k.n_bf = (int)L.frame.size();
+        k.n_f = (int)L.fwd.size(); k.n_b = (int)L.bwd.size(); k.n_bf = (int)L.frame.size();
+        k.n_ii = (int)L.ii.size(); k.n_ib = (int)L.ib.size(); k.n_b2 = k.n_ii + k.n_ib;
         // (a class that holds every tile needs no list: the kernel then uses the tile number itself)
         if (k.n_f < nf) if (int rc = upload(L.fwd, &k.d_tiles_f)) return rc;
         if (k.n_b < nb) if (int rc = upload(L.bwd, &k.d_tiles_b)) return rc;
-        if (int rc = upload(L.bwd2, &k.d_tiles_b2)) return rc;
+        if (int rc = upload(L.ii, &k.d_tiles_ii)) return rc;
+        if (k.n_ii > 1) {  // a rectangle?  (rows of equal width, equal row stride)
+            const std::vector<int>& v = L.ii;
+            int w = 1;
+            while (w < k.n_ii && v[w] == v[0] + w) ++w;
+            const int dz = w < k.n_ii ? v[w] - v[0] : G.ntx;
+            bool rect = k.n_ii % w == 0;
+            for (int i = 0; rect && i < k.n_ii; ++i) rect = v[i] == v[0] + (i / w) * dz + i % w;
+            if (rect) { k.ii_rect[0] = v[0]; k.ii_rect[1] = w; k.ii_rect[2] = dz; }
+        }
+        if (int rc = upload(L.ib, &k.d_tiles_ib)) return rc;
         if (int rc = upload(L.frame, &k.d_tiles_bf)) return rc;
         for (int i = 0; i < rtm_ctx::kFields; ++i) {
             int rc = encode_tmap(c, &k.tmap_f[i], c->field[i], k.RP, kWarps * RTM_NR_F);
             if (!rc) rc = encode_tmap(c, &k.tmap_b[i], c->field[i], k.RP, kWarps * RTM_NR_B);
-            if (!rc && k.n_b2) rc = encode_tmap(c, &k.tmap_b2[i], c->field[i], 2 * k.RP, kWarps * RTM_NR_B);
+            if (!rc && k.n_b2) rc = encode_tmap(c, &k.tmap_b2[i], c->field[i], 2 * k.RP, Tile2<4>::TZ);
             if (rc) return rc;
         }
         if (c->store_mode)
@@ -720,7 +778,7 @@ template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx
     bwd_step_kernel<RP, LS, RTM_NR_B, STORE><<<grid, kThreads, smem, st>>>(k.tmap_b[STORE ? r1 : s1], k.tmap_b[r1], G, a);
     return RTM_OK;
 }
-template <int RP, bool LS> static int launch_bwd2(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, Bwd2Args a)
+template <int RP, bool LS> static int launch_bwd2(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, Bwd2Args a, bool border)
 {
     if (k.n_b2 == 0) return RTM_OK;
     const size_t smem = (size_t)Tile2<RP>::BYTES + 16 + (LS ? (size_t)slice_bytes(RP) : 0);
@@ -728,18 +786,20 @@ template <int RP, bool LS> static int launch_bwd2(rtm_ctx* c, rtm_ctx::TileClass
         CK(cudaFuncSetAttribute(bwd2_step_kernel<RP, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k.smem_b2 = smem;
     }
-    a.tiles = k.d_tiles_b2; a.ntiles = k.n_b2;
-    if (c->dry) return RTM_OK;
+    a.tiles = border ? k.d_tiles_ib : k.d_tiles_ii; a.ntiles = border ? k.n_ib : k.n_ii;
+    a.rect_t0 = k.ii_rect[0]; a.rect_nx = border ? 0 : k.ii_rect[1]; a.rect_dz = k.ii_rect[2];
+    if (c->dry || a.ntiles == 0) return RTM_OK;
     ++c->nlaunch;
-    bwd2_step_kernel<RP, LS><<<(unsigned)(k.n_b2 * ns), kThreads, smem, st>>>(k.tmap_b2[s1], k.tmap_b2[r1], c->G, a);
+    bwd2_step_kernel<RP, LS><<<(unsigned)(a.ntiles * ns), kThreads, smem, st>>>(k.tmap_b2[s1], k.tmap_b2[r1], c->G, a);
     return RTM_OK;
 }
-static int dispatch_bwd2_class(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, const Bwd2Args& a)
+static int dispatch_bwd2_class(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, const Bwd2Args& a, bool border)
 {
     const bool ls = c->G.iLSTE == 0;
+    if (k.n_b2 == 0) return RTM_OK;
     switch (k.RP) {
-    case 4: return ls ? launch_bwd2<4, true>(c, k, st, ns, s1, r1, a) : launch_bwd2<4, false>(c, k, st, ns, s1, r1, a);
-    case 8: return ls ? launch_bwd2<8, true>(c, k, st, ns, s1, r1, a) : launch_bwd2<8, false>(c, k, st, ns, s1, r1, a);
+    case 4: return ls ? launch_bwd2<4, true>(c, k, st, ns, s1, r1, a, border) : launch_bwd2<4, false>(c, k, st, ns, s1, r1, a, border);
+    case 8: return ls ? launch_bwd2<8, true>(c, k, st, ns, s1, r1, a, border) : launch_bwd2<8, false>(c, k, st, ns, s1, r1, a, border);
     }
     return rtm_fail(RTM_ERR_ARG, "two-step kernel: unsupported operator radius %d", k.RP);
 }
@@ -1016,44 +1076,53 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
         const int t = Ra; Ra = Rb; Rb = Rc; Rc = t;
         return RTM_OK;
     };
-    // steps k and k-1: inner tiles by the two-step kernel, concurrently ring + frame tiles for slot k
-    // on a side stream, then ring + frame tiles for slot k-1
-    auto bstep2 = [&](int k) -> int {
-        CK(cudaEventRecord(c->fork_ev, c->stream));
-        for (auto& a : c->aux) CK(cudaStreamWaitEvent(a, c->fork_ev, 0));
-        Bwd2Args a2{};
-        a2.S0 = c->field[Sa]; a2.Sk = c->field[Sc]; a2.Skm = c->field[Sd];
-        a2.R0 = c->field[Ra]; a2.Rk = c->field[Rc]; a2.Rkm = c->field[Rd];
-        a2.src = c->d_src; a2.wavelet_k = wavelet(k); a2.wavelet_km = wavelet(k - 1);
-        a2.k = k; a2.nshots = ns; a2.seis = c->d_traces;
-        a2.sumS = c->acc[0]; a2.sumR = c->acc[1]; a2.rel1 = c->acc[2]; a2.rel2 = c->acc[3];
-        int nside = 0;
-        for (auto& kc : c->classes) {
-            if (!kc.n_b2) continue;
-            cudaStream_t st = nside == 0 ? c->stream : c->aux[(nside - 1) % 2];
-            ++nside;
-            if (int rc = dispatch_bwd2_class(c, kc, st, ns, Sb, Rb, a2)) return rc;
+    // Slots kfirst, kfirst-1, ..., 0 in pairs (k, k-1), software-pipelined over two streams:
+    //   A (main):  inner-inner tiles, two-step kernel                      L2ii(j)
+    //   B (aux 2): ring + frame tiles slot k (single-step kernel)          L1(j)
+    //              inner tiles next to the frame, two-step kernel          L2ib(j)
+    //              ring + frame tiles slot k-1                             L3(j)
+    // L2ii(j) needs L2ib(j-1) (its halo reaches into those tiles, and it overwrites what they read);
+    // L2ib(j) needs L2ii(j-1) for the same two reasons; everything else is ordered by stream B.
+    auto pair_loop = [&](int kfirst) -> int {
+        cudaStream_t A = c->stream, B = c->aux[2];
+        CK(cudaEventRecord(c->fork_ev, A));
+        CK(cudaStreamWaitEvent(B, c->fork_ev, 0));
+        int j = 0;
+        for (int k = kfirst; k >= 1; k -= 2, ++j) {
+            Bwd2Args a2{};
+            a2.S0 = c->field[Sa]; a2.Sk = c->field[Sc]; a2.Skm = c->field[Sd];
+            a2.R0 = c->field[Ra]; a2.Rk = c->field[Rc]; a2.Rkm = c->field[Rd];
+            a2.src = c->d_src; a2.wavelet_k = wavelet(k); a2.wavelet_km = wavelet(k - 1);
+            a2.k = k; a2.nshots = ns; a2.seis = c->d_traces;
+            a2.sumS = c->acc[0]; a2.sumR = c->acc[1]; a2.rel1 = c->acc[2]; a2.rel2 = c->acc[3];
+            if (j > 0) CK(cudaStreamWaitEvent(A, c->ev_ib[(j - 1) & 1], 0));
+            for (auto& kc : c->classes)
+                if (int rc = dispatch_bwd2_class(c, kc, A, ns, Sb, Rb, a2, false)) return rc;
+            CK(cudaEventRecord(c->ev_ii[j & 1], A));
+            if (int rc = dispatch_bwd(c, ns, Sb, Rb, args1(k, Sa, Sc, Ra, Rb, Rc), true, B)) return rc;
+            if (j > 0) CK(cudaStreamWaitEvent(B, c->ev_ii[(j - 1) & 1], 0));
+            for (auto& kc : c->classes)
+                if (int rc = dispatch_bwd2_class(c, kc, B, ns, Sb, Rb, a2, true)) return rc;
+            CK(cudaEventRecord(c->ev_ib[j & 1], B));
+            if (int rc = dispatch_bwd(c, ns, Sc, Rc, args1(k - 1, Sb, Sd, Rb, Rc, Rd), true, B)) return rc;
+            std::swap(Sa, Sc); std::swap(Sb, Sd);
+            std::swap(Ra, Rc); std::swap(Rb, Rd);
         }
-        if (int rc = dispatch_bwd(c, ns, Sb, Rb, args1(k, Sa, Sc, Ra, Rb, Rc), true, c->aux[2])) return rc;
-        for (int i = 0; i < 3; ++i) {
-            CK(cudaEventRecord(c->join_ev[i], c->aux[i]));
-            CK(cudaStreamWaitEvent(c->stream, c->join_ev[i], 0));
-        }
-        if (int rc = dispatch_bwd(c, ns, Sc, Rc, args1(k - 1, Sb, Sd, Rb, Rc, Rd), true)) return rc;
-        std::swap(Sa, Sc); std::swap(Sb, Sd);
-        std::swap(Ra, Rc); std::swap(Rb, Rd);
+        CK(cudaEventRecord(c->join_ev[2], B));
+        CK(cudaStreamWaitEvent(A, c->join_ev[2], 0));
         return RTM_OK;
     };
     bool pairs = c->fuse2 && !store;
     if (pairs) {
-        pairs = false;
-        for (auto& kc : c->classes) pairs = pairs || kc.n_b2 > 0;
+        long nii = 0, nb2 = 0;
+        for (auto& kc : c->classes) { nii += kc.n_ii; nb2 += kc.n_b2; }
+        pairs = nb2 > 0 && (c->fuse2_forced || nii * ns >= rtm_ctx::kFuse2MinCtas);
     }
     auto loop = [&](int kfirst) -> int {  // slots kfirst .. 0
         int k = kfirst;
         if (pairs) {
             if ((k + 1) % 2) { if (int rc = bstep(k)) return rc; --k; }
-            for (; k >= 1; k -= 2) if (int rc = bstep2(k)) return rc;
+            if (k >= 1) if (int rc = pair_loop(k)) return rc;
         } else {
             for (; k >= 0; --k) if (int rc = bstep(k)) return rc;
         }
@@ -1066,7 +1135,7 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
             const int sv[8] = {Sa, Sb, Sc, Sd, Ra, Rb, Rc, Rd};
             c->dry = true;
             int rc = bstep(G.NT - 3);
-            if (!rc && pairs) rc = bstep2(G.NT - 3);
+            if (!rc && pairs) rc = pair_loop(1);
             c->dry = false;
             Sa = sv[0]; Sb = sv[1]; Sc = sv[2]; Sd = sv[3]; Ra = sv[4]; Rb = sv[5]; Rc = sv[6]; Rd = sv[7];
             if (rc) return rc;

@@ -36,7 +36,10 @@ constexpr int kTX      = 128;  // interior tile width  (32 lanes x float4)
 #define RTM_NR_B 2
 #endif
 constexpr int kWarps   = kThreads / 32;
-constexpr int kRingTX  = 128;  // ring tile extent along the band
+#ifndef RTM_RING_TX
+#define RTM_RING_TX 128
+#endif
+constexpr int kRingTX  = RTM_RING_TX;  // ring tile extent along the band
 constexpr int kMaxR    = 16;
 constexpr int kSliceBins = 768;  // velocity bins whose coefficient rows a tile can stage in shared memory
 __host__ __device__ constexpr int slice_bytes(int RP) { return RP >= 8 ? 24576 : kSliceBins * (RP + 5) * 4; }
@@ -258,7 +261,6 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
     float* s1 = smem;                          // (ch+2R) x SP
     float* s0 = s1 + (ch + 2 * R) * SP;        // ch x cw   previous field
     float* s2 = s0 + ch * cw;                  // ch x cw   unblended two-way result
-    const int tid = threadIdx.x;
 
     for_cells(ch + 2 * R, SP, [&](int r, int cidx) {
         int gz = cza - R + r, gx = cxa - R + cidx;
@@ -962,13 +964,22 @@ struct Bwd2Args {
     int          nshots;
     const int*   tiles;   // inner tiles of this launch
     int          ntiles;
+    int          rect_t0, rect_nx;  // rect_nx > 0: the tiles form a rectangle rect_nx wide starting at tile rect_t0,
+                                    // row stride rect_dz tiles (no list lookup before the TMA copies are issued)
+    int          rect_dz;
     const float* seis;    // [S][NT][n]; row k+1 is imposed in step k, row k in step k-1
     float *sumS, *sumR, *rel1, *rel2;
 };
 
+// shape of the two-step kernel, tuned on the B200 (profiles/README.md)
+#ifndef RTM_NR_B2
+#define RTM_NR_B2 2      // rows per thread in phase B: tile height 8 * RTM_NR_B2, a multiple of the single-step tile's
+#endif
 template <int RP> struct Tile2 {
-    static constexpr int NR   = RTM_NR_B;
-    static constexpr int TZ   = kWarps * NR;
+    static constexpr int NR   = RTM_NR_B2;                 // rows per thread in phase B
+    static constexpr int TZ   = kWarps * NR;               // one or two tiles of the single-step tiling
+    static_assert(TZ % (kWarps * RTM_NR_B) == 0, "two-step tiles are stacks of single-step tiles");
+    static constexpr int NRA  = (TZ + 2 * RP) / kWarps;    // grown rows per thread in phase A
     static constexpr int SPA  = kTX + 4 * RP, ROWSA = TZ + 4 * RP;  // slot k+1 boxes (halo 2*RP)
     static constexpr int SPB  = kTX + 2 * RP, ROWSB = TZ + 2 * RP;  // slot k mid tiles (halo RP)
     static constexpr int CUR_BYTES = SPA * ROWSA * 4, MID_BYTES = SPB * ROWSB * 4;
@@ -976,10 +987,10 @@ template <int RP> struct Tile2 {
 };
 
 #ifndef RTM_BWD2_MINB
-#define RTM_BWD2_MINB 3
+#define RTM_BWD2_MINB (RTM_NR_B2 <= 2 ? 3 : 2)
 #endif
 template <int RP, bool LS>
-__global__ void __launch_bounds__(kThreads, (RP <= 4 ? RTM_BWD2_MINB : (RP <= 8 ? 2 : 1)))
+__global__ void __launch_bounds__(kThreads, (RP <= 4 ? RTM_BWD2_MINB : (RP <= 8 && RTM_NR_B2 <= 2 ? 2 : 1)))
 bwd2_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmR1,
                  const __grid_constant__ Geo G, const Bwd2Args a)
 {
@@ -987,11 +998,12 @@ bwd2_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant
     constexpr int NR = T2::NR, SPA = T2::SPA, SPB = T2::SPB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int  shot = blockIdx.x / a.ntiles;
-    const int  t    = a.tiles[blockIdx.x % a.ntiles];
+    const int  ti   = blockIdx.x % a.ntiles;
+    const int  t    = a.rect_nx > 0 ? a.rect_t0 + (ti / a.rect_nx) * a.rect_dz + ti % a.rect_nx : a.tiles[ti];
     const long long so = (long long)shot * G.shot_stride + G.padL;
     const int2 src = a.src[shot];
     const int  tz  = t / G.ntx, tx = t % G.ntx;
-    const int  z0  = G.N2 + tz * T2::TZ, x0 = G.N2 + tx * kTX;
+    const int  z0  = G.N2 + tz * (kWarps * RTM_NR_B), x0 = G.N2 + tx * kTX;  // t counts single-step tiles
     float*    sS1 = reinterpret_cast<float*>(smem_raw);
     float*    sR1 = reinterpret_cast<float*>(smem_raw + T2::CUR_BYTES);
     float*    mS  = reinterpret_cast<float*>(smem_raw + 2 * T2::CUR_BYTES);
@@ -1054,25 +1066,28 @@ bwd2_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant
         };
         // main part: lane -> group GH+lane (the tile's own columns), warp -> NRA consecutive rows
         const int rg0 = warp * NRA;
-        size_t    cell = (size_t)(z0 - RP + rg0) * G.pitch + x0 + 4 * lane;
-        float4 s0n = __ldg(reinterpret_cast<const float4*>(S0 + cell));
-        float4 r0n = __ldg(reinterpret_cast<const float4*>(R0 + cell));
-        float4 avn = __ldg(reinterpret_cast<const float4*>(AV + cell));
-        uint2  bn  = make_uint2(0u, 0u);
-        if (LS) bn = __ldg(reinterpret_cast<const uint2*>(BN + cell));
-        mbar_wait(bar, 0);
+        const size_t cell0 = (size_t)(z0 - RP + rg0) * G.pitch + x0 + 4 * lane;
+        {
+            size_t cell = cell0;
+            float4 s0n = __ldg(reinterpret_cast<const float4*>(S0 + cell));
+            float4 r0n = __ldg(reinterpret_cast<const float4*>(R0 + cell));
+            float4 avn = __ldg(reinterpret_cast<const float4*>(AV + cell));
+            uint2  bn  = make_uint2(0u, 0u);
+            if (LS) bn = __ldg(reinterpret_cast<const uint2*>(BN + cell));
+            mbar_wait(bar, 0);
 #pragma unroll
-        for (int r = 0; r < NRA; ++r) {
-            const float4 s0c = s0n, r0c = r0n, avc = avn;
-            const uint2  bc  = bn;
-            if (r + 1 < NRA) {
-                cell += G.pitch;
-                s0n = __ldg(reinterpret_cast<const float4*>(S0 + cell));
-                r0n = __ldg(reinterpret_cast<const float4*>(R0 + cell));
-                avn = __ldg(reinterpret_cast<const float4*>(AV + cell));
-                if (LS) bn = __ldg(reinterpret_cast<const uint2*>(BN + cell));
+            for (int r = 0; r < NRA; ++r) {
+                const float4 s0c = s0n, r0c = r0n, avc = avn;
+                const uint2  bc  = bn;
+                if (r + 1 < NRA) {
+                    cell += G.pitch;
+                    s0n = __ldg(reinterpret_cast<const float4*>(S0 + cell));
+                    r0n = __ldg(reinterpret_cast<const float4*>(R0 + cell));
+                    avn = __ldg(reinterpret_cast<const float4*>(AV + cell));
+                    if (LS) bn = __ldg(reinterpret_cast<const uint2*>(BN + cell));
+                }
+                item(rg0 + r, GH + lane, s0c, r0c, avc, bc);
             }
-            item(rg0 + r, GH + lane, s0c, r0c, avc, bc);
         }
         // the 2*GH halo groups of every grown row, flattened over the CTA
         for (int i = tid; i < T2::ROWSB * 2 * GH; i += kThreads) {
@@ -1087,6 +1102,17 @@ bwd2_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant
             item(rg, g, s0c, r0c, avc, bc);
         }
     }
+    // first-row loads of phase B fly across the barrier (phase A's registers are dead here)
+    const size_t cellB = (size_t)(z0 + warp * NR) * G.pitch + x0 + lane * 4;
+    const bool   compenB = G.iCompen == 1;
+    float4 avB = __ldg(reinterpret_cast<const float4*>(AV + cellB));
+    float4 a1B = *reinterpret_cast<const float4*>(a.rel1 + so + cellB);
+    float4 a2B = *reinterpret_cast<const float4*>(a.rel2 + so + cellB);
+    float4 aSB = make_float4(0.f, 0.f, 0.f, 0.f), aRB = aSB;
+    if (compenB) {
+        aSB = *reinterpret_cast<const float4*>(a.sumS + so + cellB);
+        aRB = *reinterpret_cast<const float4*>(a.sumR + so + cellB);
+    }
     __syncthreads();
 
     // ---- phase B: slot k-1 on the tile (always a full tile), imaging updates of both steps
@@ -1097,17 +1123,19 @@ bwd2_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant
         const float* seisB = a.seis + ((size_t)shot * G.NT + a.k) * G.n;
         size_t cell = (size_t)z * G.pitch + x;
         size_t o    = so + cell;
-        float4 avn = __ldg(reinterpret_cast<const float4*>(AV + cell));
+        float4 avn = avB;
         uint2  bn  = make_uint2(0u, 0u);
         if (LS) bn = __ldg(reinterpret_cast<const uint2*>(BN + cell));
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            const float4 a1 = *reinterpret_cast<const float4*>(a.rel1 + o);
-            const float4 a2 = *reinterpret_cast<const float4*>(a.rel2 + o);
-            float4 aS = make_float4(0.f, 0.f, 0.f, 0.f), aR = aS;
-            if (compen) {
-                aS = *reinterpret_cast<const float4*>(a.sumS + o);
-                aR = *reinterpret_cast<const float4*>(a.sumR + o);
+            float4 a1 = a1B, a2 = a2B, aS = aSB, aR = aRB;
+            if (r > 0) {
+                a1 = *reinterpret_cast<const float4*>(a.rel1 + o);
+                a2 = *reinterpret_cast<const float4*>(a.rel2 + o);
+                if (compen) {
+                    aS = *reinterpret_cast<const float4*>(a.sumS + o);
+                    aR = *reinterpret_cast<const float4*>(a.sumR + o);
+                }
             }
             float av[4];
             unpack(avn, av);
