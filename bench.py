@@ -12,8 +12,12 @@ SHOTS_PER_STEP shots; with the default K=8 steps the timed region covers the 64 
          on the stream the kernels run on; max over ranks)
   e2e    same metric through the host-buffer C-ABI call rtm_migrate(): pinned host traces in,
          per-shot images out, H2D/D2H copies inside the timed region (wall clock, synchronised)
-  roofline      the fused backward step kernel: algorithmic bytes (60 B per grid cell per step,
-                SURVEY.md 8d) / average launch time from CUDA events / measured HBM peak
+  roofline      the backward time step (source reconstruction + receiver step + ABC + imaging):
+                algorithmic bytes (60 B per grid cell per step) / average time per step
+                from CUDA events / measured HBM peak.  The backward pass advances two steps per pass
+                on the inner tiles (bwd2_step_kernel: 68 B per cell and PAIR of steps), so the
+                algorithmic figure can exceed the peak; `dram` gives the same with the bytes that
+                really crossed HBM (ncu, profiles/traffic.json)
   cpu_baseline  the reference's own kernels run on the host (oracle/_ref/ref_cpu_fast), one
                 process per shot on all host cores, on a bounded sample of the same workload
 
@@ -368,16 +372,23 @@ def main():
     achieved = bwd_bytes_per_launch / (bwd_ms * 1e-3) / 1e9
     fwd_ms = 1e3 * st["forward_seconds"] / bwd_launches
     traffic = None
+    pairs = os.environ.get("RTM_FUSE2", "1") != "0"
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get("bwd_step_kernel_dram_bytes_per_launch")
+            traffic = json.loads(tf.read_text()).get("bwd_pair_dram_bytes_per_step" if pairs else "bwd_step_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "bwd_step_kernel (source reconstruction + receiver step + ABC + imaging)",
+    roofline = {"bound": "hbm",
+                "kernel": ("backward time step = bwd2_step_kernel (inner tiles, two steps per pass) + bwd_step_kernel (ring + frame tiles)"
+                           if pairs else "bwd_step_kernel (source reconstruction + receiver step + ABC + imaging)"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes_per_launch,
                 "avg_launch_ms": bwd_ms,
+                "note": ("per time step; pair stepping moves fewer bytes than the single-step algorithmic 60 B/cell, "
+                         "so `frac` may exceed 1; `dram` = bytes that crossed HBM per step (ncu) over the same time"),
+                "dram": (None if not traffic else {"bytes_per_step": traffic, "achieved": traffic / (bwd_ms * 1e-3) / 1e9,
+                                                   "frac": traffic / (bwd_ms * 1e-3) / 1e9 / peak}),
                 "forward_step": {"achieved": 16.0 * w.NZ * w.NX * B / (fwd_ms * 1e-3) / 1e9, "avg_launch_ms": fwd_ms,
                                  "frac": 16.0 * w.NZ * w.NX * B / (fwd_ms * 1e-3) / 1e9 / peak}}
     launches = st["kernel_launches"]

@@ -748,7 +748,7 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass&
     const Geo& G = c->G;
     const int nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0;
     size_t smem = (size_t)Tile<RP, RTM_NR_F>::BYTES + 16 + (LS ? (size_t)slice_bytes(RP) : 0);
-    if (a.do_ring) smem = std::max(smem, (size_t)ring_smem_floats(G.N2, G.mmax) * 4);
+    if (a.do_ring) smem = std::max(smem, (size_t)ring_smem_floats(G.N2, G.mmax, RP) * 4);
     if (smem > k.smem_f) {  // per device, once
         CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS, RTM_NR_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k.smem_f = smem;
@@ -766,7 +766,7 @@ template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx
     const Geo& G = c->G;
     const int nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0;
     size_t smem = (size_t)(STORE ? 1 : 2) * Tile<RP, RTM_NR_B>::BYTES + 16 + (LS ? (size_t)slice_bytes(RP) : 0);
-    if (a.do_ring) smem = std::max(smem, (size_t)ring_smem_floats(G.N2, G.mmax) * 4);
+    if (a.do_ring) smem = std::max(smem, (size_t)ring_smem_floats(G.N2, G.mmax, RP) * 4);
     if (smem > k.smem_b) {
         CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k.smem_b = smem;

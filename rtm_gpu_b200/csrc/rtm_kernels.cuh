@@ -37,9 +37,9 @@ constexpr int kTX      = 128;  // interior tile width  (32 lanes x float4)
 #endif
 constexpr int kWarps   = kThreads / 32;
 #ifndef RTM_RING_TX
-#define RTM_RING_TX 128
+#define RTM_RING_TX 126
 #endif
-constexpr int kRingTX  = RTM_RING_TX;  // ring tile extent along the band
+constexpr int kRingTX  = RTM_RING_TX;  // ring tile extent along the band: grown by one cell on both sides = 32 float4 groups
 constexpr int kMaxR    = 16;
 constexpr int kSliceBins = 768;  // velocity bins whose coefficient rows a tile can stage in shared memory
 __host__ __device__ constexpr int slice_bytes(int RP) { return RP >= 8 ? 24576 : kSliceBins * (RP + 5) * 4; }
@@ -156,198 +156,12 @@ __device__ __forceinline__ float w1_first_ls(const Geo& G, float c0, float p1)
                        : __double2float_rn(__dmul_rn(__dmul_rn(G.A, (double)c0), (double)p1));
 }
 
-// ------------------------------------------------------------------ generic cell (ring path)
-// Two-way update of the cell whose current-field value is *sc in a shared tile of pitch SP.
-template <bool LS>
-__device__ __forceinline__ float two_way_generic(const Geo& G, const float* sc, int SP, float p0,
-                                                 float vv, int bin, int sum_kind)
-{
-    const float p1 = sc[0];
-    float       w1;
-    if (LS) {
-        const int top = __ldg(G.Index + bin), M = __ldg(G.Index + bin + 1) - top - 1;  // bin precomputed per cell
-        const float* cp = G.c + top;
-        w1 = w1_first_ls(G, __ldg(cp), p1);
-        for (int l = 1; l <= M; ++l) {
-            const float s = __fadd_rn(sc[-l * SP], sc[l * SP]);
-            const float t = __fmaf_rn(s, G.hzx2_1, sc[-l]);
-            const float u = __fadd_rn(t, sc[l]);
-            w1            = __fmaf_rn(__ldg(cp + l), u, w1);
-        }
-    } else {
-        w1 = w1_first_te(G, p1);
-        for (int l = 1; l <= G.nfdmax; ++l) {
-            const float s = __fadd_rn(sc[-l * SP], sc[l * SP]);
-            const float t = __fmaf_rn(s, G.hzx2_1, sc[-l]);
-            const float u = __fadd_rn(t, sc[l]);
-            w1            = __fmaf_rn(G.cTE[l], u, w1);
-        }
-    }
-    const float a = vel_factor(G, vv);
-    return sum_kind == SUM_FLOAT ? finish_float(a, w1, p1, p0) : finish_double(a, w1, p1, p0);
-}
-
 // data cell test of BKAdd (:349-353): row s_z, s_l <= x <= s_r, (x-s_l)%ds==0
 __device__ __forceinline__ int data_index(const Geo& G, int z, int x)
 {
     if (z != G.s_z || x < G.s_l || x > G.s_r) return -1;
     const int d = x - G.s_l;
     return (d % G.ds == 0) ? d / G.ds : -1;
-}
-
-// One ring tile.  Output rectangle [za,zb) x [xa,xb) lies in the ring; the two-way update is
-// evaluated on that rectangle grown by one cell (clipped to the array), because the one-way
-// formulas need the UNBLENDED two-way values of neighbours (Hybrid1 reads DFW2 before
-// Hybrid2 blends it).  Returns the blended value through `emit(z, x, value)`.
-struct RingRect { int za, zb, xa, xb; };
-
-__device__ __forceinline__ RingRect ring_rect(const Geo& G, int tile)
-{
-    RingRect r;
-    const int N2 = G.N2;
-    if (tile < 2 * G.nband) {  // top / bottom band: all columns
-        const bool top = tile < G.nband;
-        const int  i   = top ? tile : tile - G.nband;
-        r.za = top ? 0 : G.NZ - N2;
-        r.zb = r.za + N2;
-        r.xa = i * kRingTX;
-        r.xb = min(r.xa + kRingTX, G.NX);
-    } else {  // left / right side: interior rows
-        tile -= 2 * G.nband;
-        const bool left = tile < G.nside;
-        const int  i    = left ? tile : tile - G.nside;
-        r.xa = left ? 0 : G.NX - N2;
-        r.xb = r.xa + N2;
-        r.za = N2 + i * kRingTX;
-        r.zb = min(r.za + kRingTX, G.NZ - N2);
-    }
-    return r;
-}
-
-// shared memory needed by a ring tile (floats)
-__host__ __device__ inline int ring_smem_floats(int N2, int R)
-{
-    const int a = (N2 + 2 + 2 * R) * (kRingTX + 2 + 2 * R);  // current field with stencil halo
-    const int b = (N2 + 2) * (kRingTX + 2);                  // previous field, two-way result
-    return a + 2 * b;
-}
-
-// Visit the cells of an h x w rectangle with the CTA's 256 threads: row-per-warp when rows are
-// wide (band tiles, coalesced), flat indexing when they are narrow (side tiles, N2+2 columns).
-template <class F> __device__ __forceinline__ void for_cells(int h, int w, F f)
-{
-    if (w >= 32) {
-        for (int r = threadIdx.x >> 5; r < h; r += kWarps)
-            for (int c = threadIdx.x & 31; c < w; c += 32) f(r, c);
-    } else {
-        for (int i = threadIdx.x; i < h * w; i += kThreads) f(i / w, i % w);
-    }
-}
-
-template <bool LS, class Emit>
-__device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* __restrict__ P1,
-                                          const float* __restrict__ P0, int sum_kind,
-                                          bool inject, int r_u, int r_x, float wavelet,
-                                          const float* __restrict__ seis_row, float* smem, Emit emit)
-{
-    const RingRect o  = ring_rect(G, tile);
-    const int      NZ = G.NZ, NX = G.NX, N2 = G.N2, R = G.mmax, pitch = G.pitch;
-    const float*   V  = G.v + G.padL;  // cell (z,x) of the model at V[z*pitch+x]
-    // compute rectangle = output grown by 1, clipped
-    const int cza = max(o.za - 1, 0), czb = min(o.zb + 1, NZ);
-    const int cxa = max(o.xa - 1, 0), cxb = min(o.xb + 1, NX);
-    const int ch = czb - cza, cw = cxb - cxa;
-    const int SP = cw + 2 * R;  // pitch of the current-field tile (with halo R)
-    float* s1 = smem;                          // (ch+2R) x SP
-    float* s0 = s1 + (ch + 2 * R) * SP;        // ch x cw   previous field
-    float* s2 = s0 + ch * cw;                  // ch x cw   unblended two-way result
-
-    for_cells(ch + 2 * R, SP, [&](int r, int cidx) {
-        int gz = cza - R + r, gx = cxa - R + cidx;
-        if (gz < 0) gz = -gz;                      // mirror about the array edge (:65-68)
-        if (gz >= NZ) gz = 2 * NZ - 2 - gz;
-        if (gx < 0) gx = -gx;
-        if (gx >= NX) gx = 2 * NX - 2 - gx;
-        s1[r * SP + cidx] = P1[(size_t)gz * pitch + gx];
-    });
-    for_cells(ch, cw, [&](int r, int cidx) { s0[r * cw + cidx] = P0[(size_t)(cza + r) * pitch + cxa + cidx]; });
-    __syncthreads();
-
-    for_cells(ch, cw, [&](int lz, int lx) {
-        const int z = cza + lz, x = cxa + lx, i = lz * cw + lx;
-        float     val;
-        int       j = seis_row ? data_index(G, z, x) : -1;
-        float     d = (j >= 0) ? seis_row[j] : 0.0f;
-        if (j >= 0 && d != 0.0f) {
-            val = d;  // replacement (BKAdd :349-353)
-        } else {
-            const float vv  = __ldg(V + (size_t)z * pitch + x);
-            const int   bin = LS ? (int)__ldg(G.bins + G.padL + (size_t)z * pitch + x) : 0;
-            val = two_way_generic<LS>(G, s1 + (lz + R) * SP + lx + R, SP, s0[i], vv, bin, sum_kind);
-        }
-        if (inject && z == r_u && x == r_x) val = __fadd_rn(val, wavelet);
-        s2[i] = val;
-    });
-    __syncthreads();
-
-    const int oh = o.zb - o.za, ow = o.xb - o.xa;
-    for_cells(oh, ow, [&](int oz, int ox) {
-        const int z = o.za + oz, x = o.xa + ox;
-        const int lz = z - cza, lx = x - cxa;
-        const int dz = min(z, NZ - 1 - z), dx = min(x, NX - 1 - x);
-        const int a  = min(dz, dx);
-        const int sz = (z < NZ - 1 - z) ? 1 : -1, sx = (x < NX - 1 - x) ? 1 : -1;
-#define S2(zz, xx) s2[(lz + (zz)) * cw + lx + (xx)]
-#define S0(zz, xx) s0[(lz + (zz)) * cw + lx + (xx)]
-#define S1(zz, xx) s1[(lz + R + (zz)) * SP + lx + R + (xx)]
-        float Pb;
-        if (abs(dz - dx) <= 1) {
-            // corner cells (Hybrid1 :138-155): r1 = sqrt((v*tao/h)^2/2) at the cell itself
-            // (GPU_velocity_real.cpp:104-117; tao/h enters as v*tao/h in float)
-            const float vv = __ldg(V + (size_t)z * pitch + x);
-            const float r  = __fdiv_rn(__fmul_rn(vv, G.tao), G.h);
-            const float r2 = __double2float_rn(__dmul_rn(__dmul_rn((double)r, (double)r), 0.5));
-            const float r1 = __fsqrt_rn(r2);
-            const float rcp = __frcp_rn(__fmaf_rn(2.0f, r1, 1.0f));
-            const float nb  = __fadd_rn(S2(0, sx), S2(sz, 0));
-            Pb = __fmul_rn(rcp, __fmaf_rn(r1, nb, S1(0, 0)));
-        } else {
-            int   iz, ix, tz, tx;
-            float vq;
-            if (dz < dx) {  // top :124 / bottom :132
-                iz = sz; ix = 0; tz = 0; tx = 1;
-                vq = __ldg(V + (size_t)a * pitch + x);
-            } else {        // left :128 / right :136: flat index (N2-l)*NX + row
-                iz = 0; ix = sx; tz = 1; tx = 0;
-                const int flat = a * NX + z;
-                vq = __ldg(V + (size_t)(flat / NX) * pitch + flat % NX);
-            }
-            const float vb  = __ldg(V + (size_t)z * pitch + x);
-            const float tv  = __fmul_rn(G.taoh, vb);
-            const float rcp = __frcp_rn(__fadd_rn(tv, 1.0f));
-            const float p2i = S2(iz, ix), p0i = S0(iz, ix), p0b = S0(0, 0);
-            const float p1b = S1(0, 0), p1i = S1(iz, ix);
-            const float A1  = __fadd_rn(__fsub_rn(p2i, p0i), p0b);
-            float B = __fadd_rn(__fmul_rn(-2.0f, p1b), p0b);
-            B       = __fadd_rn(B, p2i);
-            B       = __fsub_rn(B, __fmul_rn(2.0f, p1i));
-            B       = __fadd_rn(B, p0i);
-            float D = __fsub_rn(S2(iz + tz, ix + tx), __fmul_rn(2.0f, p2i));
-            D       = __fadd_rn(D, S2(iz - tz, ix - tx));
-            D       = __fadd_rn(D, S0(tz, tx));
-            D       = __fsub_rn(D, __fmul_rn(2.0f, p0b));
-            D       = __fadd_rn(D, S0(-tz, -tx));
-            const float c2 = __fmul_rn(__fmul_rn(G.taoh2, vq), vq);
-            Pb = __fmul_rn(rcp, __fmaf_rn(c2, D, __fmaf_rn(tv, A1, -B)));
-        }
-        // blend (Hybrid2 :160-183): fma(1-w, P2, w*Pb)
-        const float w   = G.w[N2 - a];
-        const float val = __fmaf_rn(__fsub_rn(1.0f, w), S2(0, 0), __fmul_rn(w, Pb));
-#undef S2
-#undef S0
-#undef S1
-        emit(z, x, val);
-    });
 }
 
 }  // namespace rtmk
@@ -440,10 +254,12 @@ __device__ __forceinline__ LsTable ls_stage_slice(const Geo& G, int2 tb, float* 
 // keeps the register footprint small enough for 3-4 resident CTAs per SM.
 // M <= RP is the uniform length of the Taylor operator; the adaptive operator brings a length
 // and table offset per cell (from the cell's velocity bin).
-template <int RP, bool LS, int SP = kTX + 2 * RP>
+// SPT: pitch of the shared tile (floats); 0 = run-time pitch `spr` (ring tiles).
+template <int RP, bool LS, int SPT = kTX + 2 * RP>
 __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M, const LsTable& T,
-                                            uint2 bins4, float (&w1)[4], float (&p1)[4])
+                                            uint2 bins4, float (&w1)[4], float (&p1)[4], int spr = 0)
 {
+    const int SP = SPT ? SPT : spr;
     float xr[4 + 2 * RP];  // columns x-RP .. x+3+RP of this row
 #pragma unroll
     for (int g = 0; g < (4 + 2 * RP) / 4; ++g) {
@@ -550,6 +366,208 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
     }
 }
 
+// =====================================================================================
+// Ring tiles (hybrid absorbing boundary)
+// =====================================================================================
+// One ring tile.  Output rectangle [za,zb) x [xa,xb) lies in the ring; the two-way update is
+// evaluated on that rectangle grown by one cell (clipped to the array), because the one-way
+// formulas need the UNBLENDED two-way values of neighbours (Hybrid1 reads DFW2 before
+// Hybrid2 blends it).  Returns the blended value through `emit(z, x, value)`.
+struct RingRect { int za, zb, xa, xb; };
+
+__device__ __forceinline__ RingRect ring_rect(const Geo& G, int tile)
+{
+    RingRect r;
+    const int N2 = G.N2;
+    if (tile < 2 * G.nband) {  // top / bottom band: all columns
+        const bool top = tile < G.nband;
+        const int  i   = top ? tile : tile - G.nband;
+        r.za = top ? 0 : G.NZ - N2;
+        r.zb = r.za + N2;
+        r.xa = i * kRingTX;
+        r.xb = min(r.xa + kRingTX, G.NX);
+    } else {  // left / right side: interior rows
+        tile -= 2 * G.nband;
+        const bool left = tile < G.nside;
+        const int  i    = left ? tile : tile - G.nside;
+        r.xa = left ? 0 : G.NX - N2;
+        r.xb = r.xa + N2;
+        r.za = N2 + i * kRingTX;
+        r.zb = min(r.za + kRingTX, G.NZ - N2);
+    }
+    return r;
+}
+
+// shared memory needed by a ring tile (floats): current field with the stencil halo (rows: R,
+// columns: RP), previous field and two-way result on the compute rectangle padded to float4 groups
+__host__ __device__ inline int ring_smem_floats(int N2, int R, int RP)
+{
+    const int wb = (kRingTX + 2 + 3) / 4 * 4, ws = (N2 + 2 + 3) / 4 * 4;  // band / side compute widths
+    const int band = (N2 + 2 + 2 * R) * (wb + 2 * RP) + 2 * (N2 + 2) * wb;
+    const int side = (kRingTX + 2 + 2 * R) * (ws + 2 * RP) + 2 * (kRingTX + 2) * ws;
+    return band > side ? band : side;
+}
+
+// Visit the cells of an h x w rectangle with the CTA's 256 threads without integer division:
+// wide rows (band tiles) go row-per-warp, narrow rows (side tiles) 16 or 32 columns per row slot.
+template <class F> __device__ __forceinline__ void for_cells(int h, int w, F f)
+{
+    if (w > 32) {
+        for (int r = threadIdx.x >> 5; r < h; r += kWarps)
+            for (int c = threadIdx.x & 31; c < w; c += 32) f(r, c);
+    } else if (w > 16) {
+        const int c = threadIdx.x & 31;
+        if (c < w)
+            for (int r = threadIdx.x >> 5; r < h; r += kThreads / 32) f(r, c);
+    } else {
+        const int c = threadIdx.x & 15;
+        if (c < w)
+            for (int r = threadIdx.x >> 4; r < h; r += kThreads / 16) f(r, c);
+    }
+}
+
+template <int RP, bool LS, class Emit>
+__device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* __restrict__ P1,
+                                          const float* __restrict__ P0, int sum_kind,
+                                          bool inject, int r_u, int r_x, float wavelet,
+                                          const float* __restrict__ seis_row, float* smem, Emit emit)
+{
+    const RingRect o  = ring_rect(G, tile);
+    const int      NZ = G.NZ, NX = G.NX, N2 = G.N2, R = G.mmax, pitch = G.pitch;
+    const float*   V  = G.v + G.padL;  // cell (z,x) of the model at V[z*pitch+x]
+    // compute rectangle = output grown by 1, clipped; padded to whole float4 groups in x
+    const int cza = max(o.za - 1, 0), czb = min(o.zb + 1, NZ);
+    const int cxa = max(o.xa - 1, 0), cxb = min(o.xb + 1, NX);
+    const int ch = czb - cza, cw = cxb - cxa;
+    const int NG = (cw + 3) >> 2, CW = 4 * NG;
+    const int SP = CW + 2 * RP;                // pitch of the current-field tile
+    float* s1 = smem;                          // (ch+2R) x SP: row 0 = z cza-R, column 0 = x cxa-RP
+    float* s0 = s1 + (ch + 2 * R) * SP;        // ch x CW   previous field
+    float* s2 = s0 + ch * CW;                  // ch x CW   unblended two-way result
+
+    for_cells(ch + 2 * R, SP, [&](int r, int cidx) {
+        int gz = cza - R + r, gx = cxa - RP + cidx;
+        if (gz < 0) gz = -gz;                      // mirror about the array edge (:65-68)
+        if (gz >= NZ) gz = 2 * NZ - 2 - gz;
+        if (gx < 0) gx = -gx;
+        if (gx >= NX) gx = 2 * NX - 2 - gx;
+        gx = min(max(gx, 0), NX - 1);              // (padding columns past the operator's reach)
+        s1[r * SP + cidx] = P1[(size_t)gz * pitch + gx];
+    });
+    for_cells(ch, CW, [&](int r, int cidx) { s0[r * CW + cidx] = P0[(size_t)(cza + r) * pitch + min(cxa + cidx, NX - 1)]; });
+    __syncthreads();
+
+    // two-way update of the compute rectangle: one float4 group (4 cells) per thread and pass,
+    // the interior tiles' row stencil on the shared tile (global operator tables for the adaptive one)
+    {
+        LsTable T{};
+        T.ip = G.Index; T.cp = G.c; T.bmin = 0; T.bmax = 0xffff; T.staged = false;
+        const float* AV = G.avel + G.padL;
+        const unsigned short* BN = G.bins + G.padL;
+        int sh = 0;
+        while ((1 << sh) < NG) ++sh;               // groups per row rounded up to a power of two
+        for (int it = threadIdx.x; it < (ch << sh); it += kThreads) {
+            const int lz = it >> sh, g = it & ((1 << sh) - 1);
+            if (g >= NG) continue;
+            const int z = cza + lz, x = cxa + 4 * g;
+            const size_t row = (size_t)z * pitch;
+            int xq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xq[q] = min(x + q, NX - 1);
+            uint2 b4 = make_uint2(0u, 0u);
+            if (LS) {
+                b4.x = (unsigned)__ldg(BN + row + xq[0]) | ((unsigned)__ldg(BN + row + xq[1]) << 16);
+                b4.y = (unsigned)__ldg(BN + row + xq[2]) | ((unsigned)__ldg(BN + row + xq[3]) << 16);
+            }
+            float w1[4], p1[4], p0[4], val[4];
+            stencil_row<RP, LS, 0>(G, s1 + (lz + R) * SP + 4 * g + RP, G.nfdmax, T, b4, w1, p1, SP);
+            unpack(*reinterpret_cast<const float4*>(s0 + lz * CW + 4 * g), p0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float av = __ldg(AV + row + xq[q]);  // ((v*v)*tao2)*h2, the kernels' own rounding
+                val[q] = sum_kind == SUM_FLOAT ? finish_float(av, w1[q], p1[q], p0[q]) : finish_double(av, w1[q], p1[q], p0[q]);
+            }
+            if (seis_row && z == G.s_z) {  // replacement (BKAdd :349-353)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = data_index(G, z, x + q);
+                    if (j >= 0) {
+                        const float d = seis_row[j];
+                        if (d != 0.0f) val[q] = d;
+                    }
+                }
+            }
+            if (inject && z == r_u && r_x >= x && r_x < x + 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (x + q == r_x) val[q] = __fadd_rn(val[q], wavelet);
+            }
+            *reinterpret_cast<float4*>(s2 + lz * CW + 4 * g) = make_float4(val[0], val[1], val[2], val[3]);
+        }
+    }
+    __syncthreads();
+
+    const int oh = o.zb - o.za, ow = o.xb - o.xa;
+    for_cells(oh, ow, [&](int oz, int ox) {
+        const int z = o.za + oz, x = o.xa + ox;
+        const int lz = z - cza, lx = x - cxa;
+        const int dz = min(z, NZ - 1 - z), dx = min(x, NX - 1 - x);
+        const int a  = min(dz, dx);
+        const int sz = (z < NZ - 1 - z) ? 1 : -1, sx = (x < NX - 1 - x) ? 1 : -1;
+#define S2(zz, xx) s2[(lz + (zz)) * CW + lx + (xx)]
+#define S0(zz, xx) s0[(lz + (zz)) * CW + lx + (xx)]
+#define S1(zz, xx) s1[(lz + R + (zz)) * SP + lx + RP + (xx)]
+        float Pb;
+        if (abs(dz - dx) <= 1) {
+            // corner cells (Hybrid1 :138-155): r1 = sqrt((v*tao/h)^2/2) at the cell itself
+            // (GPU_velocity_real.cpp:104-117; tao/h enters as v*tao/h in float)
+            const float vv = __ldg(V + (size_t)z * pitch + x);
+            const float r  = __fdiv_rn(__fmul_rn(vv, G.tao), G.h);
+            const float r2 = __double2float_rn(__dmul_rn(__dmul_rn((double)r, (double)r), 0.5));
+            const float r1 = __fsqrt_rn(r2);
+            const float rcp = __frcp_rn(__fmaf_rn(2.0f, r1, 1.0f));
+            const float nb  = __fadd_rn(S2(0, sx), S2(sz, 0));
+            Pb = __fmul_rn(rcp, __fmaf_rn(r1, nb, S1(0, 0)));
+        } else {
+            int   iz, ix, tz, tx;
+            float vq;
+            if (dz < dx) {  // top :124 / bottom :132
+                iz = sz; ix = 0; tz = 0; tx = 1;
+                vq = __ldg(V + (size_t)a * pitch + x);
+            } else {        // left :128 / right :136: flat index (N2-l)*NX + row
+                iz = 0; ix = sx; tz = 1; tx = 0;
+                int fz = a, fx = z;   // (a*NX + z) / NX and % NX without the division
+                while (fx >= NX) { fx -= NX; ++fz; }
+                vq = __ldg(V + (size_t)fz * pitch + fx);
+            }
+            const float vb  = __ldg(V + (size_t)z * pitch + x);
+            const float tv  = __fmul_rn(G.taoh, vb);
+            const float rcp = __frcp_rn(__fadd_rn(tv, 1.0f));
+            const float p2i = S2(iz, ix), p0i = S0(iz, ix), p0b = S0(0, 0);
+            const float p1b = S1(0, 0), p1i = S1(iz, ix);
+            const float A1  = __fadd_rn(__fsub_rn(p2i, p0i), p0b);
+            float B = __fadd_rn(__fmul_rn(-2.0f, p1b), p0b);
+            B       = __fadd_rn(B, p2i);
+            B       = __fsub_rn(B, __fmul_rn(2.0f, p1i));
+            B       = __fadd_rn(B, p0i);
+            float D = __fsub_rn(S2(iz + tz, ix + tx), __fmul_rn(2.0f, p2i));
+            D       = __fadd_rn(D, S2(iz - tz, ix - tx));
+            D       = __fadd_rn(D, S0(tz, tx));
+            D       = __fsub_rn(D, __fmul_rn(2.0f, p0b));
+            D       = __fadd_rn(D, S0(-tz, -tx));
+            const float c2 = __fmul_rn(__fmul_rn(G.taoh2, vq), vq);
+            Pb = __fmul_rn(rcp, __fmaf_rn(c2, D, __fmaf_rn(tv, A1, -B)));
+        }
+        // blend (Hybrid2 :160-183): fma(1-w, P2, w*Pb)
+        const float w   = G.w[N2 - a];
+        const float val = __fmaf_rn(__fsub_rn(1.0f, w), S2(0, 0), __fmul_rn(w, Pb));
+#undef S2
+#undef S0
+#undef S1
+        emit(z, x, val);
+    });
+}
+
 __device__ __forceinline__ void store4(float* dst, const float (&o)[4], int x, int xend)
 {
     if (x + 3 < xend) {
@@ -625,7 +643,7 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
         const int N2 = G.N2, nf = G.nfdmax, NZ = G.NZ, NX = G.NX, k = a.k;
         const Strips st = a.st;
         float* gather = a.gather;
-        ring_tile<LS>(G, bi % nring, a.P1 + so, a.P0 + so, sum_kind, true, src.x, src.y, a.wavelet,
+        ring_tile<RP, LS>(G, bi % nring, a.P1 + so, a.P0 + so, sum_kind, true, src.x, src.y, a.wavelet,
                       nullptr, reinterpret_cast<float*>(smem_raw),
                       [&](int z, int x, float val) {
             P2[(size_t)z * G.pitch + x] = val;
@@ -778,7 +796,7 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
         float* SX = a.S2 + so;
         const int N2 = G.N2, nf = G.nfdmax, NZ = G.NZ, NX = G.NX, k = a.k;
         const Strips st = a.st;
-        ring_tile<LS>(G, bi % nring, a.R1 + so, a.R0 + so, SUM_FLOAT, false, 0, 0, 0.0f, seis_row,
+        ring_tile<RP, LS>(G, bi % nring, a.R1 + so, a.R0 + so, SUM_FLOAT, false, 0, 0, 0.0f, seis_row,
                       reinterpret_cast<float*>(smem_raw), [&](int z, int x, float val) {
             R2[(size_t)z * G.pitch + x] = val;
             // BKEqual :222-245, one step early: the ring of the buffer that becomes the
