@@ -37,10 +37,10 @@ KEYS = [
 
 
 def launches(path):
-    rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit() and r[-3] == "gpu__time_duration.sum"]
     agg = OrderedDict()
     for r in rows:
-        name, ns = r[4].split("(")[0].replace("void ", ""), float(r[-1])
+        name, ns = r[4].split("(")[0].replace("void ", ""), float(r[-1].replace(",", ""))
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += ns
