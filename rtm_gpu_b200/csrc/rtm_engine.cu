@@ -460,6 +460,7 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     G.ntz_f = (G.mod_NZ + kWarps * RTM_NR_F - 1) / (kWarps * RTM_NR_F);
     G.ntz_b = (G.mod_NZ + kWarps * RTM_NR_B - 1) / (kWarps * RTM_NR_B);
     G.nband = (G.NX + kRingTX - 1) / kRingTX; G.nside = (G.mod_NZ + kRingTX - 1) / kRingTX;
+    G.fd_ntx = make_fastdiv(G.ntx); G.fd_nring = make_fastdiv(2 * G.nband + 2 * G.nside);
     if (const char* e = std::getenv("RTM_NO_GRAPH")) c->use_graphs = std::atoi(e) == 0;
     if (const char* e = std::getenv("RTM_FUSE2")) { c->fuse2 = std::atoi(e) != 0; c->fuse2_forced = c->fuse2; }
     if (!c->fuse2_forced && p->iLSTE == 0) c->fuse2 = false;
@@ -753,7 +754,7 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass&
         CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS, RTM_NR_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k.smem_f = smem;
     }
-    a.tiles = k.d_tiles_f; a.ntiles = k.n_f;
+    a.tiles = k.d_tiles_f; a.ntiles = k.n_f; a.fd_ntiles = make_fastdiv(k.n_f);
     dim3 grid((unsigned)((nring + k.n_f) * ns));
     if (grid.x == 0 || c->dry) return RTM_OK;
     ++c->nlaunch;
@@ -771,7 +772,7 @@ template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx
         CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k.smem_b = smem;
     }
-    a.tiles = frame ? k.d_tiles_bf : k.d_tiles_b; a.ntiles = frame ? k.n_bf : k.n_b;
+    a.tiles = frame ? k.d_tiles_bf : k.d_tiles_b; a.ntiles = frame ? k.n_bf : k.n_b; a.fd_ntiles = make_fastdiv(a.ntiles);
     dim3 grid((unsigned)((nring + a.ntiles) * ns));
     if (grid.x == 0 || c->dry) return RTM_OK;
     ++c->nlaunch;
@@ -788,6 +789,7 @@ template <int RP, bool LS> static int launch_bwd2(rtm_ctx* c, rtm_ctx::TileClass
     }
     a.tiles = border ? k.d_tiles_ib : k.d_tiles_ii; a.ntiles = border ? k.n_ib : k.n_ii;
     a.rect_t0 = k.ii_rect[0]; a.rect_nx = border ? 0 : k.ii_rect[1]; a.rect_dz = k.ii_rect[2];
+    a.fd_ntiles = make_fastdiv(a.ntiles); a.fd_rect = make_fastdiv(a.rect_nx);
     if (c->dry || a.ntiles == 0) return RTM_OK;
     ++c->nlaunch;
     bwd2_step_kernel<RP, LS><<<(unsigned)(a.ntiles * ns), kThreads, smem, st>>>(k.tmap_b2[s1], k.tmap_b2[r1], c->G, a);

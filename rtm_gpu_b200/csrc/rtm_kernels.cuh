@@ -46,6 +46,30 @@ __host__ __device__ constexpr int slice_bytes(int RP) { return RP >= 8 ? 24576 :
 
 enum SumKind { SUM_FLOAT = 0, SUM_DOUBLE = 1 };
 
+// Division by a run-time constant as multiply-high + shift (0 <= n < 2^31): the CTA prologues
+// divide block indices by tile counts, which costs ~10 % of the forward kernel's instructions as
+// real integer divisions.
+struct FastDiv {
+    unsigned mul, shr;
+    int      d;
+};
+__host__ inline FastDiv make_fastdiv(int d)
+{
+    FastDiv f{0u, 0u, d < 1 ? 1 : d};
+    if (f.d > 1) {
+        int cl = 0;
+        while ((1 << cl) < f.d) ++cl;
+        const int p = 31 + cl;
+        f.mul = (unsigned)(((1ull << p) + (unsigned long long)f.d - 1) / (unsigned long long)f.d);
+        f.shr = (unsigned)(p - 32);
+    }
+    return f;
+}
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f)
+{
+    return f.d == 1 ? n : (int)(__umulhi((unsigned)n, f.mul) >> f.shr);
+}
+
 struct Geo {
     int   NZ, NX, N2, mod_NZ, mod_NX;
     int   pitch, padL;       // internal row pitch (floats) and left pad: cell (z,x) at z*pitch+padL+x
@@ -61,6 +85,7 @@ struct Geo {
     // tiling
     int   ntx, ntz_f, ntz_b; // interior tiles (forward / backward kernels use different tile heights)
     int   nband, nside;      // ring tiles per band (top/bottom) and per side (left/right)
+    FastDiv fd_ntx, fd_nring;  // dividers by ntx and by the ring tile count 2*nband+2*nside
     // operator
     const float* c;          // LS: packed table; TE: unused
     const int*   Index;
@@ -135,9 +160,9 @@ __device__ __forceinline__ float finish_float(float a, float w1, float p1, float
 __device__ __forceinline__ float finish_double(float a, float w1, float p1, float p0)
 {
     // Add_Con, BKAdd_EFF, BKAdd_EFF_Con: 2.0*P1 - P0 + (float)(a*w1) in double
-    const double d = (double)p1;
+    // (2.0*P1 is exact in double, so fma(2, P1, -P0) rounds once exactly like (P1+P1)-P0)
     return __double2float_rn(
-        __dadd_rn(__dsub_rn(__dadd_rn(d, d), (double)p0), (double)__fmul_rn(a, w1)));
+        __dadd_rn(__fma_rn((double)p1, 2.0, -(double)p0), (double)__fmul_rn(a, w1)));
 }
 __device__ __forceinline__ float vel_factor(const Geo& G, float v)
 {
@@ -594,6 +619,7 @@ struct FwdArgs {
     int          tma_s0;  // offset of shot 0 along the tensor map's 3rd dimension (store-all: slot*S)
     const int*   tiles;   // interior tiles of this launch (null: all tiles 0..ntiles-1)
     int          ntiles;  // interior tiles per shot in this launch
+    FastDiv      fd_ntiles;
     int          do_ring; // this launch also carries the ring tiles
     Strips       st;   // may hold nulls when strips are not wanted (pure modelling)
     float*       gather;  // [S][NT][n] time-major, or null
@@ -633,7 +659,8 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
     const int  nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0, nint = a.ntiles;
     const bool is_ring = (int)blockIdx.x < a.nshots * nring;
     const int  bi   = is_ring ? blockIdx.x : blockIdx.x - a.nshots * nring;
-    const int  shot = is_ring ? bi / nring : bi / nint;
+    const int  shot = is_ring ? fast_div(bi, G.fd_nring) : fast_div(bi, a.fd_ntiles);
+    const int  bt   = bi - shot * (is_ring ? nring : nint);  // ring tile / position in the tile list
     const long long so = (long long)shot * G.shot_stride + G.padL;  // (z=0,x=0) of this shot
     const int2 src = a.src[shot];
     const int  sum_kind = G.iLSTE == 0 ? SUM_FLOAT : SUM_DOUBLE;  // Add vs Add_Con
@@ -643,7 +670,7 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
         const int N2 = G.N2, nf = G.nfdmax, NZ = G.NZ, NX = G.NX, k = a.k;
         const Strips st = a.st;
         float* gather = a.gather;
-        ring_tile<RP, LS>(G, bi % nring, a.P1 + so, a.P0 + so, sum_kind, true, src.x, src.y, a.wavelet,
+        ring_tile<RP, LS>(G, bt, a.P1 + so, a.P0 + so, sum_kind, true, src.x, src.y, a.wavelet,
                       nullptr, reinterpret_cast<float*>(smem_raw),
                       [&](int z, int x, float val) {
             P2[(size_t)z * G.pitch + x] = val;
@@ -667,8 +694,8 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
     }
 
     // ---- interior tile
-    const int t   = a.tiles ? a.tiles[bi % nint] : bi % nint;
-    const int tz  = t / G.ntx, tx = t % G.ntx;
+    const int t   = a.tiles ? a.tiles[bt] : bt;
+    const int tz  = fast_div(t, G.fd_ntx), tx = t - tz * G.ntx;
     const int z0  = G.N2 + tz * (kWarps * NR), x0 = G.N2 + tx * kTX;  // first interior cell of the tile
     float*    sP  = reinterpret_cast<float*>(smem_raw);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Tile<RP, NR>::BYTES);
@@ -769,6 +796,7 @@ struct BwdArgs {
     int          nshots;
     const int*   tiles;   // interior tiles of this launch (null: all tiles 0..ntiles-1)
     int          ntiles;
+    FastDiv      fd_ntiles;
     int          do_ring;
     Strips       st;
     const float* seis;  // [S][NT][n] time-major; row k+1 is imposed
@@ -786,7 +814,8 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
     const int  nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0, nint = a.ntiles;
     const bool is_ring = (int)blockIdx.x < a.nshots * nring;
     const int  bi   = is_ring ? blockIdx.x : blockIdx.x - a.nshots * nring;
-    const int  shot = is_ring ? bi / nring : bi / nint;
+    const int  shot = is_ring ? fast_div(bi, G.fd_nring) : fast_div(bi, a.fd_ntiles);
+    const int  bt   = bi - shot * (is_ring ? nring : nint);
     const long long so = (long long)shot * G.shot_stride + G.padL;
     const int2 src = a.src[shot];
     const float* seis_row = a.seis + ((size_t)shot * G.NT + (a.k + 1)) * G.n;
@@ -796,7 +825,7 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
         float* SX = a.S2 + so;
         const int N2 = G.N2, nf = G.nfdmax, NZ = G.NZ, NX = G.NX, k = a.k;
         const Strips st = a.st;
-        ring_tile<RP, LS>(G, bi % nring, a.R1 + so, a.R0 + so, SUM_FLOAT, false, 0, 0, 0.0f, seis_row,
+        ring_tile<RP, LS>(G, bt, a.R1 + so, a.R0 + so, SUM_FLOAT, false, 0, 0, 0.0f, seis_row,
                       reinterpret_cast<float*>(smem_raw), [&](int z, int x, float val) {
             R2[(size_t)z * G.pitch + x] = val;
             // BKEqual :222-245, one step early: the ring of the buffer that becomes the
@@ -815,8 +844,8 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
         return;
     }
 
-    const int t   = a.tiles ? a.tiles[bi % nint] : bi % nint;
-    const int tz  = t / G.ntx, tx = t % G.ntx;
+    const int t   = a.tiles ? a.tiles[bt] : bt;
+    const int tz  = fast_div(t, G.fd_ntx), tx = t - tz * G.ntx;
     const int z0  = G.N2 + tz * (kWarps * NR), x0 = G.N2 + tx * kTX;
     constexpr int NTILE = STORE ? 1 : 2;  // halo tiles in shared memory
     float*    sS  = reinterpret_cast<float*>(smem_raw);
@@ -985,6 +1014,7 @@ struct Bwd2Args {
     int          rect_t0, rect_nx;  // rect_nx > 0: the tiles form a rectangle rect_nx wide starting at tile rect_t0,
                                     // row stride rect_dz tiles (no list lookup before the TMA copies are issued)
     int          rect_dz;
+    FastDiv      fd_ntiles, fd_rect;
     const float* seis;    // [S][NT][n]; row k+1 is imposed in step k, row k in step k-1
     float *sumS, *sumR, *rel1, *rel2;
 };
@@ -1015,12 +1045,13 @@ bwd2_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant
     using T2 = Tile2<RP>;
     constexpr int NR = T2::NR, SPA = T2::SPA, SPB = T2::SPB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int  shot = blockIdx.x / a.ntiles;
-    const int  ti   = blockIdx.x % a.ntiles;
-    const int  t    = a.rect_nx > 0 ? a.rect_t0 + (ti / a.rect_nx) * a.rect_dz + ti % a.rect_nx : a.tiles[ti];
+    const int  shot = fast_div(blockIdx.x, a.fd_ntiles);
+    const int  ti   = blockIdx.x - shot * a.ntiles;
+    const int  tr   = fast_div(ti, a.fd_rect);
+    const int  t    = a.rect_nx > 0 ? a.rect_t0 + tr * a.rect_dz + (ti - tr * a.rect_nx) : a.tiles[ti];
     const long long so = (long long)shot * G.shot_stride + G.padL;
     const int2 src = a.src[shot];
-    const int  tz  = t / G.ntx, tx = t % G.ntx;
+    const int  tz  = fast_div(t, G.fd_ntx), tx = t - tz * G.ntx;
     const int  z0  = G.N2 + tz * (kWarps * RTM_NR_B), x0 = G.N2 + tx * kTX;  // t counts single-step tiles
     float*    sS1 = reinterpret_cast<float*>(smem_raw);
     float*    sR1 = reinterpret_cast<float*>(smem_raw + T2::CUR_BYTES);
