@@ -311,6 +311,10 @@ struct rtm_ctx {
     bool   fuse2_forced = false;
     int    fuse2_maxrp = 4;
     static constexpr int kFuse2MinCtas = 1500;  // automatic mode: inner-inner tiles x shots per launch
+    // L2 look-ahead (profiles/README.md): one thread of every interior CTA prefetches the TMA boxes
+    // of the CTA `distance` blocks ahead (cp.async.bulk.prefetch.tensor), so that CTA's copies hit L2
+    int    lookahead_f = 148, lookahead_b = 148, lookahead_b2 = 148, lookahead_more = 1, lookahead_p0 = 3;
+    Acc4Maps tmap_acc;
     bool   dry = false;                     // launch helpers only set kernel attributes
     long   nlaunch = 0;                     // kernels launched (graph replays included)
     std::map<long long, long> graph_launches;
@@ -346,7 +350,7 @@ struct rtm_ctx {
     rtm_stats stats{};
 };
 
-static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int RP, int tile_rows, long long nslab = 0)
+static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int RP, int tile_rows, long long nslab = 0)  // RP = 0: box = the tile
 {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -465,6 +469,11 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     if (const char* e = std::getenv("RTM_FUSE2")) { c->fuse2 = std::atoi(e) != 0; c->fuse2_forced = c->fuse2; }
     if (!c->fuse2_forced && p->iLSTE == 0) c->fuse2 = false;
     if (const char* e = std::getenv("RTM_FUSE2_MAXRP")) c->fuse2_maxrp = std::atoi(e);
+    if (const char* e = std::getenv("RTM_LOOKAHEAD_F")) c->lookahead_f = std::atoi(e);
+    if (const char* e = std::getenv("RTM_LOOKAHEAD_B2")) c->lookahead_b2 = std::atoi(e);
+    if (const char* e = std::getenv("RTM_LOOKAHEAD_MORE")) c->lookahead_more = std::atoi(e);
+    if (const char* e = std::getenv("RTM_LOOKAHEAD_B")) c->lookahead_b = std::atoi(e);
+    if (const char* e = std::getenv("RTM_LOOKAHEAD_P0")) c->lookahead_p0 = std::atoi(e);
     if (p->flags & RTM_FLAG_STORE_ALL) c->fuse2 = false;
     for (int i = 0; i <= p->N2; ++i) G.w[i] = (float)((1.0 * i) / (1.0 * p->N2));  // :688-691
 
@@ -662,6 +671,10 @@ static int prepare_classes(rtm_ctx* c)
         }
         if (c->store_mode)
             if (int rc = encode_tmap(c, &k.tmap_store, c->store, k.RP, kWarps * RTM_NR_F, (long long)G.NT * c->S)) return rc;
+        // accumulators: rel1, rel2, sumS, sumR (acc[] holds sumS, sumR, rel1, rel2)
+        const int order[4] = {2, 3, 0, 1};
+        for (int i = 0; i < 4; ++i)
+            if (int rc = encode_tmap(c, &c->tmap_acc.m[i], c->acc[order[i]], 0, Tile2<4>::TZ)) return rc;
         c->classes.push_back(k);
     }
     CK(cudaDeviceSynchronize());
@@ -754,15 +767,18 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass&
         CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS, RTM_NR_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k.smem_f = smem;
     }
-    a.tiles = k.d_tiles_f; a.ntiles = k.n_f; a.fd_ntiles = make_fastdiv(k.n_f);
+    a.tiles = k.d_tiles_f; a.ntiles = k.n_f; a.fd_ntiles = make_fastdiv(k.n_f); a.lookahead = c->lookahead_f;
     dim3 grid((unsigned)((nring + k.n_f) * ns));
     if (grid.x == 0 || c->dry) return RTM_OK;
     ++c->nlaunch;
-    fwd_step_kernel<RP, LS, RTM_NR_F><<<grid, kThreads, smem, st>>>(buf < 0 ? k.tmap_store : k.tmap_f[buf], G, a);
+    a.lookahead_p0 = 1;
+    a.tma_s0_p0 = buf < 0 ? a.tma_s0 - c->S : 0;
+    fwd_step_kernel<RP, LS, RTM_NR_F><<<grid, kThreads, smem, st>>>(buf < 0 ? k.tmap_store : k.tmap_f[buf],
+                                                                 buf < 0 ? k.tmap_store : k.tmap_f[(buf + 2) % 3], G, a);
     return RTM_OK;
 }
 // frame: only the tiles that the two-step kernel does not cover
-template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, BwdArgs a, bool frame)
+template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, int s0, int r0, BwdArgs a, bool frame)
 {
     const Geo& G = c->G;
     const int nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0;
@@ -776,10 +792,12 @@ template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx
     dim3 grid((unsigned)((nring + a.ntiles) * ns));
     if (grid.x == 0 || c->dry) return RTM_OK;
     ++c->nlaunch;
-    bwd_step_kernel<RP, LS, RTM_NR_B, STORE><<<grid, kThreads, smem, st>>>(k.tmap_b[STORE ? r1 : s1], k.tmap_b[r1], G, a);
+    a.lookahead = c->lookahead_b; a.lookahead_p0 = c->lookahead_p0;
+    bwd_step_kernel<RP, LS, RTM_NR_B, STORE><<<grid, kThreads, smem, st>>>(k.tmap_b[STORE ? r1 : s1], k.tmap_b[r1], k.tmap_b[STORE ? r0 : s0],
+                                                                          k.tmap_b[r0], G, a);
     return RTM_OK;
 }
-template <int RP, bool LS> static int launch_bwd2(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, Bwd2Args a, bool border)
+template <int RP, bool LS> static int launch_bwd2(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, int s0, int r0, Bwd2Args a, bool border)
 {
     if (k.n_b2 == 0) return RTM_OK;
     const size_t smem = (size_t)Tile2<RP>::BYTES + 16 + (LS ? (size_t)slice_bytes(RP) : 0);
@@ -789,19 +807,21 @@ template <int RP, bool LS> static int launch_bwd2(rtm_ctx* c, rtm_ctx::TileClass
     }
     a.tiles = border ? k.d_tiles_ib : k.d_tiles_ii; a.ntiles = border ? k.n_ib : k.n_ii;
     a.rect_t0 = k.ii_rect[0]; a.rect_nx = border ? 0 : k.ii_rect[1]; a.rect_dz = k.ii_rect[2];
-    a.fd_ntiles = make_fastdiv(a.ntiles); a.fd_rect = make_fastdiv(a.rect_nx);
+    a.fd_ntiles = make_fastdiv(a.ntiles); a.fd_rect = make_fastdiv(a.rect_nx); a.lookahead = c->lookahead_b2;
     if (c->dry || a.ntiles == 0) return RTM_OK;
     ++c->nlaunch;
-    bwd2_step_kernel<RP, LS><<<(unsigned)(a.ntiles * ns), kThreads, smem, st>>>(k.tmap_b2[s1], k.tmap_b2[r1], c->G, a);
+    a.lookahead_more = c->lookahead_more;
+    bwd2_step_kernel<RP, LS><<<(unsigned)(a.ntiles * ns), kThreads, smem, st>>>(k.tmap_b2[s1], k.tmap_b2[r1], k.tmap_b2[s0], k.tmap_b2[r0],
+                                                                              c->tmap_acc, c->G, a);
     return RTM_OK;
 }
-static int dispatch_bwd2_class(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, const Bwd2Args& a, bool border)
+static int dispatch_bwd2_class(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, int s0, int r0, const Bwd2Args& a, bool border)
 {
     const bool ls = c->G.iLSTE == 0;
     if (k.n_b2 == 0) return RTM_OK;
     switch (k.RP) {
-    case 4: return ls ? launch_bwd2<4, true>(c, k, st, ns, s1, r1, a, border) : launch_bwd2<4, false>(c, k, st, ns, s1, r1, a, border);
-    case 8: return ls ? launch_bwd2<8, true>(c, k, st, ns, s1, r1, a, border) : launch_bwd2<8, false>(c, k, st, ns, s1, r1, a, border);
+    case 4: return ls ? launch_bwd2<4, true>(c, k, st, ns, s1, r1, s0, r0, a, border) : launch_bwd2<4, false>(c, k, st, ns, s1, r1, s0, r0, a, border);
+    case 8: return ls ? launch_bwd2<8, true>(c, k, st, ns, s1, r1, s0, r0, a, border) : launch_bwd2<8, false>(c, k, st, ns, s1, r1, s0, r0, a, border);
     }
     return rtm_fail(RTM_ERR_ARG, "two-step kernel: unsupported operator radius %d", k.RP);
 }
@@ -844,23 +864,23 @@ static int dispatch_fwd(rtm_ctx* c, int ns, int buf, FwdArgs a)
         return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", k.RP);
     });
 }
-template <bool STORE> static int dispatch_bwd_t(rtm_ctx* c, int ns, int s1, int r1, BwdArgs a, bool frame, cudaStream_t serial)
+template <bool STORE> static int dispatch_bwd_t(rtm_ctx* c, int ns, int s1, int r1, int s0, int r0, BwdArgs a, bool frame, cudaStream_t serial)
 {
     const bool ls = c->G.iLSTE == 0;
     return fork_join(c, [&](rtm_ctx::TileClass& k, cudaStream_t st, bool first) -> int {
         a.do_ring = first ? 1 : 0;
         switch (k.RP) {
-        case 4:  return ls ? launch_bwd<4, true, STORE>(c, k, st, ns, s1, r1, a, frame) : launch_bwd<4, false, STORE>(c, k, st, ns, s1, r1, a, frame);
-        case 8:  return ls ? launch_bwd<8, true, STORE>(c, k, st, ns, s1, r1, a, frame) : launch_bwd<8, false, STORE>(c, k, st, ns, s1, r1, a, frame);
-        case 12: return ls ? launch_bwd<12, true, STORE>(c, k, st, ns, s1, r1, a, frame) : launch_bwd<12, false, STORE>(c, k, st, ns, s1, r1, a, frame);
-        case 16: return ls ? launch_bwd<16, true, STORE>(c, k, st, ns, s1, r1, a, frame) : launch_bwd<16, false, STORE>(c, k, st, ns, s1, r1, a, frame);
+        case 4:  return ls ? launch_bwd<4, true, STORE>(c, k, st, ns, s1, r1, s0, r0, a, frame) : launch_bwd<4, false, STORE>(c, k, st, ns, s1, r1, s0, r0, a, frame);
+        case 8:  return ls ? launch_bwd<8, true, STORE>(c, k, st, ns, s1, r1, s0, r0, a, frame) : launch_bwd<8, false, STORE>(c, k, st, ns, s1, r1, s0, r0, a, frame);
+        case 12: return ls ? launch_bwd<12, true, STORE>(c, k, st, ns, s1, r1, s0, r0, a, frame) : launch_bwd<12, false, STORE>(c, k, st, ns, s1, r1, s0, r0, a, frame);
+        case 16: return ls ? launch_bwd<16, true, STORE>(c, k, st, ns, s1, r1, s0, r0, a, frame) : launch_bwd<16, false, STORE>(c, k, st, ns, s1, r1, s0, r0, a, frame);
         }
         return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", k.RP);
     }, serial);
 }
-static int dispatch_bwd(rtm_ctx* c, int ns, int s1, int r1, const BwdArgs& a, bool frame = false, cudaStream_t serial = nullptr)
+static int dispatch_bwd(rtm_ctx* c, int ns, int s1, int r1, int s0, int r0, const BwdArgs& a, bool frame = false, cudaStream_t serial = nullptr)
 {
-    return c->store_mode ? dispatch_bwd_t<true>(c, ns, s1, r1, a, frame, serial) : dispatch_bwd_t<false>(c, ns, s1, r1, a, frame, serial);
+    return c->store_mode ? dispatch_bwd_t<true>(c, ns, s1, r1, s0, r0, a, frame, serial) : dispatch_bwd_t<false>(c, ns, s1, r1, s0, r0, a, frame, serial);
 }
 
 static void drop_graphs(rtm_ctx* c)
@@ -1073,7 +1093,7 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
     };
     // one step, all tiles; the source slot k replaces slot k+2 in place
     auto bstep = [&](int k) -> int {
-        if (int rc = dispatch_bwd(c, ns, store ? Rb : Sb, Rb, args1(k, Sa, Sa, Ra, Rb, Rc))) return rc;
+        if (int rc = dispatch_bwd(c, ns, store ? Rb : Sb, Rb, store ? Ra : Sa, Ra, args1(k, Sa, Sa, Ra, Rb, Rc))) return rc;
         std::swap(Sa, Sb);
         const int t = Ra; Ra = Rb; Rb = Rc; Rc = t;
         return RTM_OK;
@@ -1099,14 +1119,14 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
             a2.sumS = c->acc[0]; a2.sumR = c->acc[1]; a2.rel1 = c->acc[2]; a2.rel2 = c->acc[3];
             if (j > 0) CK(cudaStreamWaitEvent(A, c->ev_ib[(j - 1) & 1], 0));
             for (auto& kc : c->classes)
-                if (int rc = dispatch_bwd2_class(c, kc, A, ns, Sb, Rb, a2, false)) return rc;
+                if (int rc = dispatch_bwd2_class(c, kc, A, ns, Sb, Rb, Sa, Ra, a2, false)) return rc;
             CK(cudaEventRecord(c->ev_ii[j & 1], A));
-            if (int rc = dispatch_bwd(c, ns, Sb, Rb, args1(k, Sa, Sc, Ra, Rb, Rc), true, B)) return rc;
+            if (int rc = dispatch_bwd(c, ns, Sb, Rb, Sa, Ra, args1(k, Sa, Sc, Ra, Rb, Rc), true, B)) return rc;
             if (j > 0) CK(cudaStreamWaitEvent(B, c->ev_ii[(j - 1) & 1], 0));
             for (auto& kc : c->classes)
-                if (int rc = dispatch_bwd2_class(c, kc, B, ns, Sb, Rb, a2, true)) return rc;
+                if (int rc = dispatch_bwd2_class(c, kc, B, ns, Sb, Rb, Sa, Ra, a2, true)) return rc;
             CK(cudaEventRecord(c->ev_ib[j & 1], B));
-            if (int rc = dispatch_bwd(c, ns, Sc, Rc, args1(k - 1, Sb, Sd, Rb, Rc, Rd), true, B)) return rc;
+            if (int rc = dispatch_bwd(c, ns, Sc, Rc, Sb, Rb, args1(k - 1, Sb, Sd, Rb, Rc, Rd), true, B)) return rc;
             std::swap(Sa, Sc); std::swap(Sb, Sd);
             std::swap(Ra, Rc); std::swap(Rb, Rd);
         }

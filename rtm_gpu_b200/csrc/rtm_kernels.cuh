@@ -141,6 +141,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, int z, int s)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"((uint64_t)map),
+                 "r"(x), "r"(z), "r"(s)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
                                             int x, int z, int s)
 {
@@ -620,6 +626,8 @@ struct FwdArgs {
     const int*   tiles;   // interior tiles of this launch (null: all tiles 0..ntiles-1)
     int          ntiles;  // interior tiles per shot in this launch
     FastDiv      fd_ntiles;
+    int          lookahead;  // CTAs ahead whose TMA box is prefetched into L2 (0: off; all-tiles launches only)
+    int          lookahead_p0, tma_s0_p0;  // ... and its slot k-2 box (tma_s0_p0: like tma_s0, for the P0 map)
     int          do_ring; // this launch also carries the ring tiles
     Strips       st;   // may hold nulls when strips are not wanted (pure modelling)
     float*       gather;  // [S][NT][n] time-major, or null
@@ -648,8 +656,8 @@ struct FwdArgs {
 #endif
 template <int RP, bool LS, int NR>
 __global__ void __launch_bounds__(kThreads, (RP <= 4 ? (LS ? RTM_FWD_MINB_LS : RTM_FWD_MINB) : (LS ? RTM_FWD_MINB_LS_BIG : (RP <= 8 ? 3 : RTM_FWD_MINB_R12))))
-fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ Geo G,
-                const FwdArgs a)
+fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ CUtensorMap tmP0,
+                const __grid_constant__ Geo G, const FwdArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // 1-D grid: the ring tiles of ALL shots first (they are the longest-running CTAs and would
@@ -707,6 +715,13 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
         mbar_expect_tx(bar, Tile<RP, NR>::BYTES);
         tma_load_3d(sP, &tmP1, bar, G.padL + x0 - RP, z0 - RP, a.tma_s0 + shot);
     }
+    // L2 look-ahead: the boxes of the CTA `lookahead` blocks further on (its TMA copy then hits L2)
+    int la_t = -1, la_s = 0;
+    if (tid == 0 && a.lookahead > 0 && bi + a.lookahead < a.nshots * nint) {
+        la_s = fast_div(bi + a.lookahead, a.fd_ntiles);
+        const int i2 = bi + a.lookahead - la_s * nint;
+        la_t = a.tiles ? __ldg(a.tiles + i2) : i2;
+    }
     const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
     LsTable T{};
     if (LS) {  // this tile's slice of the operator table -> shared memory (behind the halo tile)
@@ -735,6 +750,12 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
     uint2  bn  = make_uint2(0u, 0u);
     if (LS) bn = __ldg(reinterpret_cast<const uint2*>(bp));
     mbar_wait(bar, 0);
+    if (la_t >= 0) {
+        const int tz2 = fast_div(la_t, G.fd_ntx), tx2 = la_t - tz2 * G.ntx;
+        tma_prefetch_3d(&tmP1, G.padL + G.N2 + tx2 * kTX - RP, G.N2 + tz2 * (kWarps * NR) - RP, a.tma_s0 + la_s);
+        if (a.lookahead_p0)
+            tma_prefetch_3d(&tmP0, G.padL + G.N2 + tx2 * kTX - RP, G.N2 + tz2 * (kWarps * NR) - RP, a.tma_s0_p0 + la_s);
+    }
 
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
@@ -797,6 +818,8 @@ struct BwdArgs {
     const int*   tiles;   // interior tiles of this launch (null: all tiles 0..ntiles-1)
     int          ntiles;
     FastDiv      fd_ntiles;
+    int          lookahead;     // CTAs ahead whose TMA boxes are prefetched into L2 (0: off)
+    int          lookahead_p0;  // bit 0: also its receiver slot k+2 box, bit 1: also its source slot k+2 box
     int          do_ring;
     Strips       st;
     const float* seis;  // [S][NT][n] time-major; row k+1 is imposed
@@ -808,6 +831,7 @@ struct BwdArgs {
 template <int RP, bool LS, int NR, bool STORE>
 __global__ void __launch_bounds__(kThreads, (RP <= 4 ? (LS ? RTM_BWD_MINB_LS : RTM_BWD_MINB) : ((RP <= 8 && !LS) ? 3 : RTM_BWD_MINB_R12)))
 bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmR1,
+                const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmR0,
                 const __grid_constant__ Geo G, const BwdArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -860,6 +884,12 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
         if (!STORE) tma_load_3d(sS, &tmS1, bar, G.padL + x0 - RP, z0 - RP, shot);
         tma_load_3d(sR, &tmR1, bar, G.padL + x0 - RP, z0 - RP, shot);
     }
+    int la_t = -1, la_s = 0;  // L2 look-ahead, as in the forward kernel
+    if (tid == 0 && a.lookahead > 0 && bi + a.lookahead < a.nshots * nint) {
+        la_s = fast_div(bi + a.lookahead, a.fd_ntiles);
+        const int i2 = bi + a.lookahead - la_s * nint;
+        la_t = a.tiles ? __ldg(a.tiles + i2) : i2;
+    }
     const int zend = G.NZ - G.N2, xend = G.NX - G.N2;
     LsTable T{};
     if (LS) {
@@ -886,6 +916,14 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
     float4 s0n = *reinterpret_cast<const float4*>((STORE ? a.Sk : a.S02) + o);  // STORE: slot k itself
     float4 r0n = *reinterpret_cast<const float4*>(a.R0 + o);
     mbar_wait(bar, 0);
+    if (la_t >= 0) {
+        const int tz2 = fast_div(la_t, G.fd_ntx), tx2 = la_t - tz2 * G.ntx;
+        const int xx = G.padL + G.N2 + tx2 * kTX - RP, zz = G.N2 + tz2 * (kWarps * NR) - RP;
+        if (!STORE) tma_prefetch_3d(&tmS1, xx, zz, la_s);
+        tma_prefetch_3d(&tmR1, xx, zz, la_s);
+        if (a.lookahead_p0 & 1) tma_prefetch_3d(&tmR0, xx, zz, la_s);
+        if (!STORE && (a.lookahead_p0 & 2)) tma_prefetch_3d(&tmS0, xx, zz, la_s);
+    }
 
     auto put = [&](float* base, const float (&val)[4]) {
         if (full) {
@@ -998,6 +1036,8 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
 // ring run the single-step kernel for slot k (concurrently) and for slot k-1 (afterwards).
 // Buffers: slots k+2,k+1 are only read, slots k,k-1 go to two other buffers (4 per field).
 // ------------------------------------------------------------------------------------
+struct Acc4Maps { CUtensorMap m[4]; };  // rel1, rel2, sumS, sumR with a box of one two-step tile
+
 struct Bwd2Args {
     const float* S0;   // source slot k+2 (slot k+1 comes through the tensor map)
     float*       Sk;   // out: source slot k
@@ -1015,6 +1055,8 @@ struct Bwd2Args {
                                     // row stride rect_dz tiles (no list lookup before the TMA copies are issued)
     int          rect_dz;
     FastDiv      fd_ntiles, fd_rect;
+    int          lookahead;  // CTAs ahead whose TMA boxes are prefetched into L2 (0: off)
+    int          lookahead_more;  // bit 0: also its slot k+2 boxes, bit 1: also its accumulator tiles
     const float* seis;    // [S][NT][n]; row k+1 is imposed in step k, row k in step k-1
     float *sumS, *sumR, *rel1, *rel2;
 };
@@ -1040,7 +1082,8 @@ template <int RP> struct Tile2 {
 template <int RP, bool LS>
 __global__ void __launch_bounds__(kThreads, (RP <= 4 ? RTM_BWD2_MINB : (RP <= 8 && RTM_NR_B2 <= 2 ? 2 : 1)))
 bwd2_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmR1,
-                 const __grid_constant__ Geo G, const Bwd2Args a)
+                 const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmR0,
+                 const __grid_constant__ Acc4Maps tmAcc, const __grid_constant__ Geo G, const Bwd2Args a)
 {
     using T2 = Tile2<RP>;
     constexpr int NR = T2::NR, SPA = T2::SPA, SPB = T2::SPB;
@@ -1067,6 +1110,30 @@ bwd2_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant
         tma_load_3d(sS1, &tmS1, bar, G.padL + x0 - 2 * RP, z0 - 2 * RP, shot);
         tma_load_3d(sR1, &tmR1, bar, G.padL + x0 - 2 * RP, z0 - 2 * RP, shot);
     }
+    // L2 look-ahead: the boxes of a CTA that starts a little later (its TMA copies then hit L2);
+    // a listed tile index is fetched now and used after the wait for this CTA's own boxes
+    int la_t = -1, la_s = 0;
+    if (tid == 0 && a.lookahead > 0 && (int)blockIdx.x + a.lookahead < (int)gridDim.x) {
+        const int b2 = blockIdx.x + a.lookahead;
+        la_s = fast_div(b2, a.fd_ntiles);
+        const int i2 = b2 - la_s * a.ntiles, r2 = fast_div(i2, a.fd_rect);
+        la_t = a.rect_nx > 0 ? a.rect_t0 + r2 * a.rect_dz + (i2 - r2 * a.rect_nx) : __ldg(a.tiles + i2);
+    }
+    auto look_ahead = [&]() {
+        if (la_t < 0) return;
+        const int tz2 = fast_div(la_t, G.fd_ntx), tx2 = la_t - tz2 * G.ntx;
+        const int zz = G.N2 + tz2 * (kWarps * RTM_NR_B) - 2 * RP, xx = G.padL + G.N2 + tx2 * kTX - 2 * RP;
+        tma_prefetch_3d(&tmS1, xx, zz, la_s);
+        tma_prefetch_3d(&tmR1, xx, zz, la_s);
+        if (a.lookahead_more & 1) {  // slot k+2 (P0 of phase A)
+            tma_prefetch_3d(&tmS0, xx, zz, la_s);
+            tma_prefetch_3d(&tmR0, xx, zz, la_s);
+        }
+        if (a.lookahead_more & 2) {  // accumulators (box = the tile itself)
+            const int na = G.iCompen == 1 ? 4 : 2;
+            for (int i = 0; i < na; ++i) tma_prefetch_3d(&tmAcc.m[i], xx + 2 * RP, zz + 2 * RP, la_s);
+        }
+    };
     LsTable T{};
     if (LS) {
         T = ls_stage_slice<RP>(G, G.tile_bins_b2[t], reinterpret_cast<float*>(smem_raw + T2::BYTES + 16));
@@ -1124,6 +1191,7 @@ bwd2_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant
             uint2  bn  = make_uint2(0u, 0u);
             if (LS) bn = __ldg(reinterpret_cast<const uint2*>(BN + cell));
             mbar_wait(bar, 0);
+            look_ahead();
 #pragma unroll
             for (int r = 0; r < NRA; ++r) {
                 const float4 s0c = s0n, r0c = r0n, avc = avn;
