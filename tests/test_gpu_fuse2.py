@@ -33,6 +33,21 @@ def test_pairs_taylor8_vs_oracle(fuse_env, nt1, s_z, icompen):
     run_case(case, [10 + 75, 10 + 3], [10 + 300, 10 + 420], snaps=(2,))
 
 
+@pytest.mark.parametrize("graph", [1, 0])
+def test_pairs_sources_and_data_line_on_tile_edges(fuse_env, monkeypatch, graph):
+    """Sources one cell inside / outside tile edges (they lie in the grown region of the neighbouring
+    tiles, which inject them redundantly), data line on the last row of a tile row; replayed graph
+    and eager launches (RTM_NO_GRAPH)."""
+    fuse_env(4)
+    monkeypatch.setenv("RTM_NO_GRAPH", "0" if graph else "1")
+    case = Case(name="edges", nfdmax=4, nfdmin=2, N2=10, f0=20.0, iLSTE=1, hz=5.0, h=5.0, tao=5e-4,
+                tao1=5e-4, mod_NZ=200, mod_NX=700, NT1=26, s_l=5, s_z=10 + 16 * 4 - 10, n=230, ds=3, r_x=1, nrec=3,
+                NX_ED=700, NZ_ED=200)
+    #            tile rows start at z = 10 + 16 i, tile columns at x = 10 + 128 j
+    run_case(case, [10 + 16 * 3, 10 + 16 * 5 - 1, 10 + 16 * 2 + 15], [10 + 128 * 2 - 1, 10 + 128 * 3, 10 + 128 * 2 + 127],
+             snaps=(2,))
+
+
 def test_pairs_taylor16_vs_oracle(fuse_env):
     """Radius 8 (RP = 8 template of the two-step kernel, 2 CTAs per SM)."""
     fuse_env(8)
