@@ -157,6 +157,17 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// 4-byte asynchronous global -> shared copies (ring tiles: every thread has all its halo
+// loads in flight at once instead of one exposed HBM latency per element)
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ exact arithmetic
 // final sum of the two-way update, a = ((v*v)*tao2)*h2
 __device__ __forceinline__ float finish_float(float a, float w1, float p1, float p0)
@@ -430,22 +441,31 @@ __device__ __forceinline__ RingRect ring_rect(const Geo& G, int tile)
 }
 
 // shared memory needed by a ring tile (floats): current field with the stencil halo (rows: R,
-// columns: RP), previous field and two-way result on the compute rectangle padded to float4 groups
+// columns: RP), previous field and two-way result on the compute rectangle padded to float4 groups,
+// and three values per output cell staged for the one-way phase (velocity at the cell, velocity
+// of the edge formula's tangential term, one caller-defined value)
 __host__ __device__ inline int ring_smem_floats(int N2, int R, int RP)
 {
     const int wb = (kRingTX + 2 + 3) / 4 * 4, ws = (N2 + 2 + 3) / 4 * 4;  // band / side compute widths
     const int band = (N2 + 2 + 2 * R) * (wb + 2 * RP) + 2 * (N2 + 2) * wb;
     const int side = (kRingTX + 2 + 2 * R) * (ws + 2 * RP) + 2 * (kRingTX + 2) * ws;
-    return band > side ? band : side;
+    return (band > side ? band : side) + 3 * N2 * kRingTX;
 }
 
 // Visit the cells of an h x w rectangle with the CTA's 256 threads without integer division:
 // wide rows (band tiles) go row-per-warp, narrow rows (side tiles) 16 or 32 columns per row slot.
 template <class F> __device__ __forceinline__ void for_cells(int h, int w, F f)
 {
-    if (w > 32) {
-        for (int r = threadIdx.x >> 5; r < h; r += kWarps)
-            for (int c = threadIdx.x & 31; c < w; c += 32) f(r, c);
+    if (w > 32) {  // (row, 32-column chunk) pairs dealt round-robin to the warps
+        const int nch = (w + 31) >> 5;
+        int r = 0, ch = threadIdx.x >> 5;
+        while (ch >= nch) { ch -= nch; ++r; }
+        while (r < h) {
+            const int c = (ch << 5) + (threadIdx.x & 31);
+            if (c < w) f(r, c);
+            ch += kWarps;
+            while (ch >= nch) { ch -= nch; ++r; }
+        }
     } else if (w > 16) {
         const int c = threadIdx.x & 31;
         if (c < w)
@@ -457,11 +477,14 @@ template <class F> __device__ __forceinline__ void for_cells(int h, int w, F f)
     }
 }
 
-template <int RP, bool LS, class Emit>
+// `stage(z, x)` names one more global float per output cell (or nullptr) that is fetched together
+// with the halo and handed to `emit(z, x, value, staged)` (backward pass: the boundary-strip value
+// that BKEqual restores at that cell).
+template <int RP, bool LS, class Stage, class Emit>
 __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* __restrict__ P1,
                                           const float* __restrict__ P0, int sum_kind,
                                           bool inject, int r_u, int r_x, float wavelet,
-                                          const float* __restrict__ seis_row, float* smem, Emit emit)
+                                          const float* __restrict__ seis_row, float* smem, Stage stage, Emit emit)
 {
     const RingRect o  = ring_rect(G, tile);
     const int      NZ = G.NZ, NX = G.NX, N2 = G.N2, R = G.mmax, pitch = G.pitch;
@@ -475,7 +498,13 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
     float* s1 = smem;                          // (ch+2R) x SP: row 0 = z cza-R, column 0 = x cxa-RP
     float* s0 = s1 + (ch + 2 * R) * SP;        // ch x CW   previous field
     float* s2 = s0 + ch * CW;                  // ch x CW   unblended two-way result
+    const int oh = o.zb - o.za, ow = o.xb - o.xa;
+    float* sVb = s2 + ch * CW;                 // oh x ow   velocity at the cell
+    float* sVq = sVb + oh * ow;                // oh x ow   velocity of the edge formula's taoh2 term (Q2)
+    float* sAx = sVq + oh * ow;                // oh x ow   caller's staged value
 
+    // all global reads of the tile as asynchronous copies: every thread has its loads in flight
+    // together, one wait for the lot
     for_cells(ch + 2 * R, SP, [&](int r, int cidx) {
         int gz = cza - R + r, gx = cxa - RP + cidx;
         if (gz < 0) gz = -gz;                      // mirror about the array edge (:65-68)
@@ -483,9 +512,24 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
         if (gx < 0) gx = -gx;
         if (gx >= NX) gx = 2 * NX - 2 - gx;
         gx = min(max(gx, 0), NX - 1);              // (padding columns past the operator's reach)
-        s1[r * SP + cidx] = P1[(size_t)gz * pitch + gx];
+        cp_async4(s1 + r * SP + cidx, P1 + (size_t)gz * pitch + gx);
     });
-    for_cells(ch, CW, [&](int r, int cidx) { s0[r * CW + cidx] = P0[(size_t)(cza + r) * pitch + min(cxa + cidx, NX - 1)]; });
+    for_cells(ch, CW, [&](int r, int cidx) { cp_async4(s0 + r * CW + cidx, P0 + (size_t)(cza + r) * pitch + min(cxa + cidx, NX - 1)); });
+    for_cells(oh, ow, [&](int oz, int ox) {
+        const int z = o.za + oz, x = o.xa + ox;
+        const int dz = min(z, NZ - 1 - z), dx = min(x, NX - 1 - x);
+        const int a  = min(dz, dx);
+        cp_async4(sVb + oz * ow + ox, V + (size_t)z * pitch + x);
+        int fz = a, fx = x;              // top :124 / bottom :132 (and the corner cells, which do not use it)
+        if (dz >= dx) {                  // left :128 / right :136: flat index (N2-l)*NX + row
+            fx = z;                      // (a*NX + z) / NX and % NX without the division
+            while (fx >= NX) { fx -= NX; ++fz; }
+        }
+        cp_async4(sVq + oz * ow + ox, V + (size_t)fz * pitch + fx);
+        const float* g = stage(z, x);
+        if (g) cp_async4(sAx + oz * ow + ox, g);
+    });
+    cp_async_wait_all();
     __syncthreads();
 
     // two-way update of the compute rectangle: one float4 group (4 cells) per thread and pass,
@@ -538,10 +582,10 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
     }
     __syncthreads();
 
-    const int oh = o.zb - o.za, ow = o.xb - o.xa;
     for_cells(oh, ow, [&](int oz, int ox) {
         const int z = o.za + oz, x = o.xa + ox;
         const int lz = z - cza, lx = x - cxa;
+        const float vb = sVb[oz * ow + ox];
         const int dz = min(z, NZ - 1 - z), dx = min(x, NX - 1 - x);
         const int a  = min(dz, dx);
         const int sz = (z < NZ - 1 - z) ? 1 : -1, sx = (x < NX - 1 - x) ? 1 : -1;
@@ -549,11 +593,14 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
 #define S0(zz, xx) s0[(lz + (zz)) * CW + lx + (xx)]
 #define S1(zz, xx) s1[(lz + R + (zz)) * SP + lx + RP + (xx)]
         float Pb;
+#ifdef RTM_TIMING_SKIP_ONEWAY  // timing-only builds (wrong results): ring without the one-way solution
+        emit(z, x, S2(0, 0), sAx[oz * ow + ox]);
+        return;
+#endif
         if (abs(dz - dx) <= 1) {
             // corner cells (Hybrid1 :138-155): r1 = sqrt((v*tao/h)^2/2) at the cell itself
             // (GPU_velocity_real.cpp:104-117; tao/h enters as v*tao/h in float)
-            const float vv = __ldg(V + (size_t)z * pitch + x);
-            const float r  = __fdiv_rn(__fmul_rn(vv, G.tao), G.h);
+            const float r  = __fdiv_rn(__fmul_rn(vb, G.tao), G.h);
             const float r2 = __double2float_rn(__dmul_rn(__dmul_rn((double)r, (double)r), 0.5));
             const float r1 = __fsqrt_rn(r2);
             const float rcp = __frcp_rn(__fmaf_rn(2.0f, r1, 1.0f));
@@ -561,17 +608,12 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
             Pb = __fmul_rn(rcp, __fmaf_rn(r1, nb, S1(0, 0)));
         } else {
             int   iz, ix, tz, tx;
-            float vq;
             if (dz < dx) {  // top :124 / bottom :132
                 iz = sz; ix = 0; tz = 0; tx = 1;
-                vq = __ldg(V + (size_t)a * pitch + x);
-            } else {        // left :128 / right :136: flat index (N2-l)*NX + row
+            } else {        // left :128 / right :136
                 iz = 0; ix = sx; tz = 1; tx = 0;
-                int fz = a, fx = z;   // (a*NX + z) / NX and % NX without the division
-                while (fx >= NX) { fx -= NX; ++fz; }
-                vq = __ldg(V + (size_t)fz * pitch + fx);
             }
-            const float vb  = __ldg(V + (size_t)z * pitch + x);
+            const float vq  = sVq[oz * ow + ox];  // Q2: velocity at the reference's (mis-indexed) cell
             const float tv  = __fmul_rn(G.taoh, vb);
             const float rcp = __frcp_rn(__fadd_rn(tv, 1.0f));
             const float p2i = S2(iz, ix), p0i = S0(iz, ix), p0b = S0(0, 0);
@@ -595,7 +637,7 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
 #undef S2
 #undef S0
 #undef S1
-        emit(z, x, val);
+        emit(z, x, val, sAx[oz * ow + ox]);
     });
 }
 
@@ -674,13 +716,17 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
     const int  sum_kind = G.iLSTE == 0 ? SUM_FLOAT : SUM_DOUBLE;  // Add vs Add_Con
 
     if (is_ring) {
+#ifdef RTM_TIMING_SKIP_RING   // timing-only builds (wrong results): what the ring tiles cost
+        return;
+#endif
         float* P2 = a.P2 + so;
         const int N2 = G.N2, nf = G.nfdmax, NZ = G.NZ, NX = G.NX, k = a.k;
         const Strips st = a.st;
         float* gather = a.gather;
         ring_tile<RP, LS>(G, bt, a.P1 + so, a.P0 + so, sum_kind, true, src.x, src.y, a.wavelet,
                       nullptr, reinterpret_cast<float*>(smem_raw),
-                      [&](int z, int x, float val) {
+                      [](int, int) -> const float* { return nullptr; },
+                      [&](int z, int x, float val, float) {
             P2[(size_t)z * G.pitch + x] = val;
             if (st.up) {  // Hybrid3 :184-208 (slot k)
                 const size_t sx = ((size_t)shot * G.NT + k) * nf * G.mod_NX;
@@ -845,25 +891,40 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
     const float* seis_row = a.seis + ((size_t)shot * G.NT + (a.k + 1)) * G.n;
 
     if (is_ring) {
+#ifdef RTM_TIMING_SKIP_RING
+        return;
+#endif
         float* R2 = a.R2 + so;
         float* SX = a.S2 + so;
         const int N2 = G.N2, nf = G.nfdmax, NZ = G.NZ, NX = G.NX, k = a.k;
         const Strips st = a.st;
-        ring_tile<RP, LS>(G, bt, a.R1 + so, a.R0 + so, SUM_FLOAT, false, 0, 0, 0.0f, seis_row,
-                      reinterpret_cast<float*>(smem_raw), [&](int z, int x, float val) {
-            R2[(size_t)z * G.pitch + x] = val;
-            // BKEqual :222-245, one step early: the ring of the buffer that becomes the
-            // "current" source field at step k-1 receives the strips of slot k.
-            if (STORE) return;
+        // BKEqual :222-245, one step early: the ring of the buffer that becomes the "current"
+        // source field at step k-1 receives the strips of slot k.  The strip value of a cell is
+        // fetched with the tile's halo (`stage`) and written back by `emit`.
+        auto strip_src = [&](int z, int x) -> const float* {
+            if (STORE) return nullptr;
             const size_t sx = ((size_t)shot * G.NT + k) * nf * G.mod_NX;
             const size_t sz = ((size_t)shot * G.NT + k) * nf * G.mod_NZ;
             if (x >= N2 && x < NX - N2) {
-                if (z >= N2 - nf && z < N2) SX[(size_t)z * G.pitch + x] = st.up[sx + (size_t)(z - (N2 - nf)) * G.mod_NX + x - N2];
-                else if (z >= NZ - N2 && z < NZ - N2 + nf) SX[(size_t)z * G.pitch + x] = st.dw[sx + (size_t)(z - (NZ - N2)) * G.mod_NX + x - N2];
+                if (z >= N2 - nf && z < N2) return st.up + sx + (size_t)(z - (N2 - nf)) * G.mod_NX + x - N2;
+                if (z >= NZ - N2 && z < NZ - N2 + nf) return st.dw + sx + (size_t)(z - (NZ - N2)) * G.mod_NX + x - N2;
             } else if (z >= N2 && z < NZ - N2) {
-                if (x >= N2 - nf && x < N2) SX[(size_t)z * G.pitch + x] = st.lf[sz + (size_t)(z - N2) * nf + x - (N2 - nf)];
-                else if (x >= NX - N2 && x < NX - N2 + nf) SX[(size_t)z * G.pitch + x] = st.rt[sz + (size_t)(z - N2) * nf + x - (NX - N2)];
+                if (x >= N2 - nf && x < N2) return st.lf + sz + (size_t)(z - N2) * nf + x - (N2 - nf);
+                if (x >= NX - N2 && x < NX - N2 + nf) return st.rt + sz + (size_t)(z - N2) * nf + x - (NX - N2);
             }
+            return nullptr;
+        };
+        auto in_strips = [&](int z, int x) -> bool {
+            if (STORE) return false;
+            if (x >= N2 && x < NX - N2) return (z >= N2 - nf && z < N2) || (z >= NZ - N2 && z < NZ - N2 + nf);
+            if (z >= N2 && z < NZ - N2) return (x >= N2 - nf && x < N2) || (x >= NX - N2 && x < NX - N2 + nf);
+            return false;
+        };
+        ring_tile<RP, LS>(G, bt, a.R1 + so, a.R0 + so, SUM_FLOAT, false, 0, 0, 0.0f, seis_row,
+                      reinterpret_cast<float*>(smem_raw), strip_src,
+                      [&](int z, int x, float val, float strip) {
+            R2[(size_t)z * G.pitch + x] = val;
+            if (in_strips(z, x)) SX[(size_t)z * G.pitch + x] = strip;
         });
         return;
     }
