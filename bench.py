@@ -6,7 +6,7 @@ Workload (BASELINE.json configs[1]): Marmousi-shaped synthetic model 2301 x 751,
 NT = 7501 (3 s), 2301 data traces at the surface, 64 virtual sources.  A "step" is the full
 migration (forward modelling with boundary-strip saving, reverse-time reconstruction +
 receiver back-propagation + imaging, per-shot image filter and stacking) of one batch of
-SHOTS_PER_STEP shots; with the default K=8 steps the timed region covers the 64 shots.
+SHOTS_PER_STEP = 32 shots (two steps cover the 64 shots; the default K=4 steps migrate them twice).
 
   value  Mcell-updates/s, whole job, inputs resident in HBM (CUDA events inside the library,
          on the stream the kernels run on; max over ranks)
@@ -44,7 +44,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-SHOTS_PER_STEP = 8
+SHOTS_PER_STEP = 32   # shots per launch: 8 -> 267, 16 -> 279, 32 -> 286 Gcell-updates/s at NT=301 (profiles/README.md)
 TOTAL_SHOTS = 64
 
 
@@ -260,7 +260,7 @@ def reference_arm(args, w: Workload):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--shots-per-step", type=int, default=SHOTS_PER_STEP)
@@ -376,7 +376,10 @@ def main():
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get("bwd_pair_dram_bytes_per_step" if pairs else "bwd_step_kernel_dram_bytes_per_launch")
+            tj = json.loads(tf.read_text())  # recorded at tj["shots_per_launch"] shots per launch: scale to this run's batch
+            traffic = tj.get("bwd_pair_dram_bytes_per_step" if pairs else "bwd_step_kernel_dram_bytes_per_launch")
+            if traffic:
+                traffic = traffic * B / float(tj.get("shots_per_launch", 8))
         except Exception:
             traffic = None
     roofline = {"bound": "hbm",

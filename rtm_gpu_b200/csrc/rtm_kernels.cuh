@@ -441,14 +441,14 @@ __device__ __forceinline__ RingRect ring_rect(const Geo& G, int tile)
 }
 
 // shared memory needed by a ring tile (floats): current field with the stencil halo (rows: R,
-// columns: RP), previous field and two-way result on the compute rectangle padded to float4 groups,
+// columns: RP), previous field, velocity factor and two-way result on the compute rectangle padded to float4 groups,
 // and three values per output cell staged for the one-way phase (velocity at the cell, velocity
 // of the edge formula's tangential term, one caller-defined value)
 __host__ __device__ inline int ring_smem_floats(int N2, int R, int RP)
 {
     const int wb = (kRingTX + 2 + 3) / 4 * 4, ws = (N2 + 2 + 3) / 4 * 4;  // band / side compute widths
-    const int band = (N2 + 2 + 2 * R) * (wb + 2 * RP) + 2 * (N2 + 2) * wb;
-    const int side = (kRingTX + 2 + 2 * R) * (ws + 2 * RP) + 2 * (kRingTX + 2) * ws;
+    const int band = (N2 + 2 + 2 * R) * (wb + 2 * RP) + 3 * (N2 + 2) * wb;
+    const int side = (kRingTX + 2 + 2 * R) * (ws + 2 * RP) + 3 * (kRingTX + 2) * ws;
     return (band > side ? band : side) + 3 * N2 * kRingTX;
 }
 
@@ -458,13 +458,14 @@ template <class F> __device__ __forceinline__ void for_cells(int h, int w, F f)
 {
     if (w > 32) {  // (row, 32-column chunk) pairs dealt round-robin to the warps
         const int nch = (w + 31) >> 5;
-        int r = 0, ch = threadIdx.x >> 5;
-        while (ch >= nch) { ch -= nch; ++r; }
+        const int dq = kWarps / nch, dr = kWarps - dq * nch;   // task index advances by kWarps = dq rows + dr chunks
+        const int wp = threadIdx.x >> 5;
+        int r = wp / nch, ch = wp - r * nch;
         while (r < h) {
             const int c = (ch << 5) + (threadIdx.x & 31);
             if (c < w) f(r, c);
-            ch += kWarps;
-            while (ch >= nch) { ch -= nch; ++r; }
+            r += dq; ch += dr;
+            if (ch >= nch) { ch -= nch; ++r; }
         }
     } else if (w > 16) {
         const int c = threadIdx.x & 31;
@@ -499,7 +500,8 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
     float* s0 = s1 + (ch + 2 * R) * SP;        // ch x CW   previous field
     float* s2 = s0 + ch * CW;                  // ch x CW   unblended two-way result
     const int oh = o.zb - o.za, ow = o.xb - o.xa;
-    float* sVb = s2 + ch * CW;                 // oh x ow   velocity at the cell
+    float* sAv = s2 + ch * CW;                 // ch x CW   a = ((v*v)*tao2)*h2 of the two-way update
+    float* sVb = sAv + ch * CW;                // oh x ow   velocity at the cell
     float* sVq = sVb + oh * ow;                // oh x ow   velocity of the edge formula's taoh2 term (Q2)
     float* sAx = sVq + oh * ow;                // oh x ow   caller's staged value
 
@@ -514,7 +516,11 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
         gx = min(max(gx, 0), NX - 1);              // (padding columns past the operator's reach)
         cp_async4(s1 + r * SP + cidx, P1 + (size_t)gz * pitch + gx);
     });
-    for_cells(ch, CW, [&](int r, int cidx) { cp_async4(s0 + r * CW + cidx, P0 + (size_t)(cza + r) * pitch + min(cxa + cidx, NX - 1)); });
+    for_cells(ch, CW, [&](int r, int cidx) {
+        const size_t cell = (size_t)(cza + r) * pitch + min(cxa + cidx, NX - 1);
+        cp_async4(s0 + r * CW + cidx, P0 + cell);
+        cp_async4(sAv + r * CW + cidx, G.avel + G.padL + cell);
+    });
     for_cells(oh, ow, [&](int oz, int ox) {
         const int z = o.za + oz, x = o.xa + ox;
         const int dz = min(z, NZ - 1 - z), dx = min(x, NX - 1 - x);
@@ -537,7 +543,6 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
     {
         LsTable T{};
         T.ip = G.Index; T.cp = G.c; T.bmin = 0; T.bmax = 0xffff; T.staged = false;
-        const float* AV = G.avel + G.padL;
         const unsigned short* BN = G.bins + G.padL;
         int sh = 0;
         while ((1 << sh) < NG) ++sh;               // groups per row rounded up to a power of two
@@ -557,11 +562,11 @@ __device__ __forceinline__ void ring_tile(const Geo& G, int tile, const float* _
             float w1[4], p1[4], p0[4], val[4];
             stencil_row<RP, LS, 0>(G, s1 + (lz + R) * SP + 4 * g + RP, G.nfdmax, T, b4, w1, p1, SP);
             unpack(*reinterpret_cast<const float4*>(s0 + lz * CW + 4 * g), p0);
+            float avq[4];
+            unpack(*reinterpret_cast<const float4*>(sAv + lz * CW + 4 * g), avq);  // ((v*v)*tao2)*h2, the kernels' own rounding
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float av = __ldg(AV + row + xq[q]);  // ((v*v)*tao2)*h2, the kernels' own rounding
-                val[q] = sum_kind == SUM_FLOAT ? finish_float(av, w1[q], p1[q], p0[q]) : finish_double(av, w1[q], p1[q], p0[q]);
-            }
+            for (int q = 0; q < 4; ++q)
+                val[q] = sum_kind == SUM_FLOAT ? finish_float(avq[q], w1[q], p1[q], p0[q]) : finish_double(avq[q], w1[q], p1[q], p0[q]);
             if (seis_row && z == G.s_z) {  // replacement (BKAdd :349-353)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
