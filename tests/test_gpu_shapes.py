@@ -101,3 +101,21 @@ def test_source_inside_the_ring_and_non_compensated():
                 tao1=5e-4, mod_NZ=90, mod_NX=200, NT1=40, s_l=3, s_z=1, n=40, ds=5, r_x=3, nrec=2,
                 NX_ED=200, NZ_ED=90)
     run_case(case, [9, 4], [12, 5], snaps=(2, 3, 39))  # (N2-1, x) and a cell deep in the ring
+
+
+def test_tall_narrow_grid():
+    """NZ > NX and a grid narrower than one ring tile: each band is a single clipped tile holding both
+    corner squares, the sides take several tiles, and the left/right edge formula's velocity index
+    (kernel.cu:128/:136, a flat (N2-l)*NX + row) wraps over several rows of the model."""
+    case = Case(name="tall", nfdmax=4, nfdmin=2, N2=10, iLSTE=1, iCompen=1, hz=10.0, h=10.0, tao=5e-4,
+                tao1=5e-4, mod_NZ=400, mod_NX=60, NT1=40, s_l=1, s_z=2, n=12, ds=5, r_x=30, nrec=2,
+                NX_ED=60, NZ_ED=400)
+    run_case(case, [14, 405], [66, 12], snaps=(2, 20, 39))  # 4-5 cells from the top/right and bottom/left ring
+
+
+def test_tall_narrow_grid_adaptive():
+    """The same shape with the adaptive operator (ring tiles read the global operator tables)."""
+    case = Case(name="tall_ls", nfdmax=8, nfdmin=2, N2=10, f0=15.0, fmax=31.0, iLSTE=0, hz=20.0, h=20.0, tao=1e-3,
+                tao1=1e-3, mod_NZ=300, mod_NX=70, NT1=30, s_l=3, s_z=2, n=12, ds=5, r_x=30, nrec=2,
+                NX_ED=70, NZ_ED=300, nthita=100, dv=1.0)
+    run_case(case, [13, 306], [76, 13], snaps=(2, 15, 29))
