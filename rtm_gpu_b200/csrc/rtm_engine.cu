@@ -314,6 +314,8 @@ struct rtm_ctx {
     // L2 look-ahead (profiles/README.md): one thread of every interior CTA prefetches the TMA boxes
     // of the CTA `distance` blocks ahead (cp.async.bulk.prefetch.tensor), so that CTA's copies hit L2
     int    lookahead_f = 148, lookahead_b = 148, lookahead_b2 = 148, lookahead_more = 1, lookahead_p0 = 3;
+    // ring CTAs dealt evenly among the interior CTAs of a launch (RTM_RING_INTERLEAVE=0: all ring CTAs first)
+    bool   ring_interleave = true;
     Acc4Maps tmap_acc;
     bool   dry = false;                     // launch helpers only set kernel attributes
     long   nlaunch = 0;                     // kernels launched (graph replays included)
@@ -469,6 +471,7 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     if (const char* e = std::getenv("RTM_FUSE2")) { c->fuse2 = std::atoi(e) != 0; c->fuse2_forced = c->fuse2; }
     if (!c->fuse2_forced && p->iLSTE == 0) c->fuse2 = false;
     if (const char* e = std::getenv("RTM_FUSE2_MAXRP")) c->fuse2_maxrp = std::atoi(e);
+    if (const char* e = std::getenv("RTM_RING_INTERLEAVE")) c->ring_interleave = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_LOOKAHEAD_F")) c->lookahead_f = std::atoi(e);
     if (const char* e = std::getenv("RTM_LOOKAHEAD_B2")) c->lookahead_b2 = std::atoi(e);
     if (const char* e = std::getenv("RTM_LOOKAHEAD_MORE")) c->lookahead_more = std::atoi(e);
@@ -756,6 +759,13 @@ extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const fl
 }
 
 // ------------------------------------------------------------------------------------ launches
+// Ring CTAs of a launch of `total` blocks: every period-th block over the first 7/8 of the grid
+// (the last ring CTA must not become the launch's tail); see block_role().
+static int ring_period(const rtm_ctx* c, int ring_ctas, int total)
+{
+    if (!c->ring_interleave || ring_ctas == 0) return 1;
+    return std::max(1, (total - total / 8) / ring_ctas);
+}
 // One launch = the interior tiles of one class (+ the ring tiles when do_ring).
 template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int buf, FwdArgs a)
 {
@@ -770,6 +780,7 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass&
     a.tiles = k.d_tiles_f; a.ntiles = k.n_f; a.fd_ntiles = make_fastdiv(k.n_f); a.lookahead = c->lookahead_f;
     dim3 grid((unsigned)((nring + k.n_f) * ns));
     if (grid.x == 0 || c->dry) return RTM_OK;
+    a.ring_period = ring_period(c, nring * ns, (int)grid.x); a.fd_period = make_fastdiv(a.ring_period);
     ++c->nlaunch;
     a.lookahead_p0 = 1;
     a.tma_s0_p0 = buf < 0 ? a.tma_s0 - c->S : 0;
@@ -791,6 +802,7 @@ template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx
     a.tiles = frame ? k.d_tiles_bf : k.d_tiles_b; a.ntiles = frame ? k.n_bf : k.n_b; a.fd_ntiles = make_fastdiv(a.ntiles);
     dim3 grid((unsigned)((nring + a.ntiles) * ns));
     if (grid.x == 0 || c->dry) return RTM_OK;
+    a.ring_period = ring_period(c, nring * ns, (int)grid.x); a.fd_period = make_fastdiv(a.ring_period);
     ++c->nlaunch;
     a.lookahead = c->lookahead_b; a.lookahead_p0 = c->lookahead_p0;
     bwd_step_kernel<RP, LS, RTM_NR_B, STORE><<<grid, kThreads, smem, st>>>(k.tmap_b[STORE ? r1 : s1], k.tmap_b[r1], k.tmap_b[STORE ? r0 : s0],

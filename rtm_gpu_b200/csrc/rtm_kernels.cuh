@@ -657,6 +657,18 @@ __device__ __forceinline__ void store4(float* dst, const float (&o)[4], int x, i
     }
 }
 
+// Position of a block in a launch that carries ring CTAs.  The nrc ring CTAs are dealt evenly among
+// the interior CTAs -- block b is a ring CTA when b is one of the first nrc multiples of `period` --
+// so that an SM works on a ring tile (long, instruction-bound) next to interior tiles (HBM-bound)
+// for most of the launch instead of the ring tiles forming its first waves.  period = 1: ring first.
+struct BlockRole { bool is_ring; int index; };   // index among the ring CTAs / among the interior CTAs
+__device__ __forceinline__ BlockRole block_role(int b, int nrc, int period, const FastDiv& fd_period)
+{
+    const int  q = fast_div(b, fd_period);
+    const bool ring = q < nrc && b == q * period;           // (nrc == 0: never)
+    return BlockRole{ring, ring ? q : b - min(q + 1, nrc)};
+}
+
 // ------------------------------------------------------------------------------------
 // Forward step: slot k from slots k-1 (P1, via TMA / raw pointer) and k-2 (P0).
 // grid = (ring tiles + interior tiles, shots)
@@ -676,6 +688,8 @@ struct FwdArgs {
     int          lookahead;  // CTAs ahead whose TMA box is prefetched into L2 (0: off; all-tiles launches only)
     int          lookahead_p0, tma_s0_p0;  // ... and its slot k-2 box (tma_s0_p0: like tma_s0, for the P0 map)
     int          do_ring; // this launch also carries the ring tiles
+    int          ring_period;  // every ring_period-th block (from block 0) is a ring CTA; 1 = all ring CTAs first
+    FastDiv      fd_period;
     Strips       st;   // may hold nulls when strips are not wanted (pure modelling)
     float*       gather;  // [S][NT][n] time-major, or null
 };
@@ -712,8 +726,9 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
     // A time step may be split into several launches, one per operator-length class of the
     // interior tiles (adaptive operator): each carries its own tile list; one of them the ring.
     const int  nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0, nint = a.ntiles;
-    const bool is_ring = (int)blockIdx.x < a.nshots * nring;
-    const int  bi   = is_ring ? blockIdx.x : blockIdx.x - a.nshots * nring;
+    const BlockRole role = block_role(blockIdx.x, a.nshots * nring, a.ring_period, a.fd_period);
+    const bool is_ring = role.is_ring;
+    const int  bi   = role.index;
     const int  shot = is_ring ? fast_div(bi, G.fd_nring) : fast_div(bi, a.fd_ntiles);
     const int  bt   = bi - shot * (is_ring ? nring : nint);  // ring tile / position in the tile list
     const long long so = (long long)shot * G.shot_stride + G.padL;  // (z=0,x=0) of this shot
@@ -872,6 +887,8 @@ struct BwdArgs {
     int          lookahead;     // CTAs ahead whose TMA boxes are prefetched into L2 (0: off)
     int          lookahead_p0;  // bit 0: also its receiver slot k+2 box, bit 1: also its source slot k+2 box
     int          do_ring;
+    int          ring_period;
+    FastDiv      fd_period;
     Strips       st;
     const float* seis;  // [S][NT][n] time-major; row k+1 is imposed
     float *sumS, *sumR, *rel1, *rel2;  // accumulators, field layout
@@ -887,8 +904,9 @@ bwd_step_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant_
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int  nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0, nint = a.ntiles;
-    const bool is_ring = (int)blockIdx.x < a.nshots * nring;
-    const int  bi   = is_ring ? blockIdx.x : blockIdx.x - a.nshots * nring;
+    const BlockRole role = block_role(blockIdx.x, a.nshots * nring, a.ring_period, a.fd_period);
+    const bool is_ring = role.is_ring;
+    const int  bi   = role.index;
     const int  shot = is_ring ? fast_div(bi, G.fd_nring) : fast_div(bi, a.fd_ntiles);
     const int  bt   = bi - shot * (is_ring ? nring : nint);
     const long long so = (long long)shot * G.shot_stride + G.padL;
