@@ -759,12 +759,9 @@ extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const fl
 }
 
 // ------------------------------------------------------------------------------------ launches
-// Ring CTAs of a launch of `total` blocks: every period-th block over the first 7/8 of the grid
-// (the last ring CTA must not become the launch's tail); see block_role().
-static int ring_period(const rtm_ctx* c, int ring_ctas, int total)
+static int ring_period(const rtm_ctx* c, int ring_ctas, int total)  // see block_role()
 {
-    if (!c->ring_interleave || ring_ctas == 0) return 1;
-    return std::max(1, (total - total / 8) / ring_ctas);
+    return ring_period_for(c->ring_interleave, ring_ctas, total);
 }
 // One launch = the interior tiles of one class (+ the ring tiles when do_ring).
 template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int buf, FwdArgs a)

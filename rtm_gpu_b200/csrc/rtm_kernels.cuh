@@ -65,9 +65,13 @@ __host__ inline FastDiv make_fastdiv(int d)
     }
     return f;
 }
-__device__ __forceinline__ int fast_div(int n, const FastDiv& f)
+__host__ __device__ __forceinline__ int fast_div(int n, const FastDiv& f)
 {
+#ifdef __CUDA_ARCH__
     return f.d == 1 ? n : (int)(__umulhi((unsigned)n, f.mul) >> f.shr);
+#else   // host (tests): the same multiply-high in 64-bit arithmetic
+    return f.d == 1 ? n : (int)((unsigned)(((unsigned long long)(unsigned)n * f.mul) >> 32) >> f.shr);
+#endif
 }
 
 struct Geo {
@@ -662,11 +666,19 @@ __device__ __forceinline__ void store4(float* dst, const float (&o)[4], int x, i
 // so that an SM works on a ring tile (long, instruction-bound) next to interior tiles (HBM-bound)
 // for most of the launch instead of the ring tiles forming its first waves.  period = 1: ring first.
 struct BlockRole { bool is_ring; int index; };   // index among the ring CTAs / among the interior CTAs
-__device__ __forceinline__ BlockRole block_role(int b, int nrc, int period, const FastDiv& fd_period)
+__host__ __device__ __forceinline__ BlockRole block_role(int b, int nrc, int period, const FastDiv& fd_period)
 {
     const int  q = fast_div(b, fd_period);
     const bool ring = q < nrc && b == q * period;           // (nrc == 0: never)
-    return BlockRole{ring, ring ? q : b - min(q + 1, nrc)};
+    return BlockRole{ring, ring ? q : b - (q + 1 < nrc ? q + 1 : nrc)};
+}
+// Ring CTAs of a launch of `total` blocks: every period-th block over the first 7/8 of the grid (the
+// last ring CTA must not become the launch's tail).  Needs (ring_ctas - 1) * period < total.
+__host__ inline int ring_period_for(bool interleave, int ring_ctas, int total)
+{
+    if (!interleave || ring_ctas == 0) return 1;
+    const int p = (total - total / 8) / ring_ctas;
+    return p < 1 ? 1 : p;
 }
 
 // ------------------------------------------------------------------------------------
