@@ -733,8 +733,8 @@ fwd_step_kernel(const __grid_constant__ CUtensorMap tmP1, const __grid_constant_
                 const __grid_constant__ Geo G, const FwdArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // 1-D grid: the ring tiles of ALL shots first (they are the longest-running CTAs and would
-    // otherwise form the tail of the launch), then the interior tiles shot by shot.
+    // 1-D grid: the interior tiles shot by shot, with the ring tiles of all shots dealt evenly among
+    // them over the first 7/8 of the grid (block_role(); they are the longest-running CTAs).
     // A time step may be split into several launches, one per operator-length class of the
     // interior tiles (adaptive operator): each carries its own tile list; one of them the ring.
     const int  nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0, nint = a.ntiles;
