@@ -5,7 +5,9 @@ import numpy as np
 import pytest
 
 import oraclelib as O
-from golden_cases import GOLDEN_CASES
+from golden_cases import CPU_GOLDEN_CASES, GOLDEN_CASES
+
+ALL_CASES = {**GOLDEN_CASES, **CPU_GOLDEN_CASES}
 from refcase import ROOT, data_tiny, velocity_tiny
 
 
@@ -23,9 +25,9 @@ def setup(case, g):
     return v, vmin, vmax, c, Index
 
 
-@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+@pytest.mark.parametrize("name", list(ALL_CASES))
 def test_migrate_bit_exact(name):
-    case, g = GOLDEN_CASES[name], load(name)
+    case, g = ALL_CASES[name], load(name)
     v, vmin, vmax, c, Index = setup(case, g)
     p = O.make_params(case, vmin, vmax, contract=0)
     ups, downs = [], []
@@ -50,9 +52,9 @@ def test_migrate_bit_exact(name):
         assert np.array_equal(win, g["final"], equal_nan=True)
 
 
-@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+@pytest.mark.parametrize("name", list(ALL_CASES))
 def test_forward_gather_and_snapshots(name):
-    case, g = GOLDEN_CASES[name], load(name)
+    case, g = ALL_CASES[name], load(name)
     v, vmin, vmax, c, Index = setup(case, g)
     p = O.make_params(case, vmin, vmax, contract=0)
     for m, ru in enumerate(case.r_u):

@@ -30,7 +30,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 import oraclelib as O  # noqa: E402
 from refcase import (Case, data_tiny, read_final_image, read_shot_images, run_reference,  # noqa: E402
                      velocity_tiny, write_inputs)
-from golden_cases import GOLDEN_CASES  # noqa: E402
+from golden_cases import CPU_GOLDEN_CASES, GOLDEN_CASES  # noqa: E402
 
 
 def build(case: Case, outpath: Path):
@@ -127,9 +127,10 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["resample"]:
         build_resample(ROOT / "tests" / "golden" / "resample.npz")
         sys.exit(0)
-    want = sys.argv[1:] or list(GOLDEN_CASES)
+    cases = {**GOLDEN_CASES, **CPU_GOLDEN_CASES}
+    want = sys.argv[1:] or list(cases)
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     for name in want:
-        build(GOLDEN_CASES[name], ROOT / "tests" / "golden" / f"{name}.npz")
+        build(cases[name], ROOT / "tests" / "golden" / f"{name}.npz")
     if not sys.argv[1:]:
         build_resample(ROOT / "tests" / "golden" / "resample.npz")
