@@ -316,6 +316,7 @@ struct rtm_ctx {
     int    lookahead_f = 148, lookahead_b = 148, lookahead_b2 = 148, lookahead_more = 1, lookahead_p0 = 3;
     // ring CTAs dealt evenly among the interior CTAs of a launch (RTM_RING_INTERLEAVE=0: all ring CTAs first)
     bool   ring_interleave = true;
+    int    ring_spread = 8;                 // ... over the first ring_spread/8 of the grid (RTM_RING_SPREAD)
     Acc4Maps tmap_acc;
     bool   dry = false;                     // launch helpers only set kernel attributes
     long   nlaunch = 0;                     // kernels launched (graph replays included)
@@ -472,6 +473,7 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     if (!c->fuse2_forced && p->iLSTE == 0) c->fuse2 = false;
     if (const char* e = std::getenv("RTM_FUSE2_MAXRP")) c->fuse2_maxrp = std::atoi(e);
     if (const char* e = std::getenv("RTM_RING_INTERLEAVE")) c->ring_interleave = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RTM_RING_SPREAD")) c->ring_spread = std::atoi(e);
     if (const char* e = std::getenv("RTM_LOOKAHEAD_F")) c->lookahead_f = std::atoi(e);
     if (const char* e = std::getenv("RTM_LOOKAHEAD_B2")) c->lookahead_b2 = std::atoi(e);
     if (const char* e = std::getenv("RTM_LOOKAHEAD_MORE")) c->lookahead_more = std::atoi(e);
@@ -761,7 +763,7 @@ extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const fl
 // ------------------------------------------------------------------------------------ launches
 static int ring_period(const rtm_ctx* c, int ring_ctas, int total)  // see block_role()
 {
-    return ring_period_for(c->ring_interleave, ring_ctas, total);
+    return ring_period_for(c->ring_interleave, ring_ctas, total, c->ring_spread);
 }
 // One launch = the interior tiles of one class (+ the ring tiles when do_ring).
 template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int buf, FwdArgs a)

@@ -25,12 +25,12 @@ int main()
     // block_role: a bijection onto ring CTAs 0..nrc-1 and interior CTAs 0..nint-1, ring CTAs at multiples of the
     // period, the last one inside the grid; both with and without interleaving
     const int nrcs[] = {0, 1, 7, 50, 400, 1600, 3184}, nints[] = {0, 1, 3, 126, 1008, 3456, 13824, 197192};
-    for (int il = 0; il < 2; ++il)
+    for (int il = 0; il <= 8; ++il)   // 0: ring CTAs first; 1..8: dealt over the first il/8 of the grid
         for (int nrc : nrcs)
             for (int nint : nints) {
                 const int total = nrc + nint;
                 if (total == 0) continue;
-                const int period = ring_period_for(il != 0, nrc, total);
+                const int period = ring_period_for(il != 0, nrc, total, il);
                 if (period < 1 || (nrc > 0 && (long long)(nrc - 1) * period >= total)) { std::printf("period %d %d %d\n", nrc, nint, period); return 2; }
                 if (!il && period != 1) return 3;
                 const FastDiv fd = make_fastdiv(period);
