@@ -175,9 +175,11 @@ extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int ver
     if (ngpu <= 0 || ngpu > ndev) ngpu = ndev;
     ngpu = std::min(ngpu, c.nrec);
     if (batch <= 0) {
-        // enough cells per launch to fill the GPU (small grids are launch-bound otherwise)
+        // enough cells per launch to amortise the tail of every launch (small grids are launch-bound
+        // otherwise; on the 2301 x 751 benchmark 8 -> 16 -> 32 shots per launch = 267 -> 279 -> 286
+        // Gcell-updates/s, profiles/README.md)
         const double cells = (double)g.NZ * g.NX;
-        batch = (int)std::min(32.0, std::max(1.0, std::ceil(12.0e6 / cells)));
+        batch = (int)std::min(32.0, std::max(1.0, std::ceil(57.0e6 / cells)));
         // ... bounded by HBM: 9 fields + strips + traces per shot, keep within ~100 GB
         const double per_shot = 9.0 * cells * 4 + 8.0 * g.NT * c.nfdmax * (c.mod_NX + c.mod_NZ) + 8.0 * g.NT * c.n;
         batch = (int)std::max(1.0, std::min((double)batch, std::floor(100.0e9 / per_shot)));
