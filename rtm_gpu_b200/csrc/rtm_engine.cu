@@ -17,6 +17,7 @@
 #include "../../include/rtm_b200.h"
 #include "host/rtm_host.h"
 #include "rtm_kernels.cuh"
+#include "rtm_stream.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -301,6 +302,16 @@ struct rtm_ctx {
         int *d_tiles_ii = nullptr, *d_tiles_ib = nullptr, *d_tiles_bf = nullptr;
         CUtensorMap tmap_f[kFields], tmap_b[kFields], tmap_b2[kFields], tmap_store;
         size_t smem_f = 0, smem_b = 0, smem_b2 = 0;  // dynamic shared memory already granted to the kernels
+        // z-streaming two-step kernel (rtm_stream.cuh): the ii / ib tiles regrouped into column segments
+        int4 *d_segs_ii = nullptr, *d_segs_ib = nullptr;
+        int  n_segs_ii = 0, n_segs_ib = 0;
+        // ... and of the forward pass (32-row tiles): frame tiles stepped singly, inner tiles as segments
+        int4 *d_segs_fii = nullptr, *d_segs_fib = nullptr;
+        int  n_segs_fii = 0, n_segs_fib = 0, n_fii_tiles = 0;
+        int *d_tiles_ff = nullptr, n_ff = 0;
+        bool smem_s2f = false;
+        CUtensorMap tmap_s_cur[kFields], tmap_s_prev[kFields];   // boxes (128+4RP) x 8 and (128+2RP) x 8
+        bool smem_s2 = false;
     };
     // Pair stepping of the backward pass (two-step kernel on the inner tiles).  Measured on the
     // B200 (profiles/README.md) it pays for the Taylor operator up to radius 4 once a launch holds a
@@ -318,6 +329,12 @@ struct rtm_ctx {
     bool   ring_interleave = true;
     int    ring_spread = 8;                 // ... over the first ring_spread/8 of the grid (RTM_RING_SPREAD)
     Acc4Maps tmap_acc;
+    // z-streaming form of the two-step kernel (Taylor operator, radius <= 4): RTM_STREAM2=0 keeps the tile form;
+    // RTM_SEG_TILES = longest segment in 16-row tiles
+    bool   stream2 = true;
+    int    seg_tiles = 8;
+    int    fuse2_fwd = -1;                  // forward pass in pairs: RTM_FUSE2_FWD=0 off, 1 forced, unset: like the backward pass
+    CUtensorMap tmap_s_acc[4];              // rel1, rel2, sumS, sumR with a box of 128 x 8
     bool   dry = false;                     // launch helpers only set kernel attributes
     long   nlaunch = 0;                     // kernels launched (graph replays included)
     std::map<long long, long> graph_launches;
@@ -353,7 +370,7 @@ struct rtm_ctx {
     rtm_stats stats{};
 };
 
-static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int RP, int tile_rows, long long nslab = 0)  // RP = 0: box = the tile
+static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int RP, int tile_rows, long long nslab = 0, int box_w = 0)  // RP = 0: box = the tile; box_w > 0: box_w x tile_rows
 {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -372,6 +389,7 @@ static int encode_tmap(rtm_ctx* c, CUtensorMap* m, float* base, int RP, int tile
     cuuint64_t dims[3]    = {(cuuint64_t)G.pitch, (cuuint64_t)G.NZ, (cuuint64_t)(nslab ? nslab : c->S)};
     cuuint64_t strides[2] = {(cuuint64_t)G.pitch * 4, (cuuint64_t)G.shot_stride * 4};
     cuuint32_t box[3]     = {(cuuint32_t)(kTX + 2 * RP), (cuuint32_t)(tile_rows + 2 * RP), 1};
+    if (box_w > 0) { box[0] = (cuuint32_t)box_w; box[1] = (cuuint32_t)tile_rows; }
     cuuint32_t estr[3]    = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -395,7 +413,7 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
-    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); }
+    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); cudaFree(k.d_segs_ii); cudaFree(k.d_segs_ib); cudaFree(k.d_segs_fii); cudaFree(k.d_segs_fib); cudaFree(k.d_tiles_ff); }
     cudaFree(c->store);
     for (auto& f : c->field) cudaFree(f);
     for (auto& f : c->acc) cudaFree(f);
@@ -472,6 +490,9 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     if (const char* e = std::getenv("RTM_FUSE2")) { c->fuse2 = std::atoi(e) != 0; c->fuse2_forced = c->fuse2; }
     if (!c->fuse2_forced && p->iLSTE == 0) c->fuse2 = false;
     if (const char* e = std::getenv("RTM_FUSE2_MAXRP")) c->fuse2_maxrp = std::atoi(e);
+    if (const char* e = std::getenv("RTM_STREAM2")) c->stream2 = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RTM_FUSE2_FWD")) c->fuse2_fwd = std::atoi(e) != 0 ? 1 : 0;
+    if (const char* e = std::getenv("RTM_SEG_TILES")) c->seg_tiles = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RTM_RING_INTERLEAVE")) c->ring_interleave = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_RING_SPREAD")) c->ring_spread = std::atoi(e);
     if (const char* e = std::getenv("RTM_LOOKAHEAD_F")) c->lookahead_f = std::atoi(e);
@@ -581,7 +602,7 @@ static int prepare_ls(rtm_ctx* c)
 static int prepare_classes(rtm_ctx* c)
 {
     const Geo& G = c->G;
-    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); }
+    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); cudaFree(k.d_segs_ii); cudaFree(k.d_segs_ib); cudaFree(k.d_segs_fii); cudaFree(k.d_segs_fib); cudaFree(k.d_tiles_ff); }
     c->classes.clear();
     const int nf = G.ntx * G.ntz_f, nb = G.ntx * G.ntz_b;
     struct Lists { std::vector<int> fwd, bwd, ii, ib, frame; };
@@ -668,6 +689,67 @@ static int prepare_classes(rtm_ctx* c)
         }
         if (int rc = upload(L.ib, &k.d_tiles_ib)) return rc;
         if (int rc = upload(L.frame, &k.d_tiles_bf)) return rc;
+        if (c->stream2 && !ls && k.RP == 4 && k.n_b2 > 0) {
+            // the same tiles as column segments for the z-streaming kernel: runs of vertically adjacent
+            // tiles of one tile column, cut into pieces of at most seg_tiles tiles of equal length (+-1)
+            auto segments = [&](const std::vector<int>& tiles, int tile_rows, int4** d, int* nout) -> int {
+                std::vector<int> v(tiles);
+                std::sort(v.begin(), v.end(), [&](int a, int b) {
+                    const int ax = a % G.ntx, bx = b % G.ntx;
+                    return ax != bx ? ax < bx : a < b;
+                });
+                const int seg_tiles = std::max(1, c->seg_tiles * TZb / tile_rows);   // RTM_SEG_TILES counts 16-row tiles
+                std::vector<int4> segs;
+                for (size_t i = 0; i < v.size();) {
+                    size_t j = i + 1;
+                    while (j < v.size() && v[j] == v[j - 1] + G.ntx) ++j;   // same column, next tile row
+                    const int run = (int)(j - i), pieces = (run + seg_tiles - 1) / seg_tiles;
+                    int t0 = 0;
+                    for (int p = 0; p < pieces; ++p) {
+                        const int len = run / pieces + (p < run % pieces ? 1 : 0);
+                        const int t = v[i + t0];
+                        segs.push_back(make_int4(G.N2 + (t % G.ntx) * kTX, G.N2 + (t / G.ntx) * tile_rows, len * tile_rows / Strm<4>::BR, 0));
+                        t0 += len;
+                    }
+                    i = j;
+                }
+                *nout = (int)segs.size();
+                if (segs.empty()) return RTM_OK;
+                CK(cudaMalloc(d, sizeof(int4) * segs.size()));
+                CK(cudaMemcpy(*d, segs.data(), sizeof(int4) * segs.size(), cudaMemcpyHostToDevice));
+                return RTM_OK;
+            };
+            if (int rc = segments(L.ii, TZb, &k.d_segs_ii, &k.n_segs_ii)) return rc;
+            if (int rc = segments(L.ib, TZb, &k.d_segs_ib, &k.n_segs_ib)) return rc;
+            {   // forward tiling (32-row tiles): inner = full and, grown by one radius, inside the interior
+                const int TZf = kWarps * RTM_NR_F;
+                std::vector<char> cov(nf, 0);
+                for (int t = 0; t < nf; ++t) {
+                    const int z0 = G.N2 + (t / G.ntx) * TZf, x0 = G.N2 + (t % G.ntx) * kTX;
+                    cov[t] = z0 - c->RP >= G.N2 && x0 - c->RP >= G.N2 && z0 + TZf + c->RP <= G.NZ - G.N2 && x0 + kTX + c->RP <= G.NX - G.N2;
+                }
+                std::vector<int> fii, fib, ff;
+                for (int t = 0; t < nf; ++t) {
+                    if (!cov[t]) { ff.push_back(t); continue; }
+                    bool all = true;   // (an inner tile never touches the edge of the tiling)
+                    for (int dz = -1; dz <= 1; ++dz)
+                        for (int dx = -1; dx <= 1; ++dx) all = all && cov[t + dz * G.ntx + dx];
+                    (all ? fii : fib).push_back(t);
+                }
+                if (!fii.empty() || !fib.empty()) {
+                    if (int rc = segments(fii, TZf, &k.d_segs_fii, &k.n_segs_fii)) return rc;
+                    if (int rc = segments(fib, TZf, &k.d_segs_fib, &k.n_segs_fib)) return rc;
+                    if (int rc = upload(ff, &k.d_tiles_ff)) return rc;
+                    k.n_ff = (int)ff.size();
+                    k.n_fii_tiles = (int)fii.size();
+                }
+            }
+            for (int i = 0; i < rtm_ctx::kFields; ++i) {
+                int rc = encode_tmap(c, &k.tmap_s_cur[i], c->field[i], 0, Strm<4>::BR, 0, Strm<4>::W1);
+                if (!rc) rc = encode_tmap(c, &k.tmap_s_prev[i], c->field[i], 0, Strm<4>::BR, 0, Strm<4>::WM);
+                if (rc) return rc;
+            }
+        }
         for (int i = 0; i < rtm_ctx::kFields; ++i) {
             int rc = encode_tmap(c, &k.tmap_f[i], c->field[i], k.RP, kWarps * RTM_NR_F);
             if (!rc) rc = encode_tmap(c, &k.tmap_b[i], c->field[i], k.RP, kWarps * RTM_NR_B);
@@ -678,8 +760,10 @@ static int prepare_classes(rtm_ctx* c)
             if (int rc = encode_tmap(c, &k.tmap_store, c->store, k.RP, kWarps * RTM_NR_F, (long long)G.NT * c->S)) return rc;
         // accumulators: rel1, rel2, sumS, sumR (acc[] holds sumS, sumR, rel1, rel2)
         const int order[4] = {2, 3, 0, 1};
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) {
             if (int rc = encode_tmap(c, &c->tmap_acc.m[i], c->acc[order[i]], 0, Tile2<4>::TZ)) return rc;
+            if (int rc = encode_tmap(c, &c->tmap_s_acc[i], c->acc[order[i]], 0, Strm<4>::BR, 0, kTX)) return rc;
+        }
         c->classes.push_back(k);
     }
     CK(cudaDeviceSynchronize());
@@ -766,7 +850,9 @@ static int ring_period(const rtm_ctx* c, int ring_ctas, int total)  // see block
     return ring_period_for(c->ring_interleave, ring_ctas, total, c->ring_spread);
 }
 // One launch = the interior tiles of one class (+ the ring tiles when do_ring).
-template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int buf, FwdArgs a)
+// buf / p0buf: field buffers of slots k-1 / k-2 (buf < 0: store-all slab); frame: only the tiles the
+// streaming two-step kernel does not cover
+template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int buf, int p0buf, bool frame, FwdArgs a)
 {
     const Geo& G = c->G;
     const int nring = a.do_ring ? 2 * G.nband + 2 * G.nside : 0;
@@ -776,15 +862,15 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass&
         CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS, RTM_NR_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k.smem_f = smem;
     }
-    a.tiles = k.d_tiles_f; a.ntiles = k.n_f; a.fd_ntiles = make_fastdiv(k.n_f); a.lookahead = c->lookahead_f;
-    dim3 grid((unsigned)((nring + k.n_f) * ns));
+    a.tiles = frame ? k.d_tiles_ff : k.d_tiles_f; a.ntiles = frame ? k.n_ff : k.n_f; a.fd_ntiles = make_fastdiv(a.ntiles); a.lookahead = c->lookahead_f;
+    dim3 grid((unsigned)((nring + a.ntiles) * ns));
     if (grid.x == 0 || c->dry) return RTM_OK;
     a.ring_period = ring_period(c, nring * ns, (int)grid.x); a.fd_period = make_fastdiv(a.ring_period);
     ++c->nlaunch;
     a.lookahead_p0 = 1;
     a.tma_s0_p0 = buf < 0 ? a.tma_s0 - c->S : 0;
     fwd_step_kernel<RP, LS, RTM_NR_F><<<grid, kThreads, smem, st>>>(buf < 0 ? k.tmap_store : k.tmap_f[buf],
-                                                                 buf < 0 ? k.tmap_store : k.tmap_f[(buf + 2) % 3], G, a);
+                                                                 buf < 0 ? k.tmap_store : k.tmap_f[p0buf], G, a);
     return RTM_OK;
 }
 // frame: only the tiles that the two-step kernel does not cover
@@ -826,10 +912,36 @@ template <int RP, bool LS> static int launch_bwd2(rtm_ctx* c, rtm_ctx::TileClass
                                                                               c->tmap_acc, c->G, a);
     return RTM_OK;
 }
+// The same pair of steps by the z-streaming kernel: one CTA per column segment and shot.
+static int launch_stream_bwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, int s0, int r0, const Bwd2Args& a2, bool border)
+{
+    using T = Strm<4>;
+    if (!k.smem_s2) {
+        CK(cudaFuncSetAttribute(stream2_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::bytes(true)));
+        CK(cudaFuncSetAttribute(stream2_kernel<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        k.smem_s2 = true;
+    }
+    StrmArgs a{};
+    a.Ak[0] = a2.Sk; a.Ak[1] = a2.Rk; a.Bk[0] = a2.Skm; a.Bk[1] = a2.Rkm;
+    a.src = a2.src; a.wavelet_a = a2.wavelet_k; a.wavelet_b = a2.wavelet_km; a.k = a2.k; a.nshots = ns;
+    a.segs = border ? k.d_segs_ib : k.d_segs_ii; a.nseg = border ? k.n_segs_ib : k.n_segs_ii;
+    a.fd_nseg = make_fastdiv(a.nseg);
+    a.seis = a2.seis; a.gather = nullptr;
+    a.sumS = a2.sumS; a.sumR = a2.sumR; a.rel1 = a2.rel1; a.rel2 = a2.rel2;
+    if (c->dry || a.nseg == 0) return RTM_OK;
+    StrmMaps tm;
+    tm.cur[0] = k.tmap_s_cur[s1]; tm.cur[1] = k.tmap_s_cur[r1];
+    tm.prev[0] = k.tmap_s_prev[s0]; tm.prev[1] = k.tmap_s_prev[r0];
+    for (int i = 0; i < 4; ++i) tm.acc[i] = c->tmap_s_acc[i];
+    ++c->nlaunch;
+    stream2_kernel<4, true><<<(unsigned)(a.nseg * ns), T::kThreadsS, T::bytes(true), st>>>(tm, c->G, a);
+    return RTM_OK;
+}
 static int dispatch_bwd2_class(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, int s0, int r0, const Bwd2Args& a, bool border)
 {
     const bool ls = c->G.iLSTE == 0;
     if (k.n_b2 == 0) return RTM_OK;
+    if (k.d_segs_ii || k.d_segs_ib) return launch_stream_bwd(c, k, st, ns, s1, r1, s0, r0, a, border);
     switch (k.RP) {
     case 4: return ls ? launch_bwd2<4, true>(c, k, st, ns, s1, r1, s0, r0, a, border) : launch_bwd2<4, false>(c, k, st, ns, s1, r1, s0, r0, a, border);
     case 8: return ls ? launch_bwd2<8, true>(c, k, st, ns, s1, r1, s0, r0, a, border) : launch_bwd2<8, false>(c, k, st, ns, s1, r1, s0, r0, a, border);
@@ -861,19 +973,44 @@ template <class Launch> static int fork_join(rtm_ctx* c, Launch launch, cudaStre
     return RTM_OK;
 }
 // buf: index of the field buffer holding slot k-1, or -1 for the store-all slab
-static int dispatch_fwd(rtm_ctx* c, int ns, int buf, FwdArgs a)
+static int dispatch_fwd(rtm_ctx* c, int ns, int buf, int p0buf, FwdArgs a, bool frame = false, cudaStream_t serial = nullptr)
 {
     const bool ls = c->G.iLSTE == 0;
     return fork_join(c, [&](rtm_ctx::TileClass& k, cudaStream_t st, bool first) -> int {
         a.do_ring = first ? 1 : 0;
         switch (k.RP) {
-        case 4:  return ls ? launch_fwd<4, true>(c, k, st, ns, buf, a) : launch_fwd<4, false>(c, k, st, ns, buf, a);
-        case 8:  return ls ? launch_fwd<8, true>(c, k, st, ns, buf, a) : launch_fwd<8, false>(c, k, st, ns, buf, a);
-        case 12: return ls ? launch_fwd<12, true>(c, k, st, ns, buf, a) : launch_fwd<12, false>(c, k, st, ns, buf, a);
-        case 16: return ls ? launch_fwd<16, true>(c, k, st, ns, buf, a) : launch_fwd<16, false>(c, k, st, ns, buf, a);
+        case 4:  return ls ? launch_fwd<4, true>(c, k, st, ns, buf, p0buf, frame, a) : launch_fwd<4, false>(c, k, st, ns, buf, p0buf, frame, a);
+        case 8:  return ls ? launch_fwd<8, true>(c, k, st, ns, buf, p0buf, frame, a) : launch_fwd<8, false>(c, k, st, ns, buf, p0buf, frame, a);
+        case 12: return ls ? launch_fwd<12, true>(c, k, st, ns, buf, p0buf, frame, a) : launch_fwd<12, false>(c, k, st, ns, buf, p0buf, frame, a);
+        case 16: return ls ? launch_fwd<16, true>(c, k, st, ns, buf, p0buf, frame, a) : launch_fwd<16, false>(c, k, st, ns, buf, p0buf, frame, a);
         }
         return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", k.RP);
-    });
+    }, serial);
+}
+// Two forward steps (slots k, k+1) of the inner segments by the z-streaming kernel.
+static int launch_stream_fwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int b1, int b0, int bk, int bk1, const FwdArgs& f,
+                             float wavelet_k1, bool border)
+{
+    using T = Strm<4>;
+    if (!k.smem_s2f) {
+        CK(cudaFuncSetAttribute(stream2_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::bytes(false)));
+        CK(cudaFuncSetAttribute(stream2_kernel<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        k.smem_s2f = true;
+    }
+    StrmArgs a{};
+    a.Ak[0] = c->field[bk]; a.Bk[0] = c->field[bk1];
+    a.src = f.src; a.wavelet_a = f.wavelet; a.wavelet_b = wavelet_k1; a.k = f.k; a.nshots = ns;
+    a.segs = border ? k.d_segs_fib : k.d_segs_fii; a.nseg = border ? k.n_segs_fib : k.n_segs_fii;
+    a.fd_nseg = make_fastdiv(a.nseg);
+    a.gather = f.gather;
+    if (c->dry || a.nseg == 0) return RTM_OK;
+    StrmMaps tm;
+    tm.cur[0] = k.tmap_s_cur[b1]; tm.prev[0] = k.tmap_s_prev[b0];
+    tm.cur[1] = tm.cur[0]; tm.prev[1] = tm.prev[0];
+    for (int i = 0; i < 4; ++i) tm.acc[i] = c->tmap_s_acc[i];
+    ++c->nlaunch;
+    stream2_kernel<4, false><<<(unsigned)(a.nseg * ns), T::kThreadsS, T::bytes(false), st>>>(tm, c->G, a);
+    return RTM_OK;
 }
 template <bool STORE> static int dispatch_bwd_t(rtm_ctx* c, int ns, int s1, int r1, int s0, int r0, BwdArgs a, bool frame, cudaStream_t serial)
 {
@@ -957,11 +1094,16 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
     CK(cudaMemcpyAsync(c->d_src, src.data(), sizeof(int2) * ns, cudaMemcpyHostToDevice, c->stream));
     // time slot k lives in one of three rotating buffers, or -- store-all mode -- in its own slab
     const size_t slab = (size_t)c->S * G.shot_stride;
-    auto slot = [&](int k) -> float* { return use_store ? c->store + (size_t)k * slab : c->field[k % 3]; };
+    // forward pass in pairs (inner segments two slots per pass, ring + frame tiles singly): 4 rotating buffers
+    bool pairs = false;
+    if (!use_store && nsnap == 0 && c->fuse2_fwd != 0 && c->classes.size() == 1 && (c->classes[0].d_segs_fii || c->classes[0].d_segs_fib))
+        pairs = c->fuse2_fwd == 1 || c->fuse2_forced || (long)c->classes[0].n_fii_tiles * 2 * ns >= rtm_ctx::kFuse2MinCtas;
+    const int NB = pairs ? 4 : 3;
+    auto slot = [&](int k) -> float* { return use_store ? c->store + (size_t)k * slab : c->field[k % NB]; };
     if (use_store) {
         CK(cudaMemsetAsync(slot(0), 0, 2 * slab * 4, c->stream));
     } else {
-        for (int b = 0; b < 3; ++b) CK(cudaMemsetAsync(c->field[b], 0, c->field_floats * 4, c->stream));
+        for (int b = 0; b < NB; ++b) CK(cudaMemsetAsync(c->field[b], 0, c->field_floats * 4, c->stream));
     }
     const float fw1 = (float)(rtm::ricker(0.0f, c->p.f0) / 2.0);  // :803
     init_source_kernel<<<ns, 1, 0, c->stream>>>(slot(1), G, c->d_src, fw1);
@@ -989,28 +1131,73 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
     if (nsnap) { if (int rc = snapshot(0)) return rc; if (int rc = snapshot(1)) return rc; }
     int NT2;
     rtm_derived(c->p.h, c->p.hz, c->p.tao, c->p.tao, c->p.f0, 2, nullptr, &NT2, nullptr, nullptr, nullptr, nullptr, nullptr);
-    auto step = [&](int k) -> int {
-        FwdArgs a;
+    auto wavelet = [&](int k) { return (k < NT2) ? rtm::ricker((k - 1) * c->p.tao, c->p.f0) : 0.0f; };  // :812-813
+    auto args = [&](int k) {
+        FwdArgs a{};
         a.P1 = slot(k - 1); a.P0 = slot(k - 2); a.P2 = slot(k);
         a.src = c->d_src;
-        a.wavelet = (k < NT2) ? rtm::ricker((k - 1) * c->p.tao, c->p.f0) : 0.0f;  // :812-813
+        a.wavelet = wavelet(k);
         a.k = k; a.nshots = ns; a.st = st; a.gather = gather;
         a.tma_s0 = use_store ? (k - 1) * c->S : 0;
-        return dispatch_fwd(c, ns, use_store ? -1 : (k - 1) % 3, a);
+        return a;
+    };
+    auto step = [&](int k) -> int {
+        return dispatch_fwd(c, ns, use_store ? -1 : (k - 1) % NB, (k - 2 + NB) % NB, args(k));
+    };
+    // slots kfirst, kfirst+1, ... NT-1 in pairs (k, k+1); same two-stream pipeline as the backward pass:
+    //   A (main):  inner-inner segments, two-step kernel
+    //   B (aux 2): ring + frame tiles slot k -> inner segments next to the frame -> ring + frame tiles slot k+1
+    auto pair_loop = [&](int kfirst) -> int {
+        cudaStream_t A = c->stream, B = c->aux[2];
+        rtm_ctx::TileClass& kc = c->classes[0];
+        CK(cudaEventRecord(c->fork_ev, A));
+        CK(cudaStreamWaitEvent(B, c->fork_ev, 0));
+        int j = 0;
+        for (int k = kfirst; k + 1 < G.NT; k += 2, ++j) {
+            const int b1 = (k - 1) % NB, b0 = (k - 2) % NB, bk = k % NB, bk1 = (k + 1) % NB;
+            const FwdArgs a0 = args(k), a1 = args(k + 1);
+            if (j > 0) CK(cudaStreamWaitEvent(A, c->ev_ib[(j - 1) & 1], 0));
+            if (int rc = launch_stream_fwd(c, kc, A, ns, b1, b0, bk, bk1, a0, a1.wavelet, false)) return rc;
+            CK(cudaEventRecord(c->ev_ii[j & 1], A));
+            if (int rc = dispatch_fwd(c, ns, b1, b0, a0, true, B)) return rc;
+            if (j > 0) CK(cudaStreamWaitEvent(B, c->ev_ii[(j - 1) & 1], 0));
+            if (int rc = launch_stream_fwd(c, kc, B, ns, b1, b0, bk, bk1, a0, a1.wavelet, true)) return rc;
+            CK(cudaEventRecord(c->ev_ib[j & 1], B));
+            if (int rc = dispatch_fwd(c, ns, bk, b1, a1, true, B)) return rc;
+        }
+        CK(cudaEventRecord(c->join_ev[2], B));
+        CK(cudaStreamWaitEvent(A, c->join_ev[2], 0));
+        return RTM_OK;
+    };
+    auto steps_from = [&](int k) -> int {   // slots k .. NT-1
+        if (pairs) {
+            if ((G.NT - k) % 2) { if (int rc = step(k)) return rc; ++k; }
+            if (k + 1 < G.NT) return pair_loop(k);
+            return RTM_OK;
+        }
+        for (; k < G.NT; ++k) if (int rc = step(k)) return rc;
+        return RTM_OK;
     };
     const long nl0 = c->nlaunch;
     CK(cudaEventRecord(c->ev0, c->stream));
     if (c->use_graphs && nsnap == 0 && G.NT > 3) {
         if (int rc = step(2)) return rc;  // (also sets the kernel's shared-memory attribute before capture)
-        const long long key = 1 + 2 * (st.up ? 1 : 0) + 4 * (gather ? 1 : 0) + 8 * (use_store ? 1 : 0) + 16LL * ns;
-        if (int rc = run_as_graph(c, key, [&]() -> int {
-                for (int k = 3; k < G.NT; ++k) if (int r = step(k)) return r;
-                return RTM_OK;
-            })) return rc;
+        if (pairs) {   // kernel attributes of the pair path cannot be set during capture: a dry pass
+            c->dry = true;
+            const int rc = pair_loop(G.NT - 2);
+            c->dry = false;
+            if (rc) return rc;
+        }
+        const long long key = 1 + 2 * (st.up ? 1 : 0) + 4 * (gather ? 1 : 0) + 8 * (use_store ? 1 : 0) + 16LL * ns + (pairs ? (1LL << 40) : 0);
+        if (int rc = run_as_graph(c, key, [&]() -> int { return steps_from(3); })) return rc;
     } else {
-        for (int k = 2; k < G.NT; ++k) {
-            if (int rc = step(k)) return rc;
-            if (nsnap) if (int rc = snapshot(k)) return rc;
+        if (nsnap == 0) {
+            if (int rc = steps_from(2)) return rc;
+        } else {
+            for (int k = 2; k < G.NT; ++k) {
+                if (int rc = step(k)) return rc;
+                if (int rc = snapshot(k)) return rc;
+            }
         }
     }
     CK(cudaEventRecord(c->ev1, c->stream));
