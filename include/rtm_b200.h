@@ -64,7 +64,14 @@ typedef struct {
  * error (~1e-4 relative).  rtm_store_all_active() tells which was chosen. */
 #define RTM_FLAG_STORE_ALL 1
 
-/* Replaces cudaSetDevice + the 22 cudaMalloc calls (kernel.cu:527, 758-779). */
+/* Replaces cudaSetDevice + the 22 cudaMalloc calls (kernel.cu:527, 758-779).
+ * Constraints the reference does not have (RTM_ERR_ARG with a message otherwise):
+ *   1 <= nfdmax <= min(N2, 16)       the boundary strips lie inside the ring (kernel.cu:23-43)
+ *   1 <= N2 <= 64                    and the shared-memory staging of one ring tile must fit the
+ *                                    device's opt-in limit (227 KB): about N2 <= 55 with operators of
+ *                                    length 16, N2 <= 60 with length 4
+ *   mod_NZ, mod_NX > 2*N2 + 4        the ring tiles assume an interior between the two bands
+ *   adaptive operator: at most 65535 velocity bins (16-bit per-cell bin array; use a larger dv) */
 int  rtm_create(int device, const rtm_params *params, rtm_ctx **out);
 void rtm_destroy(rtm_ctx *ctx); /* kernel.cu:1241-1256 */
 
@@ -119,7 +126,10 @@ int rtm_stack_reset(rtm_ctx *ctx);
 int rtm_stack_get(rtm_ctx *ctx, float *up_sum, float *down_sum, int *nshots);
 int rtm_stack_device(rtm_ctx *ctx, void **dev_ptr, size_t *nfloats, int *nshots);
 int rtm_stack_reduce(rtm_ctx **ctxs, int nctx, float *up_sum, float *down_sum, int *nshots);
-/* "nccl", "p2p" (NVLink peer copies + device add, used when libnccl cannot be loaded) or "none" */
+/* rtm_stack_reduce sums into a scratch buffer on the first context's GPU: the contexts' own stacks
+ * are left as they are, so it can be called again (e.g. after more shots).  If libnccl cannot be
+ * loaded, or ncclCommInitAll / ncclReduce fail, it falls back to NVLink peer copies + a device add.
+ * Backend of the last call: "nccl", "p2p" or "none". */
 const char *rtm_stack_reduce_backend(void);
 /* sum/nrec, optional up/down normalisation (kernel.cu:1042-1059); in/out [mod_NX][mod_NZ] */
 int rtm_stack_finalize(const float *up_sum, const float *down_sum, int nrec, int iNorm,
@@ -137,6 +147,13 @@ typedef struct {
 int rtm_get_stats(rtm_ctx *ctx, rtm_stats *out);
 int rtm_reset_stats(rtm_ctx *ctx);
 int rtm_device_count(void);
+/* Device memory a context will allocate, by the engine's own formulas: `fixed` bytes + max_batch x
+ * `per_shot` bytes (wavefields, accumulators, boundary strips of a migration, traces, images).
+ * NT1 = samples per raw trace for rtm_migrate_raw (0: unused).  Uses mod_NZ, mod_NX, N2, nfdmax, NT, n
+ * of *p.  rtm_device_free_bytes reports what cudaMemGetInfo sees on `device`.  The drop-in driver
+ * sizes its shot batches with the two (the reference has no counterpart: one shot at a time). */
+int rtm_memory_estimate(const rtm_params *p, int NT1, size_t *fixed, size_t *per_shot);
+int rtm_device_free_bytes(int device, size_t *free_bytes);
 int rtm_store_all_active(rtm_ctx *ctx); /* 1 if RTM_FLAG_STORE_ALL was requested and fits */
 
 /* ------------------------------------------------------------------ host-side pieces

@@ -44,12 +44,12 @@ class Stats(C.Structure):
                 ("algorithmic_bytes", C.c_double), ("kernel_launches", C.c_long), ("shots", C.c_long)]
 
 
-# every symbol include/rtm_b200.h declares (checked by tests/test_abi.py)
+# every symbol include/rtm_b200.h declares (checked by tests/test_host.py::test_abi_exports_every_declared_symbol)
 ABI_SYMBOLS = [
     "rtm_last_error", "rtm_version", "rtm_create", "rtm_destroy", "rtm_set_model", "rtm_set_operator",
     "rtm_forward", "rtm_migrate", "rtm_migrate_raw", "rtm_resample_device", "rtm_upload_gathers", "rtm_migrate_resident", "rtm_stack_reset",
     "rtm_stack_get", "rtm_stack_device", "rtm_stack_reduce", "rtm_stack_reduce_backend", "rtm_stack_finalize", "rtm_get_stats",
-    "rtm_reset_stats", "rtm_device_count", "rtm_store_all_active", "rtm_ricker", "rtm_source_row", "rtm_derived",
+    "rtm_reset_stats", "rtm_device_count", "rtm_memory_estimate", "rtm_device_free_bytes", "rtm_store_all_active", "rtm_ricker", "rtm_source_row", "rtm_derived",
     "rtm_pad_velocity", "rtm_velocity_bins", "rtm_taylor_operator", "rtm_ls_operator",
     "rtm_ls_coefficients", "rtm_resample", "rtm_segy_decode", "rtm_segy_encode", "rtm_segy_info",
     "rtm_segy_read", "rtm_segy_write_image", "rtm_depth_to_time", "rtm_time_to_depth", "rtm_phase_rotate",
@@ -90,6 +90,8 @@ def lib():
     L.rtm_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.rtm_reset_stats.argtypes = [C.c_void_p]
     L.rtm_store_all_active.argtypes = [C.c_void_p]
+    L.rtm_memory_estimate.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.rtm_device_free_bytes.argtypes = [C.c_int, C.POINTER(C.c_size_t)]
     L.rtm_ricker.restype = C.c_float
     L.rtm_ricker.argtypes = [C.c_float, C.c_float]
     L.rtm_source_row.argtypes = [C.c_float, C.c_float, C.c_int]

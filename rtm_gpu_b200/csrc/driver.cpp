@@ -13,6 +13,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -62,7 +64,17 @@ void run_worker(const Job& job, Worker& w)
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     const auto tc0 = now();
-    if (rtm_create(w.device, &p, &w.ctx)) return fail(RTM_ERR_CUDA, rtm_last_error());
+    for (;;) {   // the estimate is made for GPU 0: another GPU may have less free memory
+        size_t fixed = 0, per_shot = 0, free_b = 0;
+        if (p.max_batch > 1 && rtm_memory_estimate(&p, c.NT1, &fixed, &per_shot) == RTM_OK &&
+            rtm_device_free_bytes(w.device, &free_b) == RTM_OK && fixed + (size_t)p.max_batch * per_shot > free_b) {
+            p.max_batch = std::max(1, p.max_batch / 2);
+            continue;
+        }
+        if (rtm_create(w.device, &p, &w.ctx) == RTM_OK) break;
+        if (p.max_batch == 1) return fail(RTM_ERR_CUDA, rtm_last_error());
+        p.max_batch = std::max(1, p.max_batch / 2);
+    }
     if (rtm_set_model(w.ctx, job.v.data(), job.bins.vmin, job.bins.vmax, c.dv)) return fail(RTM_ERR_CUDA, rtm_last_error());
     if (rtm_set_operator(w.ctx, c.iLSTE == 0 ? job.Index.data() : nullptr, job.bins.nvel, job.c.data(), (int)job.c.size()))
         return fail(RTM_ERR_ARG, rtm_last_error());
@@ -116,9 +128,23 @@ void run_worker(const Job& job, Worker& w)
 
 }  // namespace
 
+static int run_driver(const char* run_file, int ngpu, int batch, int verbose);
+
+// No C++ exception crosses the C ABI (std::length_error / bad_alloc from absurd sizes in the input files).
 extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int verbose)
 {
     if (!run_file) return rtm_fail(RTM_ERR_ARG, "rtm_run_driver: null run file");
+    try {
+        return run_driver(run_file, ngpu, batch, verbose);
+    } catch (const std::bad_alloc&) {
+        return rtm_fail(RTM_ERR_ARG, "rtm_run_driver: out of host memory (check the sizes in the parameter files)");
+    } catch (const std::exception& e) {
+        return rtm_fail(RTM_ERR_ARG, "rtm_run_driver: %s", e.what());
+    }
+}
+
+static int run_driver(const char* run_file, int ngpu, int batch, int verbose)
+{
     Job job;
     std::string err;
     rtm::RunConfig& c = job.cfg;
@@ -128,11 +154,17 @@ extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int ver
     verbose &= 1;
     if (!rtm::parse_run_file(run_file, c, err) || !rtm::parse_parameter_file(c.OutPara.c_str(), c, err) ||
         !rtm::parse_depth_file(c.OutNameDPR.c_str(), c, err))
-        return rtm_fail(RTM_ERR_IO, "%s", err.c_str());
+        return rtm_fail(err.find("positive") != std::string::npos ? RTM_ERR_ARG : RTM_ERR_IO, "%s", err.c_str());
+    if (!(c.hz > 0) || !(c.tao > 0) || !(c.f0 > 0) || !(c.dv > 0) || c.N2 < 1 || c.nfdmax < 1)
+        return rtm_fail(RTM_ERR_ARG, "%s: hz, tao, f0, dv, N2 and nfdmax must be positive (hz=%g tao=%g f0=%g dv=%g N2=%d nfdmax=%d)",
+                        run_file, c.hz, c.tao, c.f0, c.dv, c.N2, c.nfdmax);
+    if (c.NX_BG < 0 || c.NZ_BG < 0 || c.NX_ED > c.mod_NX || c.NZ_ED > c.mod_NZ || c.NX_ED <= c.NX_BG || c.NZ_ED <= c.NZ_BG)
+        return rtm_fail(RTM_ERR_ARG, "%s: output window [%d,%d) x [%d,%d) does not lie inside the %d x %d model (the reference would "
+                        "write whatever its image array holds outside the model)", run_file, c.NX_BG, c.NX_ED, c.NZ_BG, c.NZ_ED, c.mod_NX, c.mod_NZ);
     job.g = rtm::derive_geometry(c);
     const rtm::Geometry& g = job.g;
+    if (g.NT < 3) return rtm_fail(RTM_ERR_ARG, "NT = %d time slots (NT1=%d tao1=%g tao=%g): nothing to propagate", g.NT, c.NT1, c.tao1, c.tao);
     if (verbose) rtm::echo_config(c, g, stdout);
-    if (c.nrec < 1) return rtm_fail(RTM_ERR_ARG, "nrec = %d", c.nrec);
 
     std::vector<float> vraw;
     auto ends_with = [](const std::string& a, const char* suf) {
@@ -180,9 +212,14 @@ extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int ver
         // Gcell-updates/s, profiles/README.md)
         const double cells = (double)g.NZ * g.NX;
         batch = (int)std::min(32.0, std::max(1.0, std::ceil(57.0e6 / cells)));
-        // ... bounded by HBM: 9 fields + strips + traces per shot, keep within ~100 GB
-        const double per_shot = 9.0 * cells * 4 + 8.0 * g.NT * c.nfdmax * (c.mod_NX + c.mod_NZ) + 8.0 * g.NT * c.n;
-        batch = (int)std::max(1.0, std::min((double)batch, std::floor(100.0e9 / per_shot)));
+        // ... bounded by the HBM that is free on the first GPU, with the engine's own allocation formula
+        rtm_params p{};
+        p.mod_NZ = c.mod_NZ; p.mod_NX = c.mod_NX; p.N2 = c.N2; p.nfdmax = c.nfdmax; p.NT = g.NT; p.n = c.n; p.max_batch = 1;
+        size_t fixed = 0, per_shot = 0, free_b = 0;
+        if (rtm_memory_estimate(&p, c.NT1, &fixed, &per_shot) == RTM_OK && rtm_device_free_bytes(0, &free_b) == RTM_OK && per_shot > 0) {
+            const double room = 0.92 * (double)free_b - (double)fixed;
+            batch = (int)std::max(1.0, std::min((double)batch, std::floor(room / (double)per_shot)));
+        }
     }
     job.batch = batch;
 
@@ -268,7 +305,12 @@ extern "C" int rtm_run_driver(const char* run_file, int ngpu, int batch, int ver
     // the reference requires is present in the working directory
     if (std::FILE* t = std::fopen("SGY_Model.sgy", "rb")) {
         std::fclose(t);
-        const int ntr = c.NX_ED - c.NX_BG, ns = c.NZ_ED - c.NZ_BG;
+        // The reference re-reads RVSP_Migration_Real_new2.dat as (window width) x mod_NZ samples and passes
+        // ns = mod_NZ (:1181-1209), whatever the depth window was.  Same stream here; when the window is
+        // shallower than the model the reference reads past the end of the file into uninitialised memory,
+        // so that case keeps the window's own depth extent (deviations).
+        const int ntr = c.NX_ED - c.NX_BG;
+        const int ns = win.size() >= (size_t)ntr * c.mod_NZ ? c.mod_NZ : c.NZ_ED - c.NZ_BG;
         std::vector<float> SX(ntr), SY(ntr), DSR(ntr);
         for (int i = 0; i < ntr; ++i) { SX[i] = 1.0 * i * 10; SY[i] = -1.0 * i * 10; DSR[i] = 1000 - i; }
         const std::string name = c.Result + "RVSP_migration_Real.sgy";

@@ -77,6 +77,16 @@ bool parse_parameter_file(const char* path, RunConfig& c, std::string& err)
         err = std::string("parameter file ") + path + " needs 12 values";
         return false;
     }
+    // every later size derives from these: reject what the reference would silently turn into a crash
+    auto bad = [&](const char* name, double v) { err = std::string("parameter file ") + path + ": " + name + " = " + std::to_string(v) + " is not positive"; return false; };
+    if (!(c.h > 0)) return bad("h", c.h);
+    if (!(c.tao1 > 0)) return bad("tao1", c.tao1);
+    if (c.mod_NZ < 1) return bad("mod_NZ", c.mod_NZ);
+    if (c.mod_NX < 1) return bad("mod_NX", c.mod_NX);
+    if (c.NT1 < 1) return bad("NT1", c.NT1);
+    if (c.n < 1) return bad("n", c.n);
+    if (c.ds < 1) return bad("ds", c.ds);
+    if (c.nrec < 1) return bad("nrec", c.nrec);
     return true;
 }
 
@@ -84,6 +94,7 @@ bool parse_depth_file(const char* path, RunConfig& c, std::string& err)
 {
     std::ifstream in(path);
     if (!in) { err = std::string("cannot open receiver depth file ") + path; return false; }
+    if (c.nrec < 1 || c.nrec > (1 << 24)) { err = "nrec = " + std::to_string(c.nrec) + " (Parameter.txt) must be a positive count"; return false; }
     c.INRE.assign(c.nrec, 0.0f);
     for (int i = 0; i < c.nrec; ++i)
         if (!(in >> c.INRE[i])) { err = "receiver depth file has fewer than nrec values"; return false; }

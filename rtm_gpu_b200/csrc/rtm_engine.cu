@@ -435,6 +435,49 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     delete c;
 }
 
+// Row layout of a field buffer: the first interior column sits on a 128-byte boundary (padL), rows
+// are a multiple of 32 floats long.
+static void field_layout(const rtm_params& p, int* padL, int* pitch)
+{
+    const int RP = (p.nfdmax + 3) / 4 * 4, NX = p.mod_NX + 2 * p.N2;
+    *padL = (32 - p.N2 % 32) % 32;
+    if (*padL + p.N2 < RP) *padL += 32;  // the TMA box may start left of the first interior column
+    *pitch = (*padL + NX + 4 + 31) / 32 * 32;
+}
+
+// Device memory a context needs, by the formulas rtm_create / the first migrate / rtm_migrate_raw allocate
+// with: `fixed` (model-sized arrays, stack) + max_batch x `per_shot` (fields, accumulators, boundary strips,
+// traces, images).  NT1 = samples per raw trace (rtm_migrate_raw stages them when NT1 != NT; 0: not used).
+extern "C" int rtm_memory_estimate(const rtm_params* p, int NT1, size_t* fixed, size_t* per_shot)
+{
+    if (!p || p->mod_NZ < 1 || p->mod_NX < 1 || p->N2 < 1 || p->nfdmax < 1 || p->NT < 1 || p->n < 1)
+        return rtm_fail(RTM_ERR_ARG, "rtm_memory_estimate: bad parameters");
+    int padL = 0, pitch = 0;
+    field_layout(*p, &padL, &pitch);
+    const size_t NZ = (size_t)p->mod_NZ + 2 * p->N2, stride = NZ * (size_t)pitch, ncell = (size_t)p->mod_NX * p->mod_NZ;
+    const size_t ntiles = ((size_t)p->mod_NX / kTX + 1) * ((size_t)p->mod_NZ / (kWarps * RTM_NR_B) + 1);
+    if (fixed)
+        *fixed = 2 * (stride + 64) * 4 + (stride + 64) * 2          // velocity, velocity factor, bins
+                 + 2 * ncell * 4                                     // stack
+                 + (rtm_ctx::kFields + 4) * 64 * 4 + 6 * ntiles * 8  // slack of the field buffers, tile lists
+                 + (256ull << 20);                                   // CUDA context, graphs, allocator granularity
+    if (per_shot)
+        *per_shot = (rtm_ctx::kFields + 4) * stride * 4              // wavefields + imaging accumulators
+                    + 2 * (size_t)p->NT * p->nfdmax * ((size_t)p->mod_NX + p->mod_NZ) * 4   // boundary strips (4 arrays)
+                    + 2 * (size_t)p->NT * p->n * 4                   // traces time-major + staging
+                    + ((NT1 > 0 && NT1 != p->NT) ? (size_t)NT1 * p->n * 4 : 0)
+                    + 2 * ncell * 4 + 64;                            // per-shot images
+    return RTM_OK;
+}
+extern "C" int rtm_device_free_bytes(int device, size_t* free_bytes)
+{
+    if (!free_bytes) return rtm_fail(RTM_ERR_ARG, "rtm_device_free_bytes: null argument");
+    size_t total = 0;
+    CK(cudaSetDevice(device));
+    CK(cudaMemGetInfo(free_bytes, &total));
+    return RTM_OK;
+}
+
 extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
 {
     if (!p || !out) return rtm_fail(RTM_ERR_ARG, "rtm_create: null argument");
@@ -451,12 +494,20 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
         p->s_l + (p->n - 1) * p->ds >= p->mod_NX + 2 * p->N2)
         return rtm_fail(RTM_ERR_ARG, "rtm_create: data positions outside the padded grid");
     if (p->mod_NZ <= 2 * p->N2 + 4 || p->mod_NX <= 2 * p->N2 + 4)
-        return rtm_fail(RTM_ERR_ARG, "rtm_create: model smaller than the absorbing ring");
+        return rtm_fail(RTM_ERR_ARG, "rtm_create: model %d x %d must be larger than 2*N2+4 = %d in both directions (the ring tiles assume an interior between the two bands)",
+                        p->mod_NX, p->mod_NZ, 2 * p->N2 + 4);
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
         return rtm_fail(RTM_ERR_NO_DEVICE, "rtm_create: device %d is sm_%d%d; this engine is built for sm_100a only", device, prop.major, prop.minor);
+    {   // a ring tile stages its halo, previous field and one-way inputs in shared memory: wide rings with long operators do not fit
+        const int RPmax = (p->nfdmax + 3) / 4 * 4;
+        const size_t ring_bytes = (size_t)ring_smem_floats(p->N2, p->nfdmax, RPmax) * 4;
+        if (ring_bytes > (size_t)prop.sharedMemPerBlockOptin)
+            return rtm_fail(RTM_ERR_ARG, "rtm_create: absorbing ring N2=%d with operator length %d needs %zu bytes of shared memory per ring tile, "
+                            "the device grants %zu: use a narrower ring or a shorter operator", p->N2, p->nfdmax, ring_bytes, (size_t)prop.sharedMemPerBlockOptin);
+    }
 
     rtm_ctx* c = new rtm_ctx;
     c->device = device;
@@ -466,9 +517,7 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     Geo& G    = c->G;
     G.mod_NZ = p->mod_NZ; G.mod_NX = p->mod_NX; G.N2 = p->N2;
     G.NZ = p->mod_NZ + 2 * p->N2; G.NX = p->mod_NX + 2 * p->N2;
-    G.padL  = (32 - p->N2 % 32) % 32;
-    if (G.padL + p->N2 < c->RP) G.padL += 32;  // the TMA box may start left of the first interior column
-    G.pitch = (G.padL + G.NX + 4 + 31) / 32 * 32;
+    field_layout(*p, &G.padL, &G.pitch);
     G.shot_stride = (long long)G.NZ * G.pitch;
     G.nfdmax = p->nfdmax; G.mmax = p->nfdmax; G.NT = p->NT; G.iLSTE = p->iLSTE; G.iCompen = p->iCompen;
     G.tao = p->tao; G.h = p->h;
@@ -1563,8 +1612,8 @@ extern "C" int rtm_reset_stats(rtm_ctx* c)
 }
 
 // NCCL reduce of the per-GPU stacks for contexts living in one process: rtm_nccl.cpp.
-// Fallback used when NCCL cannot be loaded: peer copies over NVLink into the first context's
-// GPU and a device-side add, in context order.
+// Fallback used when NCCL cannot be loaded or fails: peer copies over NVLink into the first
+// context's GPU and a device-side add, in context order.
 namespace {
 __global__ void add_into_kernel(float* dst, const float* src, size_t n)
 {
@@ -1573,20 +1622,25 @@ __global__ void add_into_kernel(float* dst, const float* src, size_t n)
 }
 }  // namespace
 
-int rtm_stack_reduce_p2p(rtm_ctx** ctxs, int nctx)
+// out: nfl floats on the first context's GPU; the contexts' own stacks are only read.
+int rtm_stack_reduce_p2p(rtm_ctx** ctxs, int nctx, float* out)
 {
     rtm_ctx* root = ctxs[0];
     const size_t n = 2 * (size_t)root->G.mod_NX * root->G.mod_NZ;
     CK(cudaSetDevice(root->device));
     float* tmp = nullptr;
     CK(cudaMalloc(&tmp, n * 4));
+    auto fail = [&](int rc) { cudaFree(tmp); return rc; };
+    if (cudaMemcpyAsync(out, root->d_stack, n * 4, cudaMemcpyDeviceToDevice, root->stream) != cudaSuccess)
+        return fail(rtm_fail(RTM_ERR_CUDA, "rtm_stack_reduce: device copy failed"));
     for (int i = 1; i < nctx; ++i) {
-        if (2 * (size_t)ctxs[i]->G.mod_NX * ctxs[i]->G.mod_NZ != n) { cudaFree(tmp); return rtm_fail(RTM_ERR_ARG, "rtm_stack_reduce: contexts differ in image size"); }
-        CK(cudaMemcpyPeerAsync(tmp, root->device, ctxs[i]->d_stack, ctxs[i]->device, n * 4, root->stream));
-        add_into_kernel<<<(unsigned)((n + 255) / 256), 256, 0, root->stream>>>(root->d_stack, tmp, n);
+        if (2 * (size_t)ctxs[i]->G.mod_NX * ctxs[i]->G.mod_NZ != n) return fail(rtm_fail(RTM_ERR_ARG, "rtm_stack_reduce: contexts differ in image size"));
+        if (cudaMemcpyPeerAsync(tmp, root->device, ctxs[i]->d_stack, ctxs[i]->device, n * 4, root->stream) != cudaSuccess)
+            return fail(rtm_fail(RTM_ERR_CUDA, "rtm_stack_reduce: peer copy from device %d failed", ctxs[i]->device));
+        add_into_kernel<<<(unsigned)((n + 255) / 256), 256, 0, root->stream>>>(out, tmp, n);
     }
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(root->stream));
-    CK(cudaFree(tmp));
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(root->stream) != cudaSuccess)
+        return fail(rtm_fail(RTM_ERR_CUDA, "rtm_stack_reduce: peer-copy reduce failed"));
+    cudaFree(tmp);
     return RTM_OK;
 }

@@ -1,8 +1,10 @@
 // The one collective of the RTM job: sum of the per-GPU stacked images.
 // Contexts living in one process (one host thread per GPU) are reduced with a single
-// ncclReduce to the first context's GPU.  NCCL is loaded at run time (dlopen) so that the
-// library has no link-time dependency on it; multi-process launchers (torchrun) reduce the
-// buffers exposed by rtm_stack_device() with their own communicator instead.
+// ncclReduce into a scratch buffer on the first context's GPU (the per-context stacks are not
+// modified: the call is repeatable); if NCCL cannot be loaded or fails, peer copies do the same
+// sum.  NCCL is loaded at run time (dlopen) so that the library has no link-time dependency on it;
+// multi-process launchers (torchrun) reduce the buffers exposed by rtm_stack_device() with their
+// own communicator instead.
 #include "../../include/rtm_b200.h"
 
 #include <cuda_runtime.h>
@@ -56,7 +58,7 @@ Nccl* load_nccl(std::string& why)
 }  // namespace
 
 extern "C" int rtm_ctx_device(rtm_ctx* ctx);
-int rtm_stack_reduce_p2p(rtm_ctx** ctxs, int nctx);  // rtm_engine.cu
+int rtm_stack_reduce_p2p(rtm_ctx** ctxs, int nctx, float* out);  // rtm_engine.cu
 static const char* g_backend = "none";
 extern "C" const char* rtm_stack_reduce_backend(void) { return g_backend; }
 
@@ -70,46 +72,62 @@ extern "C" int rtm_stack_reduce(rtm_ctx** ctxs, int nctx, float* up_sum, float* 
     size_t nfl = 0;
     for (int i = 0; i < nctx; ++i) {
         int ns = 0;
+        size_t n_i = 0;
         devs[i] = rtm_ctx_device(ctxs[i]);
-        if (int rc = rtm_stack_device(ctxs[i], &buf[i], &nfl, &ns)) return rc;
+        if (int rc = rtm_stack_device(ctxs[i], &buf[i], &n_i, &ns)) return rc;
+        if (i > 0 && n_i != nfl) return rtm_fail(RTM_ERR_ARG, "rtm_stack_reduce: contexts differ in image size");
+        nfl = n_i;
         total += ns;
     }
+    // The sum lands in a scratch buffer on the first context's GPU: the per-context stacks stay
+    // untouched, so the call may be repeated and a failed NCCL attempt can fall back to peer copies.
+    if (cudaSetDevice(devs[0]) != cudaSuccess) return rtm_fail(RTM_ERR_CUDA, "rtm_stack_reduce: cudaSetDevice(%d) failed", devs[0]);
+    float* red = nullptr;
+    if (cudaMalloc(&red, nfl * 4) != cudaSuccess) return rtm_fail(RTM_ERR_CUDA, "rtm_stack_reduce: scratch allocation of %zu bytes failed", nfl * 4);
     std::string why;
     const char* force = std::getenv("RTM_REDUCE");
-    Nccl* n = (force && std::string(force) == "p2p") ? nullptr : load_nccl(why);
-    if (!n) {
-        // NCCL not loadable (stand-alone executable without the library on its path): the same
-        // sum over NVLink peer copies, gathered and added on the first context's GPU.
-        if (force && std::string(force) == "nccl") return rtm_fail(RTM_ERR_NCCL, "rtm_stack_reduce: %s", why.c_str());
-        int rc = rtm_stack_reduce_p2p(ctxs, nctx);
-        if (rc) return rc;
+    const bool want_p2p = force && std::string(force) == "p2p", want_nccl = force && std::string(force) == "nccl";
+    bool done = false;
+    Nccl* n = want_p2p ? nullptr : load_nccl(why);
+    if (n) {   // one ncclReduce over NVLink (ncclCommInitAll: all contexts live in this process)
+        std::vector<ncclComm_t> comms(nctx, nullptr);
+        ncclResult_t r = n->CommInitAll(comms.data(), nctx, devs.data());
+        if (r) {
+            why = std::string("ncclCommInitAll: ") + n->GetErrorString(r);
+        } else {
+            n->GroupStart();
+            for (int i = 0; i < nctx && !r; ++i) {
+                cudaSetDevice(devs[i]);
+                r = n->Reduce(buf[i], i == 0 ? (void*)red : buf[i] /* ignored on non-root ranks */, nfl, ncclFloat, ncclSum, 0, comms[i], 0);
+            }
+            const ncclResult_t r2 = n->GroupEnd();
+            if (!r) r = r2;
+            for (int i = 0; i < nctx; ++i) {
+                cudaSetDevice(devs[i]);
+                if (cudaStreamSynchronize(0) != cudaSuccess && !r) r = 1;
+            }
+            for (auto c : comms) if (c) n->CommDestroy(c);
+            if (r) why = std::string("ncclReduce: ") + n->GetErrorString(r);
+            else { done = true; g_backend = "nccl"; }
+        }
+    }
+    if (!done) {
+        // NCCL not loadable (stand-alone executable without the library on its path) or failed (no
+        // /dev/shm, version mismatch, two contexts on one device ...): the same sum over NVLink peer
+        // copies, added in context order on the first context's GPU.
+        if (want_nccl) { cudaSetDevice(devs[0]); cudaFree(red); return rtm_fail(RTM_ERR_NCCL, "rtm_stack_reduce: %s", why.c_str()); }
+        cudaGetLastError();   // a failed NCCL attempt may have left a sticky-free error behind
+        if (int rc = rtm_stack_reduce_p2p(ctxs, nctx, red)) { cudaSetDevice(devs[0]); cudaFree(red); return rc; }
         g_backend = "p2p";
-    } else {
-    std::vector<ncclComm_t> comms(nctx);
-    ncclResult_t r = n->CommInitAll(comms.data(), nctx, devs.data());
-    if (r) return rtm_fail(RTM_ERR_NCCL, "ncclCommInitAll: %s", n->GetErrorString(r));
-    // in-place reduce into rank 0's stack (a copy of it is what the caller reads back)
-    n->GroupStart();
-    for (int i = 0; i < nctx && !r; ++i) {
-        cudaSetDevice(devs[i]);
-        r = n->Reduce(buf[i], buf[i], nfl, ncclFloat, ncclSum, 0, comms[i], 0);
-    }
-    ncclResult_t r2 = n->GroupEnd();
-    if (!r) r = r2;
-    for (int i = 0; i < nctx; ++i) {
-        cudaSetDevice(devs[i]);
-        cudaStreamSynchronize(0);
-    }
-    for (auto c : comms) n->CommDestroy(c);
-    if (r) return rtm_fail(RTM_ERR_NCCL, "ncclReduce: %s", n->GetErrorString(r));
-    g_backend = "nccl";
     }
     cudaSetDevice(devs[0]);
     const size_t ncell = nfl / 2;
-    if (up_sum && cudaMemcpy(up_sum, buf[0], ncell * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
-        return rtm_fail(RTM_ERR_CUDA, "rtm_stack_reduce: copy back failed");
-    if (down_sum && cudaMemcpy(down_sum, (float*)buf[0] + ncell, ncell * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
-        return rtm_fail(RTM_ERR_CUDA, "rtm_stack_reduce: copy back failed");
+    int rc = RTM_OK;
+    if (up_sum && cudaMemcpy(up_sum, red, ncell * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = rtm_fail(RTM_ERR_CUDA, "rtm_stack_reduce: copy back failed");
+    if (!rc && down_sum && cudaMemcpy(down_sum, red + ncell, ncell * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = rtm_fail(RTM_ERR_CUDA, "rtm_stack_reduce: copy back failed");
+    cudaFree(red);
     if (nshots) *nshots = total;
-    return RTM_OK;
+    return rc;
 }
