@@ -143,6 +143,12 @@ typedef struct {
     double algorithmic_bytes;/* SURVEY.md 8(d) byte model for the same work            */
     long   kernel_launches;
     long   shots;
+    /* byte model of the schedule that really ran (two-step passes move fewer bytes than 8(d)):
+     * cells advanced two slots per pass 8 B (forward) / 32 B (backward, 16 B without compensation)
+     * per cell-step, cells stepped singly 12 B / 56 B (40 B), absorbing-ring cells 12 B + their
+     * boundary-strip traffic, the velocity factor once per launch (it is shared by the batch) */
+    double executed_bytes_forward, executed_bytes_backward;
+    double pair_cell_steps_forward, pair_cell_steps_backward;   /* cell-steps advanced by two-step passes */
 } rtm_stats;
 int rtm_get_stats(rtm_ctx *ctx, rtm_stats *out);
 int rtm_reset_stats(rtm_ctx *ctx);

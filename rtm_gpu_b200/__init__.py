@@ -41,7 +41,9 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("cell_updates", C.c_double), ("device_seconds", C.c_double),
                 ("forward_seconds", C.c_double), ("backward_seconds", C.c_double),
-                ("algorithmic_bytes", C.c_double), ("kernel_launches", C.c_long), ("shots", C.c_long)]
+                ("algorithmic_bytes", C.c_double), ("kernel_launches", C.c_long), ("shots", C.c_long),
+                ("executed_bytes_forward", C.c_double), ("executed_bytes_backward", C.c_double),
+                ("pair_cell_steps_forward", C.c_double), ("pair_cell_steps_backward", C.c_double)]
 
 
 # every symbol include/rtm_b200.h declares (checked by tests/test_host.py::test_abi_exports_every_declared_symbol)

@@ -1257,6 +1257,19 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
     const double cu = (double)(G.NT - 2) * G.NZ * G.NX * ns;
     c->stats.cell_updates += cu;
     c->stats.algorithmic_bytes += cu * 16.0;
+    {   // bytes of the schedule that ran (include/rtm_b200.h, rtm_stats)
+        const double steps = G.NT - 2, ring = (double)G.NZ * G.NX - (double)G.mod_NZ * G.mod_NX, inner = (double)G.mod_NZ * G.mod_NX;
+        double pair_cells = 0;
+        if (pairs) {
+            const rtm_ctx::TileClass& kc = c->classes[0];
+            pair_cells = ((double)kc.n_f - kc.n_ff) * kTX * (kWarps * RTM_NR_F);   // inner tiles are full tiles
+        }
+        const double pair_steps = pairs ? 2.0 * ((G.NT - 3) / 2) : 0.0;           // slots 3.. in pairs (slot 2 and an odd rest singly)
+        const double strips = st.up ? 2.0 * G.nfdmax * ((double)G.mod_NX + G.mod_NZ) * 4 : 0.0;
+        c->stats.executed_bytes_forward += ns * (pair_steps * pair_cells * 8.0 + (steps * inner - pair_steps * pair_cells) * 12.0 +
+                                                 steps * (ring * 12.0 + strips)) + steps * (double)G.NZ * G.NX * 4.0;
+        c->stats.pair_cell_steps_forward += ns * pair_steps * pair_cells;
+    }
     c->stats.forward_seconds += ms * 1e-3;
     c->stats.kernel_launches += (c->nlaunch - nl0) + 3;
     c->last_forward_ms = ms;
@@ -1436,6 +1449,18 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
     c->stats.cell_updates += steps * ((double)G.NZ * G.NX + (store ? 0.0 : (double)ncell));
     c->stats.algorithmic_bytes += steps * (double)G.NZ * G.NX * ((G.iCompen == 1 ? 60.0 : 44.0) - (store ? 8.0 : 0.0));
     c->stats.backward_seconds += ms * 1e-3;
+    {   // bytes of the schedule that ran (include/rtm_b200.h, rtm_stats)
+        const double nsteps = G.NT - 2, ring = (double)G.NZ * G.NX - (double)ncell, acc = G.iCompen == 1 ? 32.0 : 16.0;
+        double pair_cells = 0;
+        if (pairs)
+            for (auto& kc : c->classes) pair_cells += (double)kc.n_b2 * kTX * Tile2<4>::TZ;
+        const double pair_steps = pairs ? 2.0 * ((G.NT - 2) / 2) : 0.0;
+        const double single = store ? 12.0 + 4.0 + acc : 24.0 + acc;   // store-all: receiver field + stored source slot
+        const double strips = store ? 0.0 : 2.0 * 2.0 * G.nfdmax * ((double)G.mod_NX + G.mod_NZ) * 4;   // read + written into the ring
+        c->stats.executed_bytes_backward += ns * (pair_steps * pair_cells * (16.0 + acc / 2) + (nsteps * (double)ncell - pair_steps * pair_cells) * single +
+                                                  nsteps * (ring * 12.0 + strips)) + nsteps * (double)G.NZ * G.NX * 4.0;
+        c->stats.pair_cell_steps_backward += ns * pair_steps * pair_cells;
+    }
     CK(cudaEventElapsedTime(&ms, c->evA, c->evB));
     c->stats.device_seconds += ms * 1e-3;  // whole batch: init, both loops, image post, stack
     c->stats.kernel_launches += (c->nlaunch - nl0) + 4;
