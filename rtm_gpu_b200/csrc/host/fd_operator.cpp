@@ -4,10 +4,14 @@
 //
 // Replaces the reference's LSMOrCon_rec_2D.cpp (funMandC :22-73, CAL2DFDCOE_LSM
 // :236-287, fgaus/fgausf :139-233, Gauss :74-137, callenfd2d_ls :293-346,
-// calfdlen_ls :347-524, order :526-551).  Re-implemented from the algorithm; the
-// FP64 evaluation order of every sum is kept so that the float32 tables that reach
-// the device are bit-identical to the reference's (checked against goldens produced
-// by the reference's own code, tests/test_host_operator.py).
+// calfdlen_ls :347-524, order :526-551).  The search (bisection over velocity bins,
+// threaded), the quadrature (quad2d: a rewrite of the fgaus state machine) and the
+// table packing are written from the algorithm; solve_scaled_pivot is a
+// TRANSLITERATION of the reference's Gauss routine (same pivoting decisions, same
+// operation order -- any other elimination order changes the last bits of the
+// coefficients).  The FP64 evaluation order of every sum is kept so that the float32
+// tables that reach the device are bit-identical to the reference's (checked against
+// goldens produced by the reference's own code, tests/test_host.py::test_ls_operator_golden).
 #include "rtm_host.h"
 
 #include <algorithm>
@@ -89,7 +93,9 @@ double quad2d(int i, int j, double bmax, double r, bool pair, double hzx)
 }
 
 // Dense solve A x = b: rows scaled by their (signed) largest-magnitude entry, then
-// Gaussian elimination with partial pivoting, then back substitution (Gauss :74-137).
+// Gaussian elimination with partial pivoting, then back substitution.  Transliterated for
+// bit-identity from Gauss (LSMOrCon_rec_2D.cpp:74-137): statement order and pivot tests are the
+// reference's, only the containers differ.
 bool solve_scaled_pivot(std::vector<std::vector<double>>& A, std::vector<double>& b,
                         std::vector<double>& x)
 {

@@ -28,6 +28,9 @@ void regrid_linear(float* out, const float* x, const float* y, int nout, int nin
     }
 }
 
+// Transliterated for bit-identity from kbfft (phase_correction_ricker_decon.cpp:325-387): the
+// reference's twiddle recurrence (its literal 6.283185306, the 0.000001 test) and butterfly order
+// fix every rounding of the rotated traces, so the routine keeps them statement by statement.
 // In-place-style radix-2 FFT on n = 2^k points: (pr,pi) in, (fr,fi) out; pr/pi are used as the
 // twiddle table afterwards.  inverse != 0: conjugate twiddles and 1/n scaling.  polar != 0:
 // pr/pi are finally overwritten with amplitude/(n/2) and phase (kbfft :325-387; the caller of the

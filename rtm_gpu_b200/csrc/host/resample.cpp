@@ -2,9 +2,11 @@
 // kernel.cu:839-845).  The algorithm is the classic 8-point tabulated-sinc interpolation:
 // 513 fractional shifts, each an 8-tap least-squares approximation of the band-limited sinc
 // (band edge 0.066 + 0.265 ln 8 of Nyquist) obtained from a symmetric Toeplitz solve
-// (Levinson recursion).  Re-implemented from that description; the float/double evaluation
-// order is kept so resampled traces are bit-identical to the reference's
-// (tests/test_host.py::test_resample_matches_reference).
+// (Levinson recursion).  toeplitz_solve (= stoepd, :130-163), the table build (= mksinc) and
+// resample_trace (= intt8r) are TRANSLITERATIONS for bit-identity: the float/double evaluation
+// order of the classic routines is kept statement by statement so that resampled traces are
+// bit-identical to the reference's (tests/test_host.py::test_resample_matches_reference); the
+// device version (resample_traces_kernel, rtm_engine.cu) is new.
 #include "rtm_host.h"
 
 #include <cmath>
@@ -20,7 +22,8 @@ constexpr double kPi     = 3.1415926535898;
 double sinc_pi(double x) { return x == 0.0 ? 1.0 : std::sin(kPi * x) / (kPi * x); }
 
 // Solve the symmetric Toeplitz system R f = g (R from its first row r) by Levinson
-// recursion; a[] is the prediction-error filter workspace (stoepd, Resample.cpp:130-163).
+// recursion; a[] is the prediction-error filter workspace.  Transliterated for bit-identity from
+// stoepd (Resample.cpp:130-163).
 void toeplitz_solve(int n, const double* r, const double* g, double* f, double* a)
 {
     if (r[0] == 0.0) return;

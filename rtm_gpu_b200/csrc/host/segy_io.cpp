@@ -25,6 +25,9 @@ inline void put16(unsigned char* p, int v) { const uint16_t u = (uint16_t)(int16
 
 }  // namespace
 
+// ibm_to_float / float_to_ibm: transliterated for bit-identity from ibm_to_float / float_to_ibm of
+// segy.cpp:552-650 (same shift-and-normalise steps, hence the same results for every bit pattern,
+// including the saturation and underflow cases); the header codec and file IO around them are new.
 float ibm_to_float(uint32_t x)
 {
     // base-16 exponent (excess 64), 24-bit fraction -> IEEE single; the fraction is normalised by

@@ -3,9 +3,10 @@
 // One launch per time step.  A launch covers a batch of shots (1-D grid) and, per
 // shot, two kinds of CTA:
 //   * interior tiles (fast path): TMA-staged halo tile of the current wavefield in shared
-//     memory, each thread owns a 4 (x, one float4) by NR (z) register block, z neighbours
-//     from a register column, x neighbours from float4 shared loads, coalesced float4
-//     global loads/stores for the other streams;
+//     memory, each thread walks 4 x-adjacent cells (one float4) down NR rows; x neighbours = the
+//     row segment as float4 shared loads, z neighbours = one float4 shared load per row offset
+//     (a register column over z was measured slower at this occupancy, profiles/README.md),
+//     coalesced float4 global loads/stores for the other streams;
 //   * ring tiles: the N2-wide hybrid absorbing ring.  They evaluate the two-way update on
 //     the ring plus a one-cell halo, apply the one-way solution and the blend, and move
 //     the boundary strips (save in the forward pass, restore in the backward pass).
