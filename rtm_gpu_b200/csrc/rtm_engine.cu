@@ -302,16 +302,17 @@ struct rtm_ctx {
         int *d_tiles_ii = nullptr, *d_tiles_ib = nullptr, *d_tiles_bf = nullptr;
         CUtensorMap tmap_f[kFields], tmap_b[kFields], tmap_b2[kFields], tmap_store;
         size_t smem_f = 0, smem_b = 0, smem_b2 = 0;  // dynamic shared memory already granted to the kernels
-        // z-streaming two-step kernel (rtm_stream.cuh): the ii / ib tiles regrouped into column segments
+        // z-streaming two-step kernel (rtm_stream.cuh): streamed region as column segments, thin frame as strips
+        bool stream_mode = false;
         int4 *d_segs_ii = nullptr, *d_segs_ib = nullptr;
         int  n_segs_ii = 0, n_segs_ib = 0;
-        // ... and of the forward pass (32-row tiles): frame tiles stepped singly, inner tiles as segments
-        int4 *d_segs_fii = nullptr, *d_segs_fib = nullptr;
-        int  n_segs_fii = 0, n_segs_fib = 0, n_fii_tiles = 0;
-        int *d_tiles_ff = nullptr, n_ff = 0;
-        bool smem_s2f = false;
+        long ii_blocks = 0;
+        double stream_cells = 0;                                  // cells per shot advanced two slots per pass
+        ThinTile* d_thin = nullptr;
+        int  n_thin = 0;
         CUtensorMap tmap_s_cur[kFields], tmap_s_prev[kFields];   // boxes (128+4RP) x 8 and (128+2RP) x 8
-        bool smem_s2 = false;
+        CUtensorMap tmap_t_row[kFields], tmap_t_col[kFields];    // thin-frame boxes
+        bool smem_s2 = false, smem_s2f = false, smem_t = false;
     };
     // Pair stepping of the backward pass (two-step kernel on the inner tiles).  Measured on the
     // B200 (profiles/README.md) it pays for the Taylor operator up to radius 4 once a launch holds a
@@ -413,7 +414,7 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
-    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); cudaFree(k.d_segs_ii); cudaFree(k.d_segs_ib); cudaFree(k.d_segs_fii); cudaFree(k.d_segs_fib); cudaFree(k.d_tiles_ff); }
+    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); cudaFree(k.d_segs_ii); cudaFree(k.d_segs_ib); cudaFree(k.d_thin); }
     cudaFree(c->store);
     for (auto& f : c->field) cudaFree(f);
     for (auto& f : c->acc) cudaFree(f);
@@ -651,7 +652,7 @@ static int prepare_ls(rtm_ctx* c)
 static int prepare_classes(rtm_ctx* c)
 {
     const Geo& G = c->G;
-    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); cudaFree(k.d_segs_ii); cudaFree(k.d_segs_ib); cudaFree(k.d_segs_fii); cudaFree(k.d_segs_fib); cudaFree(k.d_tiles_ff); }
+    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); cudaFree(k.d_segs_ii); cudaFree(k.d_segs_ib); cudaFree(k.d_thin); }
     c->classes.clear();
     const int nf = G.ntx * G.ntz_f, nb = G.ntx * G.ntz_b;
     struct Lists { std::vector<int> fwd, bwd, ii, ib, frame; };
@@ -738,65 +739,70 @@ static int prepare_classes(rtm_ctx* c)
         }
         if (int rc = upload(L.ib, &k.d_tiles_ib)) return rc;
         if (int rc = upload(L.frame, &k.d_tiles_bf)) return rc;
-        if (c->stream2 && !ls && k.RP == 4 && k.n_b2 > 0) {
-            // the same tiles as column segments for the z-streaming kernel: runs of vertically adjacent
-            // tiles of one tile column, cut into pieces of at most seg_tiles tiles of equal length (+-1)
-            auto segments = [&](const std::vector<int>& tiles, int tile_rows, int4** d, int* nout) -> int {
-                std::vector<int> v(tiles);
-                std::sort(v.begin(), v.end(), [&](int a, int b) {
-                    const int ax = a % G.ntx, bx = b % G.ntx;
-                    return ax != bx ? ax < bx : a < b;
-                });
-                const int seg_tiles = std::max(1, c->seg_tiles * TZb / tile_rows);   // RTM_SEG_TILES counts 16-row tiles
-                std::vector<int4> segs;
-                for (size_t i = 0; i < v.size();) {
-                    size_t j = i + 1;
-                    while (j < v.size() && v[j] == v[j - 1] + G.ntx) ++j;   // same column, next tile row
-                    const int run = (int)(j - i), pieces = (run + seg_tiles - 1) / seg_tiles;
-                    int t0 = 0;
-                    for (int p = 0; p < pieces; ++p) {
-                        const int len = run / pieces + (p < run % pieces ? 1 : 0);
-                        const int t = v[i + t0];
-                        segs.push_back(make_int4(G.N2 + (t % G.ntx) * kTX, G.N2 + (t / G.ntx) * tile_rows, len * tile_rows / Strm<4>::BR, 0));
-                        t0 += len;
+        if (c->stream2 && c->fuse2 && !ls && k.RP == 4) {
+            // z-streaming form (rtm_stream.cuh).  Regions, for the forward and the backward pass alike:
+            //   ring        the N2 outermost cells                    ring tiles of the single-step kernels
+            //   thin frame  the RP interior cells next to the ring    thin_frame_kernel, stepped singly
+            //   streamed    the rest [C0, xe) x [R0, ze)              stream2_kernel, two slots per pass: 128-wide columns
+            //               (the last may be partial) of 8-row blocks (the last may be partial), cut into segments;
+            //               "ib" = the columns / blocks next to the thin frame (the inner-inner segments' halo
+            //               never reaches a cell stepped singly), "ii" = everything inside them
+            using T = Strm<4>;
+            const int RPc = k.RP, C0 = G.N2 + RPc, R0 = G.N2 + RPc, xe = G.NX - G.N2 - RPc, ze = G.NZ - G.N2 - RPc;
+            const int ncol = (xe - C0 + kTX - 1) / kTX, nblk = (ze - R0 + T::BR - 1) / T::BR;
+            const int nbot = (ze - R0) % T::BR ? 2 : 1;           // bottom "ib" blocks: at least 8 rows
+            const int nright = (xe - C0 - (ncol - 1) * kTX >= 2 * RPc) ? 1 : 2;   // right "ib" columns: at least 2*RP cells
+            if (ncol >= 2 + nright && nblk >= nbot + 3) {
+                const int seg_blocks = std::max(1, c->seg_tiles * TZb / T::BR);
+                std::vector<int4> ii, ib;
+                auto run = [&](std::vector<int4>& out, int col, int b0, int nb) {   // blocks [b0, b0+nb) of a column, in pieces
+                    const int pieces = (nb + seg_blocks - 1) / seg_blocks;
+                    for (int p = 0, b = b0; p < pieces; ++p) {
+                        const int len = nb / pieces + (p < nb % pieces ? 1 : 0);
+                        out.push_back(make_int4(C0 + col * kTX, R0 + b * T::BR, len, 0));
+                        b += len;
                     }
-                    i = j;
+                };
+                const int nmid = nblk - 1 - nbot;                 // blocks between the top and the bottom ib rows
+                for (int col = 0; col < ncol; ++col) {
+                    run(ib, col, 0, 1);
+                    run(ib, col, nblk - nbot, nbot);
+                    run((col == 0 || col >= ncol - nright) ? ib : ii, col, 1, nmid);
                 }
-                *nout = (int)segs.size();
-                if (segs.empty()) return RTM_OK;
-                CK(cudaMalloc(d, sizeof(int4) * segs.size()));
-                CK(cudaMemcpy(*d, segs.data(), sizeof(int4) * segs.size(), cudaMemcpyHostToDevice));
-                return RTM_OK;
-            };
-            if (int rc = segments(L.ii, TZb, &k.d_segs_ii, &k.n_segs_ii)) return rc;
-            if (int rc = segments(L.ib, TZb, &k.d_segs_ib, &k.n_segs_ib)) return rc;
-            {   // forward tiling (32-row tiles): inner = full and, grown by one radius, inside the interior
-                const int TZf = kWarps * RTM_NR_F;
-                std::vector<char> cov(nf, 0);
-                for (int t = 0; t < nf; ++t) {
-                    const int z0 = G.N2 + (t / G.ntx) * TZf, x0 = G.N2 + (t % G.ntx) * kTX;
-                    cov[t] = z0 - c->RP >= G.N2 && x0 - c->RP >= G.N2 && z0 + TZf + c->RP <= G.NZ - G.N2 && x0 + kTX + c->RP <= G.NX - G.N2;
+                auto up4 = [&](const std::vector<int4>& v, int4** d, int* n) -> int {
+                    *n = (int)v.size();
+                    if (v.empty()) return RTM_OK;
+                    CK(cudaMalloc(d, sizeof(int4) * v.size()));
+                    CK(cudaMemcpy(*d, v.data(), sizeof(int4) * v.size(), cudaMemcpyHostToDevice));
+                    return RTM_OK;
+                };
+                if (int rc = up4(ii, &k.d_segs_ii, &k.n_segs_ii)) return rc;
+                if (int rc = up4(ib, &k.d_segs_ib, &k.n_segs_ib)) return rc;
+                k.ii_blocks = 0;
+                for (auto& sgm : ii) k.ii_blocks += sgm.z;
+                k.stream_cells = (double)(xe - C0) * (ze - R0);
+                // thin-frame strips
+                std::vector<ThinTile> thin;
+                for (int x0 = G.N2; x0 < G.NX - G.N2; x0 += kTX) {   // top and bottom: RP rows, all interior columns
+                    thin.push_back(ThinTile{x0, G.N2, G.N2, G.NX - G.N2, G.N2 + RPc, 0, 0, 0});
+                    thin.push_back(ThinTile{x0, ze, G.N2, G.NX - G.N2, ze + RPc, 0, 0, 0});
                 }
-                std::vector<int> fii, fib, ff;
-                for (int t = 0; t < nf; ++t) {
-                    if (!cov[t]) { ff.push_back(t); continue; }
-                    bool all = true;   // (an inner tile never touches the edge of the tiling)
-                    for (int dz = -1; dz <= 1; ++dz)
-                        for (int dx = -1; dx <= 1; ++dx) all = all && cov[t + dz * G.ntx + dx];
-                    (all ? fii : fib).push_back(t);
+                const int xr = xe - ((G.padL + xe) % 4);              // float4-aligned start of the right strip's groups
+                for (int z0 = R0; z0 < ze; z0 += 64) {                // left and right: RP columns, the rows in between
+                    thin.push_back(ThinTile{G.N2, z0, G.N2, C0, std::min(z0 + 64, ze), 1, 0, 0});
+                    thin.push_back(ThinTile{xr, z0, xe, G.NX - G.N2, std::min(z0 + 64, ze), 1, 0, 0});
                 }
-                if (!fii.empty() || !fib.empty()) {
-                    if (int rc = segments(fii, TZf, &k.d_segs_fii, &k.n_segs_fii)) return rc;
-                    if (int rc = segments(fib, TZf, &k.d_segs_fib, &k.n_segs_fib)) return rc;
-                    if (int rc = upload(ff, &k.d_tiles_ff)) return rc;
-                    k.n_ff = (int)ff.size();
-                    k.n_fii_tiles = (int)fii.size();
+                k.n_thin = (int)thin.size();
+                CK(cudaMalloc(&k.d_thin, sizeof(ThinTile) * thin.size()));
+                CK(cudaMemcpy(k.d_thin, thin.data(), sizeof(ThinTile) * thin.size(), cudaMemcpyHostToDevice));
+                for (int i = 0; i < rtm_ctx::kFields; ++i) {
+                    int rc = encode_tmap(c, &k.tmap_s_cur[i], c->field[i], 0, T::BR, 0, T::W1);
+                    if (!rc) rc = encode_tmap(c, &k.tmap_s_prev[i], c->field[i], 0, T::BR, 0, T::WM);
+                    if (!rc) rc = encode_tmap(c, &k.tmap_t_row[i], c->field[i], 0, Thin<4>::ROW_H, 0, Thin<4>::ROW_W);
+                    if (!rc) rc = encode_tmap(c, &k.tmap_t_col[i], c->field[i], 0, Thin<4>::COL_H, 0, Thin<4>::COL_W);
+                    if (rc) return rc;
                 }
-            }
-            for (int i = 0; i < rtm_ctx::kFields; ++i) {
-                int rc = encode_tmap(c, &k.tmap_s_cur[i], c->field[i], 0, Strm<4>::BR, 0, Strm<4>::W1);
-                if (!rc) rc = encode_tmap(c, &k.tmap_s_prev[i], c->field[i], 0, Strm<4>::BR, 0, Strm<4>::WM);
-                if (rc) return rc;
+                k.stream_mode = true;
             }
         }
         for (int i = 0; i < rtm_ctx::kFields; ++i) {
@@ -899,8 +905,8 @@ static int ring_period(const rtm_ctx* c, int ring_ctas, int total)  // see block
     return ring_period_for(c->ring_interleave, ring_ctas, total, c->ring_spread);
 }
 // One launch = the interior tiles of one class (+ the ring tiles when do_ring).
-// buf / p0buf: field buffers of slots k-1 / k-2 (buf < 0: store-all slab); frame: only the tiles the
-// streaming two-step kernel does not cover
+// buf / p0buf: field buffers of slots k-1 / k-2 (buf < 0: store-all slab); frame: only the ring tiles
+// (stream mode: the thin frame has its own kernel, the rest is streamed)
 template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int buf, int p0buf, bool frame, FwdArgs a)
 {
     const Geo& G = c->G;
@@ -911,7 +917,7 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass&
         CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS, RTM_NR_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k.smem_f = smem;
     }
-    a.tiles = frame ? k.d_tiles_ff : k.d_tiles_f; a.ntiles = frame ? k.n_ff : k.n_f; a.fd_ntiles = make_fastdiv(a.ntiles); a.lookahead = c->lookahead_f;
+    a.tiles = frame ? nullptr : k.d_tiles_f; a.ntiles = frame ? 0 : k.n_f; a.fd_ntiles = make_fastdiv(a.ntiles); a.lookahead = c->lookahead_f;   // frame (stream mode): ring tiles only
     dim3 grid((unsigned)((nring + a.ntiles) * ns));
     if (grid.x == 0 || c->dry) return RTM_OK;
     a.ring_period = ring_period(c, nring * ns, (int)grid.x); a.fd_period = make_fastdiv(a.ring_period);
@@ -933,7 +939,9 @@ template <int RP, bool LS, bool STORE> static int launch_bwd(rtm_ctx* c, rtm_ctx
         CK(cudaFuncSetAttribute(bwd_step_kernel<RP, LS, RTM_NR_B, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k.smem_b = smem;
     }
-    a.tiles = frame ? k.d_tiles_bf : k.d_tiles_b; a.ntiles = frame ? k.n_bf : k.n_b; a.fd_ntiles = make_fastdiv(a.ntiles);
+    a.tiles = frame ? k.d_tiles_bf : k.d_tiles_b; a.ntiles = frame ? k.n_bf : k.n_b;
+    if (frame && k.stream_mode) { a.tiles = nullptr; a.ntiles = 0; }   // ring tiles only: thin_frame_kernel + stream2_kernel do the interior
+    a.fd_ntiles = make_fastdiv(a.ntiles);
     dim3 grid((unsigned)((nring + a.ntiles) * ns));
     if (grid.x == 0 || c->dry) return RTM_OK;
     a.ring_period = ring_period(c, nring * ns, (int)grid.x); a.fd_period = make_fastdiv(a.ring_period);
@@ -977,6 +985,7 @@ static int launch_stream_bwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st,
     a.fd_nseg = make_fastdiv(a.nseg);
     a.seis = a2.seis; a.gather = nullptr;
     a.sumS = a2.sumS; a.sumR = a2.sumR; a.rel1 = a2.rel1; a.rel2 = a2.rel2;
+    a.xend = c->G.NX - c->G.N2 - k.RP; a.zend = c->G.NZ - c->G.N2 - k.RP;
     if (c->dry || a.nseg == 0) return RTM_OK;
     StrmMaps tm;
     tm.cur[0] = k.tmap_s_cur[s1]; tm.cur[1] = k.tmap_s_cur[r1];
@@ -986,11 +995,29 @@ static int launch_stream_bwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st,
     stream2_kernel<4, true><<<(unsigned)(a.nseg * ns), T::kThreadsS, T::bytes(true), st>>>(tm, c->G, a);
     return RTM_OK;
 }
+// The thin frame (stream mode), one slot: backward (b1 = current source / receiver buffers, P0/P2 in `a`) or forward.
+template <bool BWD> static int launch_thin(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int cur0, int cur1, ThinArgs a)
+{
+    using T = Thin<4>;
+    if (!k.smem_t) {
+        CK(cudaFuncSetAttribute(thin_frame_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::bytes(true)));
+        CK(cudaFuncSetAttribute(thin_frame_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::bytes(false)));
+        k.smem_t = true;
+    }
+    a.nshots = ns; a.tiles = k.d_thin; a.ntiles = k.n_thin; a.fd_ntiles = make_fastdiv(k.n_thin);
+    if (c->dry || k.n_thin == 0) return RTM_OK;
+    ThinMaps tm;
+    tm.row[0] = k.tmap_t_row[cur0]; tm.col[0] = k.tmap_t_col[cur0];
+    tm.row[1] = k.tmap_t_row[cur1]; tm.col[1] = k.tmap_t_col[cur1];
+    ++c->nlaunch;
+    thin_frame_kernel<4, BWD><<<(unsigned)(k.n_thin * ns), T::kThreadsT, T::bytes(BWD), st>>>(tm, c->G, a);
+    return RTM_OK;
+}
 static int dispatch_bwd2_class(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, int s0, int r0, const Bwd2Args& a, bool border)
 {
     const bool ls = c->G.iLSTE == 0;
-    if (k.n_b2 == 0) return RTM_OK;
-    if (k.d_segs_ii || k.d_segs_ib) return launch_stream_bwd(c, k, st, ns, s1, r1, s0, r0, a, border);
+    if (k.n_b2 == 0 && !k.stream_mode) return RTM_OK;
+    if (k.stream_mode) return launch_stream_bwd(c, k, st, ns, s1, r1, s0, r0, a, border);
     switch (k.RP) {
     case 4: return ls ? launch_bwd2<4, true>(c, k, st, ns, s1, r1, s0, r0, a, border) : launch_bwd2<4, false>(c, k, st, ns, s1, r1, s0, r0, a, border);
     case 8: return ls ? launch_bwd2<8, true>(c, k, st, ns, s1, r1, s0, r0, a, border) : launch_bwd2<8, false>(c, k, st, ns, s1, r1, s0, r0, a, border);
@@ -1049,9 +1076,10 @@ static int launch_stream_fwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st,
     StrmArgs a{};
     a.Ak[0] = c->field[bk]; a.Bk[0] = c->field[bk1];
     a.src = f.src; a.wavelet_a = f.wavelet; a.wavelet_b = wavelet_k1; a.k = f.k; a.nshots = ns;
-    a.segs = border ? k.d_segs_fib : k.d_segs_fii; a.nseg = border ? k.n_segs_fib : k.n_segs_fii;
+    a.segs = border ? k.d_segs_ib : k.d_segs_ii; a.nseg = border ? k.n_segs_ib : k.n_segs_ii;
     a.fd_nseg = make_fastdiv(a.nseg);
     a.gather = f.gather;
+    a.xend = c->G.NX - c->G.N2 - k.RP; a.zend = c->G.NZ - c->G.N2 - k.RP;
     if (c->dry || a.nseg == 0) return RTM_OK;
     StrmMaps tm;
     tm.cur[0] = k.tmap_s_cur[b1]; tm.prev[0] = k.tmap_s_prev[b0];
@@ -1145,8 +1173,8 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
     const size_t slab = (size_t)c->S * G.shot_stride;
     // forward pass in pairs (inner segments two slots per pass, ring + frame tiles singly): 4 rotating buffers
     bool pairs = false;
-    if (!use_store && nsnap == 0 && c->fuse2_fwd != 0 && c->classes.size() == 1 && (c->classes[0].d_segs_fii || c->classes[0].d_segs_fib))
-        pairs = c->fuse2_fwd == 1 || c->fuse2_forced || (long)c->classes[0].n_fii_tiles * 2 * ns >= rtm_ctx::kFuse2MinCtas;
+    if (!use_store && nsnap == 0 && c->fuse2_fwd != 0 && c->classes.size() == 1 && c->classes[0].stream_mode)
+        pairs = c->fuse2_fwd == 1 || c->fuse2_forced || c->classes[0].ii_blocks / 2 * ns >= rtm_ctx::kFuse2MinCtas;
     const int NB = pairs ? 4 : 3;
     auto slot = [&](int k) -> float* { return use_store ? c->store + (size_t)k * slab : c->field[k % NB]; };
     if (use_store) {
@@ -1208,11 +1236,19 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
             if (j > 0) CK(cudaStreamWaitEvent(A, c->ev_ib[(j - 1) & 1], 0));
             if (int rc = launch_stream_fwd(c, kc, A, ns, b1, b0, bk, bk1, a0, a1.wavelet, false)) return rc;
             CK(cudaEventRecord(c->ev_ii[j & 1], A));
+            auto thin = [&](const FwdArgs& f, int cur, int prev, int out) -> int {
+                ThinArgs t{};
+                t.P0[0] = c->field[prev]; t.P2[0] = c->field[out];
+                t.src = f.src; t.wavelet = f.wavelet; t.k = f.k; t.gather = f.gather;
+                return launch_thin<false>(c, kc, B, ns, cur, cur, t);
+            };
             if (int rc = dispatch_fwd(c, ns, b1, b0, a0, true, B)) return rc;
+            if (int rc = thin(a0, b1, b0, bk)) return rc;
             if (j > 0) CK(cudaStreamWaitEvent(B, c->ev_ii[(j - 1) & 1], 0));
             if (int rc = launch_stream_fwd(c, kc, B, ns, b1, b0, bk, bk1, a0, a1.wavelet, true)) return rc;
             CK(cudaEventRecord(c->ev_ib[j & 1], B));
             if (int rc = dispatch_fwd(c, ns, bk, b1, a1, true, B)) return rc;
+            if (int rc = thin(a1, bk, b1, bk1)) return rc;
         }
         CK(cudaEventRecord(c->join_ev[2], B));
         CK(cudaStreamWaitEvent(A, c->join_ev[2], 0));
@@ -1262,7 +1298,7 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
         double pair_cells = 0;
         if (pairs) {
             const rtm_ctx::TileClass& kc = c->classes[0];
-            pair_cells = ((double)kc.n_f - kc.n_ff) * kTX * (kWarps * RTM_NR_F);   // inner tiles are full tiles
+            pair_cells = kc.stream_cells;
         }
         const double pair_steps = pairs ? 2.0 * ((G.NT - 3) / 2) : 0.0;           // slots 3.. in pairs (slot 2 and an odd rest singly)
         const double strips = st.up ? 2.0 * G.nfdmax * ((double)G.mod_NX + G.mod_NZ) * 4 : 0.0;
@@ -1381,12 +1417,25 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
             for (auto& kc : c->classes)
                 if (int rc = dispatch_bwd2_class(c, kc, A, ns, Sb, Rb, Sa, Ra, a2, false)) return rc;
             CK(cudaEventRecord(c->ev_ii[j & 1], A));
+            auto thin = [&](int kk, int s1, int r1, int s0, int r0, int s2, int r2) -> int {   // the thin frame of slot kk (stream mode)
+                for (auto& kc : c->classes) {
+                    if (!kc.stream_mode) continue;
+                    ThinArgs t{};
+                    t.P0[0] = c->field[s0]; t.P0[1] = c->field[r0]; t.P2[0] = c->field[s2]; t.P2[1] = c->field[r2];
+                    t.src = c->d_src; t.wavelet = wavelet(kk); t.k = kk; t.seis = c->d_traces;
+                    t.sumS = c->acc[0]; t.sumR = c->acc[1]; t.rel1 = c->acc[2]; t.rel2 = c->acc[3];
+                    if (int rc = launch_thin<true>(c, kc, B, ns, s1, r1, t)) return rc;
+                }
+                return RTM_OK;
+            };
             if (int rc = dispatch_bwd(c, ns, Sb, Rb, Sa, Ra, args1(k, Sa, Sc, Ra, Rb, Rc), true, B)) return rc;
+            if (int rc = thin(k, Sb, Rb, Sa, Ra, Sc, Rc)) return rc;
             if (j > 0) CK(cudaStreamWaitEvent(B, c->ev_ii[(j - 1) & 1], 0));
             for (auto& kc : c->classes)
                 if (int rc = dispatch_bwd2_class(c, kc, B, ns, Sb, Rb, Sa, Ra, a2, true)) return rc;
             CK(cudaEventRecord(c->ev_ib[j & 1], B));
             if (int rc = dispatch_bwd(c, ns, Sc, Rc, Sb, Rb, args1(k - 1, Sb, Sd, Rb, Rc, Rd), true, B)) return rc;
+            if (int rc = thin(k - 1, Sc, Rc, Sb, Rb, Sd, Rd)) return rc;
             std::swap(Sa, Sc); std::swap(Sb, Sd);
             std::swap(Ra, Rc); std::swap(Rb, Rd);
         }
@@ -1397,7 +1446,7 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
     bool pairs = c->fuse2 && !store;
     if (pairs) {
         long nii = 0, nb2 = 0;
-        for (auto& kc : c->classes) { nii += kc.n_ii; nb2 += kc.n_b2; }
+        for (auto& kc : c->classes) { nii += kc.stream_mode ? kc.ii_blocks / 2 : kc.n_ii; nb2 += kc.stream_mode ? kc.n_segs_ii + kc.n_segs_ib : kc.n_b2; }
         pairs = nb2 > 0 && (c->fuse2_forced || nii * ns >= rtm_ctx::kFuse2MinCtas);
     }
     auto loop = [&](int kfirst) -> int {  // slots kfirst .. 0
@@ -1453,7 +1502,7 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
         const double nsteps = G.NT - 2, ring = (double)G.NZ * G.NX - (double)ncell, acc = G.iCompen == 1 ? 32.0 : 16.0;
         double pair_cells = 0;
         if (pairs)
-            for (auto& kc : c->classes) pair_cells += (double)kc.n_b2 * kTX * Tile2<4>::TZ;
+            for (auto& kc : c->classes) pair_cells += kc.stream_mode ? kc.stream_cells : (double)kc.n_b2 * kTX * Tile2<4>::TZ;
         const double pair_steps = pairs ? 2.0 * ((G.NT - 2) / 2) : 0.0;
         const double single = store ? 12.0 + 4.0 + acc : 24.0 + acc;   // store-all: receiver field + stored source slot
         const double strips = store ? 0.0 : 2.0 * 2.0 * G.nfdmax * ((double)G.mod_NX + G.mod_NZ) * 4;   // read + written into the ring

@@ -62,6 +62,7 @@ struct StrmArgs {
     int    nshots;
     const int4* segs;              // (x0, z0, blocks, -) : out rows [z0, z0 + 8*blocks), columns [x0, x0+128)
     int    nseg;
+    int    xend, zend;             // the streamed region ends here (exclusive): the last column / block may be partial
     FastDiv fd_nseg;
     const float* seis;             // backward: [S][NT][n], row k+1 imposed in phase A, row k in phase B
     float* gather;                 // forward: [S][NT][n] or null
@@ -86,6 +87,18 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity)
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bar_consumers(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+// float4 store of the cells x..x+3 that lie in [xbeg, xend)
+__device__ __forceinline__ void store4c(float* dst, const float (&o)[4], int x, int xbeg, int xend)
+{
+    if (x >= xbeg && x + 3 < xend) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (x + q >= xbeg && x + q < xend) dst[q] = o[q];
+    }
+}
 
 #ifndef RTM_STRM_MINB_B
 #define RTM_STRM_MINB_B 2
@@ -161,6 +174,7 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
     const int xA = x0 - RP + colm;              // global column of the first cell of the phase-A group
     const int xB = x0 + 4 * lane;               // phase B: the segment's own columns
 
+    const int zlast = min(z0 + BR * n, a.zend); // rows of this segment that are stored: [z0, zlast)
     int slot_i = 0, slot_s = 1;                 // ring slots of stages i and i+1
     for (int i = 0; i <= n; ++i) {
         const int s = i + 1;
@@ -179,10 +193,10 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
         const int  zA = z0 - RP + BR * i + rA;
         const bool doA = workA;                                // (mid block n is needed whole: out block n reads RP rows past its end)
         const int  zO = z0 + BR * (i - 1) + warp;
-        const bool doB = warp < BR && i >= 1;
+        const bool doB = warp < BR && i >= 1 && zO < zlast && xB < a.xend;   // (rows / groups past the region's end feed nobody)
         // velocity factor a = ((v*v)*tao2)*h2 of both rows (L2-resident, shared by all shots): in flight during the wait
         float4 avA4 = make_float4(0.f, 0.f, 0.f, 0.f), avB4 = avA4;
-        if (doA) avA4 = __ldg(reinterpret_cast<const float4*>(AV + (size_t)zA * G.pitch + xA));
+        if (doA && zA < G.NZ) avA4 = __ldg(reinterpret_cast<const float4*>(AV + (size_t)zA * G.pitch + xA));
         if (doB) avB4 = __ldg(reinterpret_cast<const float4*>(AV + (size_t)zO * G.pitch + xB));
 
         if (i == 0) mbar_wait_b(full + 0, 0);
@@ -229,12 +243,12 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
                 const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<float4*>(pm) = o4;
                 if (slot_s == 0) *reinterpret_cast<float4*>(pm + 3 * BR * WM) = o4;   // the copy behind slot 2
-                if (ownA && zA >= z0 && zA < z0 + BR * n) {
-                    *reinterpret_cast<float4*>(a.Ak[f] + so + (size_t)zA * G.pitch + xA) = o4;
+                if (ownA && zA >= z0 && zA < zlast && xA < a.xend) {
+                    store4c(a.Ak[f] + so + (size_t)zA * G.pitch + xA, o, xA, 0, a.xend);
                     if (!BWD && a.gather && zA == G.s_z) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const int j = data_index(G, zA, xA + q);
+                            const int j = xA + q < a.xend ? data_index(G, zA, xA + q) : -1;
                             if (j >= 0) a.gather[((size_t)shot * G.NT + a.k) * G.n + j] = o[q];
                         }
                     }
@@ -280,13 +294,13 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
                         }
                     }
                 }
-                *reinterpret_cast<float4*>(a.Bk[f] + o) = make_float4(okm[f][0], okm[f][1], okm[f][2], okm[f][3]);
+                store4c(a.Bk[f] + o, okm[f], xB, 0, a.xend);
             }
             if constexpr (!BWD) {
                 if (a.gather && zO == G.s_z) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const int j = data_index(G, zO, xB + q);
+                        const int j = xB + q < a.xend ? data_index(G, zO, xB + q) : -1;
                         if (j >= 0) a.gather[((size_t)shot * G.NT + a.k + 1) * G.n + j] = okm[0][q];
                     }
                 }
@@ -311,8 +325,8 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
                         r1v[q] = __fmaf_rn(sRv[q], sSv[q], r1v[q]);
                         r2v[q] = __fmaf_rn(okm[0][q], okm[0][q], r2v[q]);
                     }
-                    *reinterpret_cast<float4*>(a.sumS + o) = make_float4(sSv[0], sSv[1], sSv[2], sSv[3]);
-                    *reinterpret_cast<float4*>(a.sumR + o) = make_float4(sRv[0], sRv[1], sRv[2], sRv[3]);
+                    store4c(a.sumS + o, sSv, xB, 0, a.xend);
+                    store4c(a.sumR + o, sRv, xB, 0, a.xend);
                 } else {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -322,8 +336,8 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
                         r2v[q] = __fmaf_rn(okm[0][q], okm[0][q], r2v[q]);
                     }
                 }
-                *reinterpret_cast<float4*>(a.rel1 + o) = make_float4(r1v[0], r1v[1], r1v[2], r1v[3]);
-                *reinterpret_cast<float4*>(a.rel2 + o) = make_float4(r2v[0], r2v[1], r2v[2], r2v[3]);
+                store4c(a.rel1 + o, r1v, xB, 0, a.xend);
+                store4c(a.rel2 + o, r2v, xB, 0, a.xend);
             }
         }
         // this warp is done with iteration i: its slots may be refilled by TMA (generic -> async proxy order)
@@ -332,6 +346,159 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
         if (warp < BR && lane == 0) mbar_arrive(done + (i & 1));
         slot_i = slot_s;
         slot_s = slot_s == 2 ? 0 : slot_s + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// The thin frame: the RP interior cells next to the absorbing ring.  They cannot advance two slots per
+// pass (slot k-1 there needs the ring's one-way solution of slot k), so they -- and only they, not the
+// 128 x 16 tiles around them as in the tile form -- are stepped singly, between the two-step passes of
+// the streamed region.  One CTA of 128 threads per strip tile:
+//   kind 0 (top / bottom strip)   4 rows x 128 columns: warp = row, lane = float4 group
+//   kind 1 (left / right strip)  64 rows x 2 groups   : thread = (row, group); the strip's RP columns need
+//                                 not start on a float4 boundary, so two groups cover them
+// The current field(s) arrive as one TMA box with the stencil halo (two box shapes), everything else is
+// the single-step arithmetic of fwd_step_kernel / bwd_step_kernel on one float4 group.
+// ------------------------------------------------------------------------------------
+struct ThinTile { int x0, z0, xbeg, xend, zend, kind, pad0, pad1; };   // cells [z0,zend) x ([x0,..) clipped to [xbeg,xend))
+struct ThinMaps { CUtensorMap row[2], col[2]; };                      // boxes (128+2RP) x (4+2RP) and (8+2RP) x (64+2RP)
+
+struct ThinArgs {
+    const float* P0[2];    // previous slot (forward: k-2, backward: k+2) of the forward/source field [0] and the receiver field [1]
+    float*       P2[2];    // out (slot k)
+    const int2*  src;
+    float        wavelet;
+    int          k, nshots;
+    const ThinTile* tiles;
+    int          ntiles;
+    FastDiv      fd_ntiles;
+    const float* seis;     // backward: row k+1 is imposed
+    float*       gather;   // forward
+    float *sumS, *sumR, *rel1, *rel2;
+};
+
+template <int RP> struct Thin {
+    static constexpr int kThreadsT = 128;
+    static constexpr int ROW_W = kTX + 2 * RP, ROW_H = 4 + 2 * RP;     // kind 0 box
+    static constexpr int COL_W = 8 + 2 * RP, COL_H = 64 + 2 * RP;      // kind 1 box
+    static constexpr int FLOATS = ROW_W * ROW_H > COL_W * COL_H ? ROW_W * ROW_H : COL_W * COL_H;
+    __host__ __device__ static constexpr int bytes(bool bwd) { return (bwd ? 2 : 1) * ((FLOATS * 4 + 127) / 128 * 128) + 16; }
+};
+
+template <int RP, bool BWD>
+__global__ void __launch_bounds__(Thin<RP>::kThreadsT)
+thin_frame_kernel(const __grid_constant__ ThinMaps tm, const __grid_constant__ Geo G, const ThinArgs a)
+{
+    using T = Thin<RP>;
+    constexpr int NF = BWD ? 2 : 1;
+    constexpr int FSTRIDE = (T::FLOATS * 4 + 127) / 128 * 128 / 4;     // floats between the two field tiles
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float*    tile = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bar  = reinterpret_cast<uint64_t*>(smem_raw + NF * FSTRIDE * 4);
+    const int shot = fast_div(blockIdx.x, a.fd_ntiles);
+    const ThinTile tl = a.tiles[blockIdx.x - shot * a.ntiles];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool colk = tl.kind == 1;
+    const int  SP = colk ? T::COL_W : T::ROW_W;
+
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, NF * (colk ? T::COL_W * T::COL_H : T::ROW_W * T::ROW_H) * 4);
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+            tma_load_3d(tile + f * FSTRIDE, colk ? &tm.col[f] : &tm.row[f], bar, G.padL + tl.x0 - RP, tl.z0 - RP, shot);
+    }
+    const int lr = colk ? tid >> 1 : warp, lg = colk ? tid & 1 : lane;   // row and float4 group inside the tile
+    const int z = tl.z0 + lr, x = tl.x0 + 4 * lg;
+    const bool work = z < tl.zend && x + 3 >= tl.xbeg && x < tl.xend;
+    const long long so = (long long)shot * G.shot_stride + G.padL;
+    const int2 src = a.src[shot];
+    const size_t cell = (size_t)z * G.pitch + x;
+    float4 av4 = make_float4(0.f, 0.f, 0.f, 0.f), p04[2] = {av4, av4}, a1 = av4, a2 = av4, aS = av4, aR = av4;
+    const bool compen = BWD && G.iCompen == 1;
+    if (work) {   // (whole float4 groups: the row pitch leaves room past the last column)
+        av4 = __ldg(reinterpret_cast<const float4*>(G.avel + G.padL + cell));
+#pragma unroll
+        for (int f = 0; f < NF; ++f) p04[f] = *reinterpret_cast<const float4*>(a.P0[f] + so + cell);
+        if (BWD) {
+            a1 = *reinterpret_cast<const float4*>(a.rel1 + so + cell);
+            a2 = *reinterpret_cast<const float4*>(a.rel2 + so + cell);
+            if (compen) {
+                aS = *reinterpret_cast<const float4*>(a.sumS + so + cell);
+                aR = *reinterpret_cast<const float4*>(a.sumR + so + cell);
+            }
+        }
+    }
+    mbar_wait_b(bar, 0);
+    if (!work) return;
+    const LsTable T0{};
+    float av[4], o[NF][4];
+    unpack(av4, av);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        float w1[4], p1[4], p0[4];
+        stencil_row<RP, false, 0>(G, tile + f * FSTRIDE + (lr + RP) * SP + 4 * lg + RP, G.nfdmax, T0, make_uint2(0u, 0u), w1, p1, SP);
+        unpack(p04[f], p0);
+        if (f == 0) {   // forward field (Add_Con) / reconstructed source field (BKAdd_EFF_Con): double final sum, source term
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[f][q] = finish_double(av[q], w1[q], p1[q], p0[q]);
+            if (z == src.x && src.y >= x && src.y < x + 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (x + q == src.y) o[f][q] = __fadd_rn(o[f][q], a.wavelet);
+            }
+        } else {        // receiver field (BKAdd_Con): float final sum, data replacement
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[f][q] = finish_float(av[q], w1[q], p1[q], p0[q]);
+            if (z == G.s_z) {
+                const float* seis_row = a.seis + ((size_t)shot * G.NT + (a.k + 1)) * G.n;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = data_index(G, z, x + q);
+                    if (j >= 0) {
+                        const float d = seis_row[j];
+                        if (d != 0.0f) o[f][q] = d;
+                    }
+                }
+            }
+        }
+        store4c(a.P2[f] + so + cell, o[f], x, tl.xbeg, tl.xend);
+    }
+    if constexpr (!BWD) {
+        if (a.gather && z == G.s_z) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = (x + q >= tl.xbeg && x + q < tl.xend) ? data_index(G, z, x + q) : -1;
+                if (j >= 0) a.gather[((size_t)shot * G.NT + a.k) * G.n + j] = o[0][q];
+            }
+        }
+    } else {
+        constexpr int F1 = NF - 1;
+        float r1v[4], r2v[4], sSv[4], sRv[4];
+        unpack(a1, r1v);
+        unpack(a2, r2v);
+        unpack(aS, sSv);
+        unpack(aR, sRv);
+        if (compen) {   // Rel_Compen :503-517
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                sSv[q] = __fadd_rn(o[0][q], sSv[q]);
+                sRv[q] = __fadd_rn(o[F1][q], sRv[q]);
+                r1v[q] = __fmaf_rn(sRv[q], sSv[q], r1v[q]);
+                r2v[q] = __fmaf_rn(o[0][q], o[0][q], r2v[q]);
+            }
+            store4c(a.sumS + so + cell, sSv, x, tl.xbeg, tl.xend);
+            store4c(a.sumR + so + cell, sRv, x, tl.xbeg, tl.xend);
+        } else {        // Rel_NonCompen :489-501
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                r1v[q] = __fmaf_rn(o[F1][q], o[0][q], r1v[q]);
+                r2v[q] = __fmaf_rn(o[0][q], o[0][q], r2v[q]);
+            }
+        }
+        store4c(a.rel1 + so + cell, r1v, x, tl.xbeg, tl.xend);
+        store4c(a.rel2 + so + cell, r2v, x, tl.xbeg, tl.xend);
     }
 }
 
