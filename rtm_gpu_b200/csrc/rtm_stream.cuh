@@ -73,9 +73,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// bounded spin: a protocol error becomes a trap (CUDA error) instead of a hung GPU box
+// RTM_MBAR_TRAP=1 (debug builds): bounded spin, a protocol error becomes a trap (CUDA error) instead of a hung GPU
+#ifndef RTM_MBAR_TRAP
+#define RTM_MBAR_TRAP 0
+#endif
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity)
 {
+    if (!RTM_MBAR_TRAP) { mbar_wait(bar, parity); return; }
     const uint32_t addr = smem_u32(bar);
     for (int tries = 0;; ++tries) {
         uint32_t ok;
@@ -176,7 +180,13 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
 
     const int zlast = min(z0 + BR * n, a.zend); // rows of this segment that are stored: [z0, zlast)
     int slot_i = 0, slot_s = 1;                 // ring slots of stages i and i+1
-    for (int i = 0; i <= n; ++i) {
+    // rows of iteration 0 and their running addresses (every iteration moves BR rows down)
+    const size_t rowstep = (size_t)BR * G.pitch;
+    int zA = z0 - RP + rA, zO = z0 - BR + warp;
+    const float* pavA = AV + (size_t)zA * G.pitch + xA;
+    const float* pavB = AV + (ptrdiff_t)zO * G.pitch + xB;
+    size_t soA = (size_t)so + (size_t)zA * G.pitch + xA, soB = (size_t)so + (size_t)((ptrdiff_t)zO * G.pitch) + xB;
+    for (int i = 0; i <= n; ++i, zA += BR, zO += BR, pavA += rowstep, pavB += rowstep, soA += rowstep, soB += rowstep) {
         const int s = i + 1;
         if (warp == BR) {
             if (lane == 0) {
@@ -189,15 +199,12 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
             }
             __syncwarp();
         }
-        // rows of this iteration
-        const int  zA = z0 - RP + BR * i + rA;
         const bool doA = workA;                                // (mid block n is needed whole: out block n reads RP rows past its end)
-        const int  zO = z0 + BR * (i - 1) + warp;
         const bool doB = warp < BR && i >= 1 && zO < zlast && xB < a.xend;   // (rows / groups past the region's end feed nobody)
         // velocity factor a = ((v*v)*tao2)*h2 of both rows (L2-resident, shared by all shots): in flight during the wait
         float4 avA4 = make_float4(0.f, 0.f, 0.f, 0.f), avB4 = avA4;
-        if (doA && zA < G.NZ) avA4 = __ldg(reinterpret_cast<const float4*>(AV + (size_t)zA * G.pitch + xA));
-        if (doB) avB4 = __ldg(reinterpret_cast<const float4*>(AV + (size_t)zO * G.pitch + xB));
+        if (doA && zA < G.NZ) avA4 = __ldg(reinterpret_cast<const float4*>(pavA));
+        if (doB) avB4 = __ldg(reinterpret_cast<const float4*>(pavB));
 
         if (i == 0) mbar_wait_b(full + 0, 0);
         mbar_wait_b(full + slot_s, (s / 3) & 1);
@@ -243,8 +250,9 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
                 const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<float4*>(pm) = o4;
                 if (slot_s == 0) *reinterpret_cast<float4*>(pm + 3 * BR * WM) = o4;   // the copy behind slot 2
+                if (f == NF - 1) fence_async_smem();   // these slots are refilled by TMA later (generic -> async proxy order)
                 if (ownA && zA >= z0 && zA < zlast && xA < a.xend) {
-                    store4c(a.Ak[f] + so + (size_t)zA * G.pitch + xA, o, xA, 0, a.xend);
+                    store4c(a.Ak[f] + soA, o, xA, 0, a.xend);
                     if (!BWD && a.gather && zA == G.s_z) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -265,7 +273,7 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
             float av[4];
             unpack(avB4, av);
             float ok[NF][4], okm[NF][4];
-            const size_t o = so + (size_t)zO * G.pitch + xB;
+            const size_t o = soB;
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 float w1[4], p0[4];
@@ -340,8 +348,7 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
                 store4c(a.rel2 + o, r2v, xB, 0, a.xend);
             }
         }
-        // this warp is done with iteration i: its slots may be refilled by TMA (generic -> async proxy order)
-        fence_async_smem();
+        // this warp is done with iteration i: its slots may be refilled by TMA
         __syncwarp();
         if (warp < BR && lane == 0) mbar_arrive(done + (i & 1));
         slot_i = slot_s;
