@@ -334,7 +334,8 @@ struct rtm_ctx {
     // RTM_SEG_TILES = longest segment in 16-row tiles
     bool   stream2 = true;
     int    seg_tiles = 8;
-    int    fuse2_fwd = -1;                  // forward pass in pairs: RTM_FUSE2_FWD=0 off, 1 forced, unset: like the backward pass
+    int    fuse2_fwd = 0;                   // forward pass in pairs: RTM_FUSE2_FWD=1 on (measured slower than single steps: the forward
+                                            // step already runs at 74 % of the HBM peak and pays the pipeline's extra launches), default off
     CUtensorMap tmap_s_acc[4];              // rel1, rel2, sumS, sumR with a box of 128 x 8
     bool   dry = false;                     // launch helpers only set kernel attributes
     long   nlaunch = 0;                     // kernels launched (graph replays included)
@@ -750,24 +751,28 @@ static int prepare_classes(rtm_ctx* c)
             using T = Strm<4>;
             const int RPc = k.RP, C0 = G.N2 + RPc, R0 = G.N2 + RPc, xe = G.NX - G.N2 - RPc, ze = G.NZ - G.N2 - RPc;
             const int ncol = (xe - C0 + kTX - 1) / kTX, nblk = (ze - R0 + T::BR - 1) / T::BR;
-            const int nbot = (ze - R0) % T::BR ? 2 : 1;           // bottom "ib" blocks: at least 8 rows
             const int nright = (xe - C0 - (ncol - 1) * kTX >= 2 * RPc) ? 1 : 2;   // right "ib" columns: at least 2*RP cells
-            if (ncol >= 2 + nright && nblk >= nbot + 3) {
-                const int seg_blocks = std::max(1, c->seg_tiles * TZb / T::BR);
+            if (ncol >= 1 + nright && nblk >= 2) {
+                const int seg_blocks = std::max(2, c->seg_tiles * TZb / T::BR);
                 std::vector<int4> ii, ib;
-                auto run = [&](std::vector<int4>& out, int col, int b0, int nb) {   // blocks [b0, b0+nb) of a column, in pieces
-                    const int pieces = (nb + seg_blocks - 1) / seg_blocks;
-                    for (int p = 0, b = b0; p < pieces; ++p) {
-                        const int len = nb / pieces + (p < nb % pieces ? 1 : 0);
-                        out.push_back(make_int4(C0 + col * kTX, R0 + b * T::BR, len, 0));
+                // a column's blocks in pieces of (nearly) equal length <= seg_blocks.  "ib": the whole first / last column(s)
+                // and, of every other column, its first and last piece -- long pieces, so the ib launch streams as
+                // efficiently as the ii launch; their outer 8 rows / 2*RP columns are what the ii segments' halo may reach
+                for (int col = 0; col < ncol; ++col) {
+                    const bool edge = col == 0 || col >= ncol - nright;
+                    const int pieces = (nblk + seg_blocks - 1) / seg_blocks;
+                    std::vector<int2> pc;   // (first block, blocks)
+                    for (int p = 0, b = 0; p < pieces; ++p) {
+                        const int len = nblk / pieces + (p < nblk % pieces ? 1 : 0);
+                        pc.push_back(make_int2(b, len));
                         b += len;
                     }
-                };
-                const int nmid = nblk - 1 - nbot;                 // blocks between the top and the bottom ib rows
-                for (int col = 0; col < ncol; ++col) {
-                    run(ib, col, 0, 1);
-                    run(ib, col, nblk - nbot, nbot);
-                    run((col == 0 || col >= ncol - nright) ? ib : ii, col, 1, nmid);
+                    int nlast = 1;          // trailing pieces that go to ib: at least 8 valid rows
+                    while (nlast < (int)pc.size() && ze - (R0 + pc[pc.size() - nlast].x * T::BR) < T::BR) ++nlast;
+                    for (int p = 0; p < (int)pc.size(); ++p) {
+                        const bool border = edge || p == 0 || p >= (int)pc.size() - nlast;
+                        (border ? ib : ii).push_back(make_int4(C0 + col * kTX, R0 + pc[p].x * T::BR, pc[p].y, 0));
+                    }
                 }
                 auto up4 = [&](const std::vector<int4>& v, int4** d, int* n) -> int {
                     *n = (int)v.size();

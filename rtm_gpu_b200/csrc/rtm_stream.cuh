@@ -125,6 +125,7 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
     float*    accb = reinterpret_cast<float*>(smem_raw + NF * (T::CUR_RING + T::MID_RING));      // [2][4][BR][kTX]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NF * (T::CUR_RING + T::MID_RING) + (BWD ? 2 * 4 * T::ACC_BLK : 0));
     uint64_t* done = full + 3;
+    uint64_t* midr = full + 5;   // "mid block i is complete" (all 9 warps arrive, all wait): the A -> B barrier, split in arrive / wait
 
     const int  shot = fast_div(blockIdx.x, a.fd_nseg);
     const int4 sg   = __ldg(a.segs + (blockIdx.x - shot * a.nseg));
@@ -139,6 +140,7 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) mbar_init(full + i, 1);
         for (int i = 0; i < 2; ++i) mbar_init(done + i, BR);
+        for (int i = 0; i < 2; ++i) mbar_init(midr + i, BR + 1);
     }
     __syncthreads();
 
@@ -186,6 +188,9 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
     const float* pavA = AV + (size_t)zA * G.pitch + xA;
     const float* pavB = AV + (ptrdiff_t)zO * G.pitch + xB;
     size_t soA = (size_t)so + (size_t)zA * G.pitch + xA, soB = (size_t)so + (size_t)((ptrdiff_t)zO * G.pitch) + xB;
+    // velocity factor a = ((v*v)*tao2)*h2 of the two rows (L2-resident, shared by all shots), loaded one iteration ahead
+    float4 avA4 = make_float4(0.f, 0.f, 0.f, 0.f), avB4 = avA4;
+    if (workA && zA < G.NZ) avA4 = __ldg(reinterpret_cast<const float4*>(pavA));
     for (int i = 0; i <= n; ++i, zA += BR, zO += BR, pavA += rowstep, pavB += rowstep, soA += rowstep, soB += rowstep) {
         const int s = i + 1;
         if (warp == BR) {
@@ -201,27 +206,30 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
         }
         const bool doA = workA;                                // (mid block n is needed whole: out block n reads RP rows past its end)
         const bool doB = warp < BR && i >= 1 && zO < zlast && xB < a.xend;   // (rows / groups past the region's end feed nobody)
-        // velocity factor a = ((v*v)*tao2)*h2 of both rows (L2-resident, shared by all shots): in flight during the wait
-        float4 avA4 = make_float4(0.f, 0.f, 0.f, 0.f), avB4 = avA4;
-        if (doA && zA < G.NZ) avA4 = __ldg(reinterpret_cast<const float4*>(pavA));
-        if (doB) avB4 = __ldg(reinterpret_cast<const float4*>(pavB));
+        const float4 avAc = avA4, avBc = avB4;                 // this iteration's; the next iteration's go in flight now
+        if (i < n) {
+            if (workA && zA + BR < G.NZ) avA4 = __ldg(reinterpret_cast<const float4*>(pavA + rowstep));
+            if (warp < BR && zO + BR < zlast && xB < a.xend) avB4 = __ldg(reinterpret_cast<const float4*>(pavB + rowstep));
+        }
 
         if (i == 0) mbar_wait_b(full + 0, 0);
         mbar_wait_b(full + slot_s, (s / 3) & 1);
 
         // ---- phase A: mid block i (slot k / forward: k), rows [z0-RP+8i, +8)
+        float oA[NF][4];
         if (doA) {
             // centre row in the current-field ring: rows 0..RP-1 of the mid block lie in stage i, the others in stage i+1
             int rc = rA < RP ? slot_i * BR + rA + RP : slot_s * BR + rA - RP;
             if (rc < RP) rc += COPY;
             const int rm = slot_s * BR + rA;              // mid block i lives in the slot of stage i+1
             float av[4];
-            unpack(avA4, av);
+            unpack(avAc, av);
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 const float* pc = cur + f * CURF + rc * W1 + colm + RP;
                 float*       pm = mid + f * MIDF + rm * WM + colm;
-                float w1[4], p1[4], p0[4], o[4];
+                float w1[4], p1[4], p0[4];
+                float (&o)[4] = oA[f];
                 stencil_row<RP, false, W1>(G, pc, G.nfdmax, T0, nobins, w1, p1);
                 unpack(*reinterpret_cast<const float4*>(pm), p0);
                 if (f == 0) {   // source field / forward field: double final sum (Add_Con, BKAdd_EFF_Con), + wavelet
@@ -250,20 +258,24 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
                 const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<float4*>(pm) = o4;
                 if (slot_s == 0) *reinterpret_cast<float4*>(pm + 3 * BR * WM) = o4;   // the copy behind slot 2
-                if (f == NF - 1) fence_async_smem();   // these slots are refilled by TMA later (generic -> async proxy order)
-                if (ownA && zA >= z0 && zA < zlast && xA < a.xend) {
-                    store4c(a.Ak[f] + soA, o, xA, 0, a.xend);
-                    if (!BWD && a.gather && zA == G.s_z) {
+            }
+            fence_async_smem();   // these slots are refilled by TMA later (generic -> async proxy order)
+        }
+        // A -> B barrier, split: arrive now, store this warp's slot-k values, then wait for the other warps' rows
+        __syncwarp();
+        if (lane == 0) mbar_arrive(midr + (i & 1));
+        if (doA && ownA && zA >= z0 && zA < zlast && xA < a.xend) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int j = xA + q < a.xend ? data_index(G, zA, xA + q) : -1;
-                            if (j >= 0) a.gather[((size_t)shot * G.NT + a.k) * G.n + j] = o[q];
-                        }
-                    }
+            for (int f = 0; f < NF; ++f) store4c(a.Ak[f] + soA, oA[f], xA, 0, a.xend);
+            if (!BWD && a.gather && zA == G.s_z) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = xA + q < a.xend ? data_index(G, zA, xA + q) : -1;
+                    if (j >= 0) a.gather[((size_t)shot * G.NT + a.k) * G.n + j] = oA[0][q];
                 }
             }
         }
-        bar_consumers(T::kThreadsS);
+        mbar_wait_b(midr + (i & 1), (i >> 1) & 1);
 
         // ---- phase B: out block i (slot k-1 / forward: k+1), rows [z0+8(i-1), +8)
         if (doB) {
@@ -271,7 +283,7 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
             if (rb < RP) rb += COPY;
             const int rp = slot_i * BR + warp;                                         // same row, current-field ring (P0)
             float av[4];
-            unpack(avB4, av);
+            unpack(avBc, av);
             float ok[NF][4], okm[NF][4];
             const size_t o = soB;
 #pragma unroll
