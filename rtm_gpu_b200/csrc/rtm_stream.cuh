@@ -5,11 +5,11 @@
 // make phase A evaluate 24 rows for 16 and whose loads are exposed at every CTA start -- a CTA owns a
 // SEGMENT, a 128-wide column of 8n rows, and marches down it in blocks of 8 rows:
 //
-//   warp 8 (producer)   one lane issues, one block ahead of the arithmetic, the TMA copies of the next
+//   warp 9 (producer)   one lane issues, one block ahead of the arithmetic, the TMA copies of the next
 //                       stage: 8 new rows of the current fields (slot k+1, halo 2*RP in x), 8 rows of
 //                       the previous fields (slot k+2, halo RP; they land IN the mid ring, where
-//                       phase A overwrites them in place) and the 8 x 128 accumulator blocks; its
-//                       other lanes evaluate the 2 x RP halo columns of phase A;
+//                       phase A overwrites them in place) and the 8 x 128 accumulator blocks;
+//   warp 8 (halo)       evaluates the 2 x RP halo columns of phase A (16 float4 groups per block);
 //   warps 0..7          phase A: warp w evaluates row w of mid block i (slot k) from the ring of
 //                       current-field rows;  named barrier;  phase B: row w of out block i (slot k-1)
 //                       from the mid ring, both imaging updates, all stores.
@@ -42,7 +42,7 @@ template <int RP> struct Strm {
     static constexpr int WM = kTX + 2 * RP;            // pitch of the mid ring (halo RP)
     static constexpr int CUR_BLK = BR * W1 * 4, MID_BLK = BR * WM * 4, ACC_BLK = BR * kTX * 4;
     static constexpr int CUR_RING = RING * W1 * 4, MID_RING = RING * WM * 4;
-    static constexpr int kThreadsS = 32 * (BR + 1);    // 8 consumer warps + the producer / halo warp
+    static constexpr int kThreadsS = 32 * (BR + 2);    // 8 consumer warps + the halo warp + the producer warp
     static_assert(CUR_BLK % 128 == 0 && MID_BLK % 128 == 0 && CUR_RING % 128 == 0 && MID_RING % 128 == 0, "TMA destinations");
     __host__ __device__ static constexpr int bytes(bool bwd)
     {
@@ -108,7 +108,7 @@ __device__ __forceinline__ void store4c(float* dst, const float (&o)[4], int x, 
 #define RTM_STRM_MINB_B 2
 #endif
 #ifndef RTM_STRM_MINB_F
-#define RTM_STRM_MINB_F 4
+#define RTM_STRM_MINB_F 3
 #endif
 
 template <int RP, bool BWD>
@@ -174,8 +174,21 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
     // segment's own columns (its values are stored, the halo groups' are not)
     int rA = warp, colm = RP + 4 * lane;
     bool ownA = true, workA = warp < BR;
-    if (warp == BR) {            // producer warp: lanes 0..15 take the 2 halo groups of the 8 rows
+    if (warp == BR) {            // halo warp: lanes 0..15 take the 2 halo groups of the 8 rows
         rA = lane >> 1; colm = (lane & 1) ? kTX + RP : 0; ownA = false; workA = lane < 2 * BR;
+    }
+    if (warp == BR + 1) {
+        // ---- producer warp: one lane keeps the TMA copies one block ahead of the arithmetic.  It must not share a warp
+        // with phase-A work: it waits for EVERY consumer warp to finish block i-1 before it can refill their slots, and
+        // work queued behind that wait would make all consumers wait for it at the A -> B barrier.
+        if (lane == 0) {
+            issue(0); issue(1); issue(2);
+            for (int i = 1; i + 2 <= n + 1; ++i) {
+                mbar_wait_b(done + ((i - 1) & 1), ((i - 1) >> 1) & 1);   // every consumer warp is past B(i-1)
+                issue(i + 2);
+            }
+        }
+        return;
     }
     const int xA = x0 - RP + colm;              // global column of the first cell of the phase-A group
     const int xB = x0 + 4 * lane;               // phase B: the segment's own columns
@@ -193,17 +206,6 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
     if (workA && zA < G.NZ) avA4 = __ldg(reinterpret_cast<const float4*>(pavA));
     for (int i = 0; i <= n; ++i, zA += BR, zO += BR, pavA += rowstep, pavB += rowstep, soA += rowstep, soB += rowstep) {
         const int s = i + 1;
-        if (warp == BR) {
-            if (lane == 0) {
-                if (i == 0) {
-                    issue(0); issue(1); issue(2);
-                } else if (i + 2 <= n + 1) {
-                    mbar_wait_b(done + ((i - 1) & 1), ((i - 1) >> 1) & 1);   // every consumer warp is past B(i-1)
-                    issue(i + 2);
-                }
-            }
-            __syncwarp();
-        }
         const bool doA = workA;                                // (mid block n is needed whole: out block n reads RP rows past its end)
         const bool doB = warp < BR && i >= 1 && zO < zlast && xB < a.xend;   // (rows / groups past the region's end feed nobody)
         const float4 avAc = avA4, avBc = avB4;                 // this iteration's; the next iteration's go in flight now
