@@ -771,7 +771,8 @@ static int prepare_classes(rtm_ctx* c)
                     while (nlast < (int)pc.size() && ze - (R0 + pc[pc.size() - nlast].x * T::BR) < T::BR) ++nlast;
                     for (int p = 0; p < (int)pc.size(); ++p) {
                         const bool border = edge || p == 0 || p >= (int)pc.size() - nlast;
-                        (border ? ib : ii).push_back(make_int4(C0 + col * kTX, R0 + pc[p].x * T::BR, pc[p].y, 0));
+                        const int edges = (col == 0 ? 1 : 0) | (col == ncol - 1 ? 2 : 0) | (p == 0 ? 4 : 0) | (p == (int)pc.size() - 1 ? 8 : 0);
+                        (border ? ib : ii).push_back(make_int4(C0 + col * kTX, R0 + pc[p].x * T::BR, pc[p].y, edges));
                     }
                 }
                 auto up4 = [&](const std::vector<int4>& v, int4** d, int* n) -> int {
@@ -1247,8 +1248,7 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
                 t.src = f.src; t.wavelet = f.wavelet; t.k = f.k; t.gather = f.gather;
                 return launch_thin<false>(c, kc, B, ns, cur, cur, t);
             };
-            if (int rc = dispatch_fwd(c, ns, b1, b0, a0, true, B)) return rc;
-            if (int rc = thin(a0, b1, b0, bk)) return rc;
+            if (int rc = dispatch_fwd(c, ns, b1, b0, a0, true, B)) return rc;   // (slot k of the thin frame: the ib segments' halo)
             if (j > 0) CK(cudaStreamWaitEvent(B, c->ev_ii[(j - 1) & 1], 0));
             if (int rc = launch_stream_fwd(c, kc, B, ns, b1, b0, bk, bk1, a0, a1.wavelet, true)) return rc;
             CK(cudaEventRecord(c->ev_ib[j & 1], B));
@@ -1422,19 +1422,21 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
             for (auto& kc : c->classes)
                 if (int rc = dispatch_bwd2_class(c, kc, A, ns, Sb, Rb, Sa, Ra, a2, false)) return rc;
             CK(cudaEventRecord(c->ev_ii[j & 1], A));
-            auto thin = [&](int kk, int s1, int r1, int s0, int r0, int s2, int r2) -> int {   // the thin frame of slot kk (stream mode)
+            // the thin frame (stream mode): slot k's values come out of the streamed segments' halo (ib launch), slot k-1 -- which
+            // needs the ring of slot k -- from thin_frame_kernel, which also applies the imaging update of slot k there
+            auto thin = [&](int kk, int s1, int r1, int s0, int r0, int s2, int r2) -> int {
                 for (auto& kc : c->classes) {
                     if (!kc.stream_mode) continue;
                     ThinArgs t{};
                     t.P0[0] = c->field[s0]; t.P0[1] = c->field[r0]; t.P2[0] = c->field[s2]; t.P2[1] = c->field[r2];
                     t.src = c->d_src; t.wavelet = wavelet(kk); t.k = kk; t.seis = c->d_traces;
                     t.sumS = c->acc[0]; t.sumR = c->acc[1]; t.rel1 = c->acc[2]; t.rel2 = c->acc[3];
+                    t.twice = 1;
                     if (int rc = launch_thin<true>(c, kc, B, ns, s1, r1, t)) return rc;
                 }
                 return RTM_OK;
             };
             if (int rc = dispatch_bwd(c, ns, Sb, Rb, Sa, Ra, args1(k, Sa, Sc, Ra, Rb, Rc), true, B)) return rc;
-            if (int rc = thin(k, Sb, Rb, Sa, Ra, Sc, Rc)) return rc;
             if (j > 0) CK(cudaStreamWaitEvent(B, c->ev_ii[(j - 1) & 1], 0));
             for (auto& kc : c->classes)
                 if (int rc = dispatch_bwd2_class(c, kc, B, ns, Sb, Rb, Sa, Ra, a2, true)) return rc;

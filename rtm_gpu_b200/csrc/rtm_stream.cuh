@@ -60,7 +60,8 @@ struct StrmArgs {
     float  wavelet_a, wavelet_b;   // source term of the two steps
     int    k;                      // slot produced by phase A
     int    nshots;
-    const int4* segs;              // (x0, z0, blocks, -) : out rows [z0, z0 + 8*blocks), columns [x0, x0+128)
+    const int4* segs;              // (x0, z0, blocks, edges) : out rows [z0, z0 + 8*blocks), columns [x0, x0+128); edges: bit 0 left,
+                                   // 1 right, 2 top, 3 bottom = the segment touches the thin frame there and stores its slot-k halo
     int    nseg;
     int    xend, zend;             // the streamed region ends here (exclusive): the last column / block may be partial
     FastDiv fd_nseg;
@@ -129,7 +130,7 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
 
     const int  shot = fast_div(blockIdx.x, a.fd_nseg);
     const int4 sg   = __ldg(a.segs + (blockIdx.x - shot * a.nseg));
-    const int  x0 = sg.x, z0 = sg.y, n = sg.z;
+    const int  x0 = sg.x, z0 = sg.y, n = sg.z, edges = sg.w;
     const int  tid = threadIdx.x, lane = tid & 31;
     const int  warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
     const long long so = (long long)shot * G.shot_stride + G.padL;
@@ -173,9 +174,9 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
     // Row of block `blk` handled in phase A: r (0..7); first mid column colm (float4 group); own: the group lies in the
     // segment's own columns (its values are stored, the halo groups' are not)
     int rA = warp, colm = RP + 4 * lane;
-    bool ownA = true, workA = warp < BR;
+    bool workA = warp < BR;
     if (warp == BR) {            // halo warp: lanes 0..15 take the 2 halo groups of the 8 rows
-        rA = lane >> 1; colm = (lane & 1) ? kTX + RP : 0; ownA = false; workA = lane < 2 * BR;
+        rA = lane >> 1; colm = (lane & 1) ? kTX + RP : 0; workA = lane < 2 * BR;
     }
     if (warp == BR + 1) {
         // ---- producer warp: one lane keeps the TMA copies one block ahead of the arithmetic.  It must not share a warp
@@ -194,6 +195,11 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
     const int xB = x0 + 4 * lane;               // phase B: the segment's own columns
 
     const int zlast = min(z0 + BR * n, a.zend); // rows of this segment that are stored: [z0, zlast)
+    // Phase A also evaluates slot k on the RP cells around the segment.  Where those are thin-frame cells (the segment lies on
+    // the edge of the streamed region) their values are the thin frame's slot k: stored here, so that the thin frame needs a
+    // kernel of its own only for the second slot of the pair (which waits for the ring's one-way solution of slot k).
+    const int zloA = (edges & 4) ? z0 - RP : z0, zhiA = (edges & 8) ? a.zend + RP : zlast;
+    const int xloA = (edges & 1) ? x0 - RP : x0, xhiA = (edges & 2) ? a.xend + RP : min(x0 + kTX, a.xend);
     int slot_i = 0, slot_s = 1;                 // ring slots of stages i and i+1
     // rows of iteration 0 and their running addresses (every iteration moves BR rows down)
     const size_t rowstep = (size_t)BR * G.pitch;
@@ -266,13 +272,13 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
         // A -> B barrier, split: arrive now, store this warp's slot-k values, then wait for the other warps' rows
         __syncwarp();
         if (lane == 0) mbar_arrive(midr + (i & 1));
-        if (doA && ownA && zA >= z0 && zA < zlast && xA < a.xend) {
+        if (doA && zA >= zloA && zA < zhiA && xA + 3 >= xloA && xA < xhiA) {
 #pragma unroll
-            for (int f = 0; f < NF; ++f) store4c(a.Ak[f] + soA, oA[f], xA, 0, a.xend);
+            for (int f = 0; f < NF; ++f) store4c(a.Ak[f] + soA, oA[f], xA, xloA, xhiA);
             if (!BWD && a.gather && zA == G.s_z) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int j = xA + q < a.xend ? data_index(G, zA, xA + q) : -1;
+                    const int j = (xA + q >= xloA && xA + q < xhiA) ? data_index(G, zA, xA + q) : -1;
                     if (j >= 0) a.gather[((size_t)shot * G.NT + a.k) * G.n + j] = oA[0][q];
                 }
             }
@@ -396,6 +402,8 @@ struct ThinArgs {
     const float* seis;     // backward: row k+1 is imposed
     float*       gather;   // forward
     float *sumS, *sumR, *rel1, *rel2;
+    int    twice;          // backward: also apply the imaging update of the CURRENT slot (k+1) first -- its field values were
+                           // stored by the streaming kernel's halo, its imaging update was left to this kernel
 };
 
 template <int RP> struct Thin {
@@ -454,11 +462,12 @@ thin_frame_kernel(const __grid_constant__ ThinMaps tm, const __grid_constant__ G
     mbar_wait_b(bar, 0);
     if (!work) return;
     const LsTable T0{};
-    float av[4], o[NF][4];
+    float av[4], o[NF][4], c1[NF][4];   // c1: the current fields at the cell
     unpack(av4, av);
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
-        float w1[4], p1[4], p0[4];
+        float w1[4], p0[4];
+        float (&p1)[4] = c1[f];
         stencil_row<RP, false, 0>(G, tile + f * FSTRIDE + (lr + RP) * SP + 4 * lg + RP, G.nfdmax, T0, make_uint2(0u, 0u), w1, p1, SP);
         unpack(p04[f], p0);
         if (f == 0) {   // forward field (Add_Con) / reconstructed source field (BKAdd_EFF_Con): double final sum, source term
@@ -501,6 +510,19 @@ thin_frame_kernel(const __grid_constant__ ThinMaps tm, const __grid_constant__ G
         unpack(a2, r2v);
         unpack(aS, sSv);
         unpack(aR, sRv);
+        if (a.twice) {  // slot k+1 first (time order), with the current fields at the cell
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (compen) {
+                    sSv[q] = __fadd_rn(c1[0][q], sSv[q]);
+                    sRv[q] = __fadd_rn(c1[F1][q], sRv[q]);
+                    r1v[q] = __fmaf_rn(sRv[q], sSv[q], r1v[q]);
+                } else {
+                    r1v[q] = __fmaf_rn(c1[F1][q], c1[0][q], r1v[q]);
+                }
+                r2v[q] = __fmaf_rn(c1[0][q], c1[0][q], r2v[q]);
+            }
+        }
         if (compen) {   // Rel_Compen :503-517
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
