@@ -160,6 +160,10 @@ int rtm_device_count(void);
  * sizes its shot batches with the two (the reference has no counterpart: one shot at a time). */
 int rtm_memory_estimate(const rtm_params *p, int NT1, size_t *fixed, size_t *per_shot);
 int rtm_device_free_bytes(int device, size_t *free_bytes);
+/* Page-locked host memory for the buffers handed to rtm_migrate / rtm_migrate_raw (optional: pageable
+ * buffers work too, with slower copies).  The reference reads traces into plain malloc memory (:827-838). */
+int  rtm_host_alloc_pinned(void **p, size_t bytes);
+void rtm_host_free_pinned(void *p);
 int rtm_store_all_active(rtm_ctx *ctx); /* 1 if RTM_FLAG_STORE_ALL was requested and fits */
 
 /* ------------------------------------------------------------------ host-side pieces

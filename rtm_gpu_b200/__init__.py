@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "rtm_last_error", "rtm_version", "rtm_create", "rtm_destroy", "rtm_set_model", "rtm_set_operator",
     "rtm_forward", "rtm_migrate", "rtm_migrate_raw", "rtm_resample_device", "rtm_upload_gathers", "rtm_migrate_resident", "rtm_stack_reset",
     "rtm_stack_get", "rtm_stack_device", "rtm_stack_reduce", "rtm_stack_reduce_backend", "rtm_stack_finalize", "rtm_get_stats",
-    "rtm_reset_stats", "rtm_device_count", "rtm_memory_estimate", "rtm_device_free_bytes", "rtm_store_all_active", "rtm_ricker", "rtm_source_row", "rtm_derived",
+    "rtm_reset_stats", "rtm_device_count", "rtm_memory_estimate", "rtm_device_free_bytes", "rtm_host_alloc_pinned", "rtm_host_free_pinned", "rtm_store_all_active", "rtm_ricker", "rtm_source_row", "rtm_derived",
     "rtm_pad_velocity", "rtm_velocity_bins", "rtm_taylor_operator", "rtm_ls_operator",
     "rtm_ls_coefficients", "rtm_resample", "rtm_segy_decode", "rtm_segy_encode", "rtm_segy_info",
     "rtm_segy_read", "rtm_segy_write_image", "rtm_depth_to_time", "rtm_time_to_depth", "rtm_phase_rotate",

@@ -18,6 +18,7 @@
 #include "host/rtm_host.h"
 #include "rtm_kernels.cuh"
 #include "rtm_stream.cuh"
+#include "rtm_ring.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -337,6 +338,13 @@ struct rtm_ctx {
     int    fuse2_fwd = 0;                   // forward pass in pairs: RTM_FUSE2_FWD=1 on (measured slower than single steps: the forward
                                             // step already runs at 74 % of the HBM peak and pays the pipeline's extra launches), default off
     CUtensorMap tmap_s_acc[4];              // rel1, rel2, sumS, sumR with a box of 128 x 8
+    // the absorbing ring as a kernel of its own (rtm_ring.cuh; Taylor operator): RTM_RING2=0 keeps ring_tile<> everywhere,
+    // RTM_RING2_FWD=0 keeps it in the single-step forward launches
+    bool   ring2 = true, ring2_fwd = true, ring_ready = false, smem_ring = false;
+    RingGeo rgeo{};
+    float4* d_ring_coef = nullptr;
+    int*    d_ring_meta = nullptr;
+    CUtensorMap tmap_r_p1b[kFields], tmap_r_p1s[kFields], tmap_r_p0b[kFields], tmap_r_p0s[kFields], tmap_r_avb, tmap_r_avs;
     bool   dry = false;                     // launch helpers only set kernel attributes
     long   nlaunch = 0;                     // kernels launched (graph replays included)
     std::map<long long, long> graph_launches;
@@ -417,6 +425,7 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
     for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); cudaFree(k.d_segs_ii); cudaFree(k.d_segs_ib); cudaFree(k.d_thin); }
     cudaFree(c->store);
+    cudaFree(c->d_ring_coef); cudaFree(c->d_ring_meta);
     for (auto& f : c->field) cudaFree(f);
     for (auto& f : c->acc) cudaFree(f);
     cudaFree(c->d_v); cudaFree(c->d_avel); cudaFree(c->d_bins); cudaFree(c->d_tile_bins_f); cudaFree(c->d_tile_bins_b); cudaFree(c->d_tile_bins_b2); cudaFree(c->d_c); cudaFree(c->d_Index);
@@ -470,6 +479,23 @@ extern "C" int rtm_memory_estimate(const rtm_params* p, int NT1, size_t* fixed, 
                     + ((NT1 > 0 && NT1 != p->NT) ? (size_t)NT1 * p->n * 4 : 0)
                     + 2 * ncell * 4 + 64;                            // per-shot images
     return RTM_OK;
+}
+// Page-locked host buffers for the traces / images of rtm_migrate(_raw): copies from pinned memory run at full PCIe
+// rate and asynchronously to the host.
+extern "C" int rtm_host_alloc_pinned(void** p, size_t bytes)
+{
+    if (!p) return rtm_fail(RTM_ERR_ARG, "rtm_host_alloc_pinned: null argument");
+    *p = nullptr;
+    if (cudaHostAlloc(p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return rtm_fail(RTM_ERR_CUDA, "rtm_host_alloc_pinned: cannot page-lock %zu bytes", bytes);
+    }
+    return RTM_OK;
+}
+extern "C" void rtm_host_free_pinned(void* p)
+{
+    if (p) cudaFreeHost(p);
 }
 extern "C" int rtm_device_free_bytes(int device, size_t* free_bytes)
 {
@@ -542,6 +568,8 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     if (!c->fuse2_forced && p->iLSTE == 0) c->fuse2 = false;
     if (const char* e = std::getenv("RTM_FUSE2_MAXRP")) c->fuse2_maxrp = std::atoi(e);
     if (const char* e = std::getenv("RTM_STREAM2")) c->stream2 = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RTM_RING2")) c->ring2 = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RTM_RING2_FWD")) c->ring2_fwd = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_FUSE2_FWD")) c->fuse2_fwd = std::atoi(e) != 0 ? 1 : 0;
     if (const char* e = std::getenv("RTM_SEG_TILES")) c->seg_tiles = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RTM_RING_INTERLEAVE")) c->ring_interleave = std::atoi(e) != 0;
@@ -827,6 +855,34 @@ static int prepare_classes(rtm_ctx* c)
         }
         c->classes.push_back(k);
     }
+    // ring kernel (rtm_ring.cuh): per-cell one-way coefficients of this model, tensor maps of the tile boxes
+    c->ring_ready = false;
+    if (c->ring2 && !ls && c->have_model && c->have_op) {
+        const int nring = 2 * G.nband + 2 * G.nside;
+        c->rgeo = make_ring_geo(G.N2, G.mmax, c->RP);
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, c->device));
+        if ((size_t)c->rgeo.smem_bytes() <= (size_t)prop.sharedMemPerBlockOptin && c->rgeo.chS + 2 * c->rgeo.R <= 256 && c->rgeo.spB <= 256) {
+            cudaFree(c->d_ring_coef); cudaFree(c->d_ring_meta);
+            c->d_ring_coef = nullptr; c->d_ring_meta = nullptr;
+            CK(cudaMalloc(&c->d_ring_coef, sizeof(float4) * (size_t)nring * c->rgeo.cells));
+            CK(cudaMalloc(&c->d_ring_meta, sizeof(int) * (size_t)nring * c->rgeo.cells));
+            dim3 grid((c->rgeo.cells + 255) / 256, nring);
+            ring_coef_kernel<<<grid, 256, 0, c->stream>>>(G, c->rgeo.cells, c->d_ring_coef, c->d_ring_meta);
+            CK(cudaGetLastError());
+            const RingGeo& r = c->rgeo;
+            for (int i = 0; i < rtm_ctx::kFields; ++i) {
+                int rc = encode_tmap(c, &c->tmap_r_p1b[i], c->field[i], 0, r.chB + 2 * r.R, 0, r.spB);
+                if (!rc) rc = encode_tmap(c, &c->tmap_r_p1s[i], c->field[i], 0, r.chS + 2 * r.R, 0, r.spS);
+                if (!rc) rc = encode_tmap(c, &c->tmap_r_p0b[i], c->field[i], 0, r.chB, 0, r.cwB);
+                if (!rc) rc = encode_tmap(c, &c->tmap_r_p0s[i], c->field[i], 0, r.chS, 0, r.cwS);
+                if (rc) return rc;
+            }
+            if (int rc = encode_tmap(c, &c->tmap_r_avb, c->d_avel, 0, r.chB, 1, r.cwB)) return rc;
+            if (int rc = encode_tmap(c, &c->tmap_r_avs, c->d_avel, 0, r.chS, 1, r.cwS)) return rc;
+            c->ring_ready = true;
+        }
+    }
     CK(cudaDeviceSynchronize());
     return RTM_OK;
 }
@@ -1055,8 +1111,71 @@ template <class Launch> static int fork_join(rtm_ctx* c, Launch launch, cudaStre
     return RTM_OK;
 }
 // buf: index of the field buffer holding slot k-1, or -1 for the store-all slab
+// The ring tiles of one slot by ring_kernel: cur / prev = field buffers of the current / previous slot of the field that
+// carries the absorbing boundary (forward field; backward: receiver field).
+template <bool BWD> static int launch_ring(rtm_ctx* c, cudaStream_t st, int ns, int cur, int prev, RingArgs a)
+{
+    const int smem = c->rgeo.smem_bytes();
+    if (!c->smem_ring) {
+        CK(cudaFuncSetAttribute(ring_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(ring_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(ring_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(ring_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(ring_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(ring_kernel<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(ring_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(ring_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        c->smem_ring = true;
+    }
+    const Geo& G = c->G;
+    const int nring = 2 * G.nband + 2 * G.nside;
+    a.nshots = ns; a.rc = RingCoef{c->d_ring_coef, c->d_ring_meta}; a.rg = c->rgeo;
+    if (c->dry) return RTM_OK;
+    RingMaps tm;
+    tm.p1b = c->tmap_r_p1b[cur]; tm.p1s = c->tmap_r_p1s[cur]; tm.p0b = c->tmap_r_p0b[prev]; tm.p0s = c->tmap_r_p0s[prev];
+    tm.avb = c->tmap_r_avb; tm.avs = c->tmap_r_avs;
+    ++c->nlaunch;
+    const unsigned grid = (unsigned)(nring * ns);
+    switch (c->RP) {
+    case 4:  ring_kernel<4, BWD><<<grid, kThreads, smem, st>>>(tm, G, a); break;
+    case 8:  ring_kernel<8, BWD><<<grid, kThreads, smem, st>>>(tm, G, a); break;
+    case 12: ring_kernel<12, BWD><<<grid, kThreads, smem, st>>>(tm, G, a); break;
+    case 16: ring_kernel<16, BWD><<<grid, kThreads, smem, st>>>(tm, G, a); break;
+    default: return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", c->RP);
+    }
+    return RTM_OK;
+}
+static RingArgs ring_args_fwd(rtm_ctx* c, const FwdArgs& f)
+{
+    RingArgs r{};
+    r.P2 = f.P2; r.SX = nullptr; r.src = f.src; r.wavelet = f.wavelet; r.inject = 1; r.k = f.k; r.st = f.st;
+    r.seis = nullptr; r.gather = f.gather; r.sum_double = c->G.iLSTE == 0 ? 0 : 1;
+    return r;
+}
 static int dispatch_fwd(rtm_ctx* c, int ns, int buf, int p0buf, FwdArgs a, bool frame = false, cudaStream_t serial = nullptr)
 {
+    if (c->ring_ready && buf >= 0 && (frame || c->ring2_fwd)) {
+        // the ring by its own kernel: alone (frame step of the pair loop), or next to the interior launch on a side stream
+        if (frame) return launch_ring<false>(c, serial ? serial : c->stream, ns, buf, p0buf, ring_args_fwd(c, a));
+        CK(cudaEventRecord(c->fork_ev, c->stream));
+        CK(cudaStreamWaitEvent(c->aux[1], c->fork_ev, 0));
+        if (int rc = launch_ring<false>(c, c->aux[1], ns, buf, p0buf, ring_args_fwd(c, a))) return rc;
+        CK(cudaEventRecord(c->join_ev[1], c->aux[1]));
+        const bool ls0 = c->G.iLSTE == 0;
+        int rc = fork_join(c, [&](rtm_ctx::TileClass& k, cudaStream_t st, bool) -> int {
+            a.do_ring = 0;
+            switch (k.RP) {
+            case 4:  return ls0 ? launch_fwd<4, true>(c, k, st, ns, buf, p0buf, false, a) : launch_fwd<4, false>(c, k, st, ns, buf, p0buf, false, a);
+            case 8:  return ls0 ? launch_fwd<8, true>(c, k, st, ns, buf, p0buf, false, a) : launch_fwd<8, false>(c, k, st, ns, buf, p0buf, false, a);
+            case 12: return ls0 ? launch_fwd<12, true>(c, k, st, ns, buf, p0buf, false, a) : launch_fwd<12, false>(c, k, st, ns, buf, p0buf, false, a);
+            case 16: return ls0 ? launch_fwd<16, true>(c, k, st, ns, buf, p0buf, false, a) : launch_fwd<16, false>(c, k, st, ns, buf, p0buf, false, a);
+            }
+            return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", k.RP);
+        });
+        if (rc) return rc;
+        CK(cudaStreamWaitEvent(c->stream, c->join_ev[1], 0));
+        return RTM_OK;
+    }
     const bool ls = c->G.iLSTE == 0;
     return fork_join(c, [&](rtm_ctx::TileClass& k, cudaStream_t st, bool first) -> int {
         a.do_ring = first ? 1 : 0;
@@ -1111,6 +1230,12 @@ template <bool STORE> static int dispatch_bwd_t(rtm_ctx* c, int ns, int s1, int 
 }
 static int dispatch_bwd(rtm_ctx* c, int ns, int s1, int r1, int s0, int r0, const BwdArgs& a, bool frame = false, cudaStream_t serial = nullptr)
 {
+    if (frame && c->ring_ready && !c->store_mode && c->classes.size() == 1 && c->classes[0].stream_mode) {
+        // stream mode: a frame step is the ring alone (receiver field + strip restore), by ring_kernel
+        RingArgs r{};
+        r.P2 = a.R2; r.SX = a.S2; r.src = a.src; r.inject = 0; r.k = a.k; r.st = a.st; r.seis = a.seis; r.sum_double = 0;
+        return launch_ring<true>(c, serial ? serial : c->stream, ns, r1, r0, r);
+    }
     return c->store_mode ? dispatch_bwd_t<true>(c, ns, s1, r1, s0, r0, a, frame, serial) : dispatch_bwd_t<false>(c, ns, s1, r1, s0, r0, a, frame, serial);
 }
 
