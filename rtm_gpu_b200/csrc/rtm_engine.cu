@@ -858,8 +858,8 @@ static int prepare_classes(rtm_ctx* c)
     // ring kernel (rtm_ring.cuh): per-cell one-way coefficients of this model, tensor maps of the tile boxes
     c->ring_ready = false;
     if (c->ring2 && !ls && c->have_model && c->have_op) {
-        const int nring = 2 * G.nband + 2 * G.nside;
-        c->rgeo = make_ring_geo(G.N2, G.mmax, c->RP);
+        c->rgeo = make_ring_geo(G, G.mmax, c->RP);
+        const int nring = c->rgeo.ntiles;
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, c->device));
         if ((size_t)c->rgeo.smem_bytes() <= (size_t)prop.sharedMemPerBlockOptin && c->rgeo.chS + 2 * c->rgeo.R <= 256 && c->rgeo.spB <= 256) {
@@ -868,7 +868,7 @@ static int prepare_classes(rtm_ctx* c)
             CK(cudaMalloc(&c->d_ring_coef, sizeof(float4) * (size_t)nring * c->rgeo.cells));
             CK(cudaMalloc(&c->d_ring_meta, sizeof(int) * (size_t)nring * c->rgeo.cells));
             dim3 grid((c->rgeo.cells + 255) / 256, nring);
-            ring_coef_kernel<<<grid, 256, 0, c->stream>>>(G, c->rgeo.cells, c->d_ring_coef, c->d_ring_meta);
+            ring_coef_kernel<<<grid, 256, 0, c->stream>>>(G, c->rgeo, c->d_ring_coef, c->d_ring_meta);
             CK(cudaGetLastError());
             const RingGeo& r = c->rgeo;
             for (int i = 0; i < rtm_ctx::kFields; ++i) {
@@ -1128,7 +1128,7 @@ template <bool BWD> static int launch_ring(rtm_ctx* c, cudaStream_t st, int ns, 
         c->smem_ring = true;
     }
     const Geo& G = c->G;
-    const int nring = 2 * G.nband + 2 * G.nside;
+    const int nring = c->rgeo.ntiles;
     a.nshots = ns; a.rc = RingCoef{c->d_ring_coef, c->d_ring_meta}; a.rg = c->rgeo;
     if (c->dry) return RTM_OK;
     RingMaps tm;

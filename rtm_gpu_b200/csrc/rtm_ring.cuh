@@ -25,26 +25,70 @@
 
 namespace rtmk {
 
+// Tiling of the ring for ring_kernel.  A TMA box must start on a 16-byte boundary in global memory and the float4
+// groups of the row stencil on one in shared memory, so the COMPUTE rectangle of every tile starts at a column x with
+// (padL + x) % 4 == 0: band tiles are 120 columns wide, grown by 4 columns on both sides (128 = 32 groups), the first one
+// starting left of the array; side tiles take 16 (N2 + 2, rounded) columns from an aligned column at or left of their
+// first needed one.  Rows carry no such constraint: grown by one row.
+constexpr int kRing2TX = 120;
 struct RingGeo {            // per context
     int RP;                 // rounded operator radius (x halo of the box)
     int R;                  // operator radius (z halo)
     int chB, cwB, spB;      // band tiles:  compute rows N2+2, compute width 128, box pitch 128+2RP
-    int chS, cwS, spS;      // side tiles:  compute rows 128,  compute width (N2+2 rounded up to 4), box pitch cwS+2RP
-    int cells;              // cells per tile in the coefficient arrays (N2 * kRingTX, rounded up to 4)
+    int chS, cwS, spS;      // side tiles:  compute rows 128,  compute width (N2+5 rounded up to 4), box pitch cwS+2RP
+    int xshift;             // band tile i covers columns [120 i - xshift, 120 (i+1) - xshift)
+    int cxl, cxr;           // first compute column of the left / right side tiles
+    int nband, nside, ntiles;
+    FastDiv fd_ntiles;
+    int cells;              // cells per tile in the coefficient arrays (N2 * 126, rounded up to 4)
     int n1, nc;             // floats reserved for the halo box / for each compute-rectangle array (both tile kinds, 128-byte multiples)
     __host__ __device__ int smem_bytes() const { return (n1 + 3 * nc + 5 * cells) * 4 + 16; }
 };
-__host__ inline RingGeo make_ring_geo(int N2, int R, int RP)
+__host__ inline RingGeo make_ring_geo(const Geo& G, int R, int RP)
 {
     RingGeo g;
+    const int N2 = G.N2;
     g.RP = RP; g.R = R;
-    g.chB = N2 + 2; g.cwB = kRingTX + 2; g.spB = g.cwB + 2 * RP;
-    g.chS = kRingTX + 2; g.cwS = (N2 + 2 + 3) / 4 * 4; g.spS = g.cwS + 2 * RP;
+    g.chB = N2 + 2; g.cwB = kRing2TX + 8; g.spB = g.cwB + 2 * RP;
+    g.chS = kRingTX + 2; g.cwS = (N2 + 5 + 3) / 4 * 4; g.spS = g.cwS + 2 * RP;
+    g.xshift = G.padL % 4;
+    g.cxl = -(G.padL % 4 ? G.padL % 4 : 4);
+    g.cxr = (G.NX - N2 - 1) - (G.padL + G.NX - N2 - 1) % 4;
+    g.nband = (G.NX + g.xshift + kRing2TX - 1) / kRing2TX;
+    g.nside = (G.mod_NZ + kRingTX - 1) / kRingTX;
+    g.ntiles = 2 * g.nband + 2 * g.nside;
+    g.fd_ntiles = make_fastdiv(g.ntiles);
     g.cells = (N2 * kRingTX + 3) / 4 * 4;
     auto up32 = [](int n) { return (n + 31) / 32 * 32; };
     g.n1 = up32(std::max((g.chB + 2 * R) * g.spB, (g.chS + 2 * R) * g.spS));
     g.nc = up32(std::max(g.chB * g.cwB, g.chS * g.cwS));
     return g;
+}
+// output rectangle (clipped to the array) and compute-rectangle origin of a tile
+__host__ __device__ inline RingRect ring2_rect(const Geo& G, const RingGeo& g, int tile, int* cz0, int* cx0)
+{
+    RingRect r;
+    const int N2 = G.N2;
+    if (tile < 2 * g.nband) {
+        const bool top = tile < g.nband;
+        const int  i   = top ? tile : tile - g.nband;
+        r.za = top ? 0 : G.NZ - N2;
+        r.zb = r.za + N2;
+        const int xa = i * kRing2TX - g.xshift;
+        r.xa = xa < 0 ? 0 : xa;
+        r.xb = xa + kRing2TX < G.NX ? xa + kRing2TX : G.NX;
+        *cz0 = r.za - 1; *cx0 = xa - 4;
+    } else {
+        tile -= 2 * g.nband;
+        const bool left = tile < g.nside;
+        const int  i    = left ? tile : tile - g.nside;
+        r.xa = left ? 0 : G.NX - N2;
+        r.xb = r.xa + N2;
+        r.za = N2 + i * kRingTX;
+        r.zb = r.za + kRingTX < G.NZ - N2 ? r.za + kRingTX : G.NZ - N2;
+        *cz0 = r.za - 1; *cx0 = left ? g.cxl : g.cxr;
+    }
+    return r;
 }
 struct RingMaps { CUtensorMap p1b, p1s, p0b, p0s, avb, avs; };   // current (with halo) / previous field, velocity factor; band / side boxes
 
@@ -53,10 +97,11 @@ struct RingMaps { CUtensorMap p1b, p1s, p0b, p0s, avb, avs; };   // current (wit
 struct RingCoef { const float4* coef; const int* meta; };   // [tiles][cells]: (rcp, tv | r1, c2, w)
 
 // One thread per ring cell (tile-major), once per model.
-__global__ void ring_coef_kernel(Geo G, int cells, float4* coef, int* meta)
+__global__ void ring_coef_kernel(Geo G, RingGeo rg, float4* coef, int* meta)
 {
-    const int tile = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
-    const RingRect o = ring_rect(G, tile);
+    const int tile = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x, cells = rg.cells;
+    int cz0, cx0;
+    const RingRect o = ring2_rect(G, rg, tile, &cz0, &cx0);
     const int oh = o.zb - o.za, ow = o.xb - o.xa;
     if (c >= cells) return;
     float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -129,14 +174,13 @@ __global__ void __launch_bounds__(kThreads, RTM_RING_MINB)
 ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, const RingArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int nring = 2 * G.nband + 2 * G.nside;
-    const int shot = fast_div(blockIdx.x, G.fd_nring), tile = blockIdx.x - shot * nring;
-    const bool band = tile < 2 * G.nband;
-    const RingRect o = ring_rect(G, tile);
+    const int shot = fast_div(blockIdx.x, a.rg.fd_ntiles), tile = blockIdx.x - shot * a.rg.ntiles;
+    const bool band = tile < 2 * a.rg.nband;
+    int cz0, cx0;                                      // compute rectangle origin (may lie outside the array: never consumed there)
+    const RingRect o = ring2_rect(G, a.rg, tile, &cz0, &cx0);
     const int R = a.rg.R, NZ = G.NZ, NX = G.NX;
     const int ch = band ? a.rg.chB : a.rg.chS, CW = band ? a.rg.cwB : a.rg.cwS, SP = band ? a.rg.spB : a.rg.spS;
     const int NG = CW >> 2;
-    const int cz0 = o.za - 1, cx0 = o.xa - 1;          // compute rectangle origin (may be -1: never consumed there)
     float* s1  = reinterpret_cast<float*>(smem_raw);   // (ch+2R) x SP: row 0 = z cz0-R, column 0 = x cx0-RP
     float* s0  = s1 + a.rg.n1;                         // ch x CW previous field
     float* sAv = s0 + a.rg.nc;                         // ch x CW velocity factor
@@ -255,7 +299,7 @@ ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, 
         const float4 cf = sCf[c];
         const int    m  = sMt[c];
         const int oz = c / ow, ox = c - oz * ow;
-        const int lz = oz + 1, lx = ox + 1;                    // position in the compute rectangle
+        const int lz = o.za + oz - cz0, lx = o.xa + ox - cx0;  // position in the compute rectangle
         const int kind = m & 7;
         const float* q2 = s2 + lz * CW + lx;
         const float* q0 = s0 + lz * CW + lx;
