@@ -202,8 +202,6 @@ ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, 
     // this thread's output cells (tile-major cell index c = oz*ow + ox): coefficients, meta word and -- backward --
     // the boundary-strip value to restore, all in flight during the TMA copies
     const int oh = o.zb - o.za, ow = o.xb - o.xa, ncell = oh * ow;
-    constexpr int kMaxPer = (64 * kRingTX + kThreads - 1) / kThreads;   // N2 <= 64
-    const int nper = (ncell + kThreads - 1) / kThreads;
     const float4* cfp = a.rc.coef + (size_t)tile * a.rg.cells;
     const int*    mtp = a.rc.meta + (size_t)tile * a.rg.cells;
     for (int c = tid; c < ncell; c += kThreads) {   // asynchronous copies, consumed after the two-way phase
@@ -214,18 +212,6 @@ ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, 
     const int2 src = a.src[shot];
     const size_t slot = (size_t)shot * G.NT + a.k;
     const size_t sxs = slot * G.nfdmax * G.mod_NX, szs = slot * G.nfdmax * G.mod_NZ;   // this slot inside up/dw and lf/rt
-    auto strip_ptr = [&](int m) -> float* {
-        const int arr = (m >> 3) & 7;
-        const size_t off = (size_t)(m >> 6);
-        switch (arr) {
-        case 1: return a.st.up + sxs + off;
-        case 2: return a.st.dw + sxs + off;
-        case 3: return a.st.lf + szs + off;
-        case 4: return a.st.rt + szs + off;
-        }
-        return nullptr;
-    };
-
     mbar_wait(bar, 0);
     // mirror about the array edge (:65-68) where the box reaches outside the array (TMA wrote zeros there)
     {
@@ -233,21 +219,22 @@ ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, 
         const int ztop = cz0 - R, xleft = cx0 - RP;            // array coordinates of box row 0 / column 0
         if (ztop < 0 || ztop + rows > NZ) {                    // rows outside: whole box width
             const int nout = ztop < 0 ? -ztop : ztop + rows - NZ;
-            for (int i = tid; i < nout * SP; i += kThreads) {
-                const int r = i / SP, cidx = i - r * SP;
+            for (int r = tid >> 5; r < nout; r += kWarps) {    // a warp per outside row
                 const int zr = ztop < 0 ? r : rows - nout + r; // box row outside the array
                 const int z  = ztop + zr, zm = z < 0 ? -z : 2 * NZ - 2 - z;
-                s1[zr * SP + cidx] = s1[(zm - ztop) * SP + cidx];
+                // (a short last tile: the box reaches far past the array, rows whose mirror image lies outside the box feed nobody)
+                if (zm - ztop >= 0 && zm - ztop < rows)
+                    for (int cidx = tid & 31; cidx < SP; cidx += 32) s1[zr * SP + cidx] = s1[(zm - ztop) * SP + cidx];
             }
             __syncthreads();
         }
         if (xleft < 0 || xleft + SP > NX) {                    // columns outside: all rows (mirrored rows included)
             const int nl = xleft < 0 ? -xleft : 0, nr = xleft + SP > NX ? xleft + SP - NX : 0;
-            for (int i = tid; i < rows * (nl + nr); i += kThreads) {
-                const int r = i / (nl + nr), j = i - r * (nl + nr);
+            for (int j = tid & 31; j < nl + nr; j += 32) {     // a lane per outside column, the warps share the rows
                 const int cidx = j < nl ? j : SP - nr + (j - nl);
                 const int x = xleft + cidx, xm = x < 0 ? -x : 2 * NX - 2 - x;
-                if (xm - xleft >= 0 && xm - xleft < SP) s1[r * SP + cidx] = s1[r * SP + xm - xleft];
+                if (xm - xleft >= 0 && xm - xleft < SP)
+                    for (int r = tid >> 5; r < rows; r += kWarps) s1[r * SP + cidx] = s1[r * SP + xm - xleft];
             }
         }
         __syncthreads();
@@ -291,14 +278,18 @@ ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    // one-way solution, blend, stores
+    // one-way solution, blend, stores.  Thread t takes cells t, t + 256, ...: (oz, ox) advance without divisions
     float* P2 = a.P2 + so;
-    for (int i = 0; i < nper && i < kMaxPer; ++i) {
-        const int c = tid + i * kThreads;
-        if (c >= ncell) break;
+    float* const sb1 = a.st.up ? a.st.up + sxs : nullptr;
+    float* const sb2 = a.st.up ? a.st.dw + sxs : nullptr;
+    float* const sb3 = a.st.up ? a.st.lf + szs : nullptr;
+    float* const sb4 = a.st.up ? a.st.rt + szs : nullptr;
+    const int dq = kThreads / ow, dr = kThreads - dq * ow;
+    int oz = tid / ow, ox = tid - oz * ow;
+    for (int c = tid; c < ncell; c += kThreads, oz += dq, ox += dr) {
+        if (ox >= ow) { ox -= ow; ++oz; }
         const float4 cf = sCf[c];
         const int    m  = sMt[c];
-        const int oz = c / ow, ox = c - oz * ow;
         const int lz = o.za + oz - cz0, lx = o.xa + ox - cx0;  // position in the compute rectangle
         const int kind = m & 7;
         const float* q2 = s2 + lz * CW + lx;
@@ -330,10 +321,11 @@ ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, 
         const float val = __fmaf_rn(__fsub_rn(1.0f, cf.w), q2[0], __fmul_rn(cf.w, Pb));   // Hybrid2 :160-183
         const int z = o.za + oz, x = o.xa + ox;
         P2[(size_t)z * G.pitch + x] = val;
-        if ((m >> 3) & 7) {
-            float* sp = strip_ptr(m);
+        const int arr = (m >> 3) & 7;
+        if (arr && sb1) {
+            float* sp = (arr == 1 ? sb1 : arr == 2 ? sb2 : arr == 3 ? sb3 : sb4) + (m >> 6);
             if (BWD) { if (a.SX) a.SX[so + (size_t)z * G.pitch + x] = *sp; }   // BKEqual :222-245 (slot k, one step early)
-            else if (a.st.up) *sp = val;                                        // Hybrid3 :184-208
+            else *sp = val;                                                     // Hybrid3 :184-208
         }
         if (!BWD && a.gather) {
             const int j = data_index(G, z, x);
