@@ -132,18 +132,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
                  "r"(bytes)
                  : "memory");
 }
+// The waiting thread may be suspended by the hardware until the phase completes or the time hint (ns) runs out; with a
+// generous hint a waiting warp polls a handful of times instead of spinning (round 2: the spinning warps of the streaming
+// kernel issued 30 % of its instructions and cost power under the 1 kW cap).
+#ifndef RTM_MBAR_HINT_NS
+#define RTM_MBAR_HINT_NS 20000
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE;\n"
         "bra WAIT_LOOP;\n"
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"((uint32_t)RTM_MBAR_HINT_NS)
         : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, int z, int s)

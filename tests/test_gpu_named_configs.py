@@ -101,18 +101,24 @@ def test_c2_whole_shot_full_time_axis():
     check(case, np.rint(np.clip(v, 1500.0, 4500.0)).astype(np.float32))
 
 
+@pytest.mark.parametrize("mod_NZ", [512, 4096])
 @pytest.mark.parametrize("operator", ["taylor12", "adaptive2_12"])
-def test_c5_shape_4096_squared(operator):
-    """configs[4]: 4096 x 4096, N2 = 12; fixed radius 12 and per-cell adaptive radius 2..12."""
+def test_c5_shape_4096_wide(operator, mod_NZ):
+    """configs[4]: 4096 x 4096, N2 = 12; fixed radius 12 and per-cell adaptive radius 2..12.  The square grid costs
+    ~110 s per operator, nearly all in the reference's element-wise host IO (both passed on the B200:
+    profiles/r2_c7_pytest_gpu_full.log); they run when RTM_TEST_SLOW=1, the 4096 x 512 slice of the same model always."""
+    import os
+    if mod_NZ == 4096 and os.environ.get("RTM_TEST_SLOW", "0") != "1":
+        pytest.skip("4096 x 4096 against the reference takes ~110 s of host IO: set RTM_TEST_SLOW=1")
     if operator == "taylor12":
         case = Case(name="c5_te", nfdmax=12, nfdmin=2, N2=12, f0=15.0, iLSTE=1, hz=10.0, h=10.0, tao=5e-4, tao1=5e-4,
-                    mod_NZ=4096, mod_NX=4096, NT1=30, s_l=5, s_z=40, n=400, ds=10, r_x=2100, nrec=1,
-                    NX_ED=4096, NZ_ED=4096, depths=[3000.0])
+                    mod_NZ=mod_NZ, mod_NX=4096, NT1=30, s_l=5, s_z=40, n=400, ds=10, r_x=2100, nrec=1,
+                    NX_ED=4096, NZ_ED=mod_NZ, depths=[3000.0])
     else:
         case = Case(name="c5_ls", nfdmax=12, nfdmin=2, N2=12, f0=15.0, fmax=34.0, iLSTE=0, hz=20.0, h=20.0, tao=1e-3,
-                    tao1=1e-3, mod_NZ=4096, mod_NX=4096, NT1=30, s_l=5, s_z=40, n=400, ds=10, r_x=2100, nrec=1,
-                    NX_ED=4096, NZ_ED=4096, depths=[6000.0], nthita=100)
-    check(case, synthetic_model(case.mod_NX, case.mod_NZ, case.h, case.hz))
+                    tao1=1e-3, mod_NZ=mod_NZ, mod_NX=4096, NT1=30, s_l=5, s_z=40, n=400, ds=10, r_x=2100, nrec=1,
+                    NX_ED=4096, NZ_ED=mod_NZ, depths=[6000.0], nthita=100)
+    check(case, synthetic_model(case.mod_NX, 4096, case.h, case.hz)[:, :mod_NZ].copy())
 
 
 @pytest.mark.parametrize("mod_NZ", [320, 5000])
