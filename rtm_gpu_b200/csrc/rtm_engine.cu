@@ -313,6 +313,9 @@ struct rtm_ctx {
         int  n_thin = 0;
         CUtensorMap tmap_s_cur[kFields], tmap_s_prev[kFields];   // boxes (128+4RP) x 8 and (128+2RP) x 8
         CUtensorMap tmap_t_row[kFields], tmap_t_col[kFields];    // thin-frame boxes
+        CUtensorMap tmap_s_own[kFields];                         // 128 x 8 (previous field of the single-step streaming forward kernel)
+        int4* d_segs_f1 = nullptr;                               // ... and its segments: the whole interior
+        int   n_segs_f1 = 0;
         bool smem_s2 = false, smem_s2f = false, smem_t = false;
     };
     // Pair stepping of the backward pass (two-step kernel on the inner tiles).  Measured on the
@@ -335,6 +338,7 @@ struct rtm_ctx {
     // RTM_SEG_TILES = longest segment in 16-row tiles
     bool   stream2 = true;
     int    seg_tiles = 8;
+ bool   stream1_fwd = true;              // single-step forward pass by stream1_fwd_kernel (RTM_STREAM1_FWD=0: tile kernel)
     int    fuse2_fwd = 0;                   // forward pass in pairs: RTM_FUSE2_FWD=1 on (measured slower than single steps: the forward
                                             // step already runs at 74 % of the HBM peak and pays the pipeline's extra launches), default off
     CUtensorMap tmap_s_acc[4];              // rel1, rel2, sumS, sumR with a box of 128 x 8
@@ -423,7 +427,7 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
-    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); cudaFree(k.d_segs_ii); cudaFree(k.d_segs_ib); cudaFree(k.d_thin); }
+    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); cudaFree(k.d_segs_ii); cudaFree(k.d_segs_ib); cudaFree(k.d_thin); cudaFree(k.d_segs_f1); }
     cudaFree(c->store);
     cudaFree(c->d_ring_coef); cudaFree(c->d_ring_meta);
     for (auto& f : c->field) cudaFree(f);
@@ -571,6 +575,7 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     if (const char* e = std::getenv("RTM_RING2")) c->ring2 = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_RING2_FWD")) c->ring2_fwd = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_FUSE2_FWD")) c->fuse2_fwd = std::atoi(e) != 0 ? 1 : 0;
+    if (const char* e = std::getenv("RTM_STREAM1_FWD")) c->stream1_fwd = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_SEG_TILES")) c->seg_tiles = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RTM_RING_INTERLEAVE")) c->ring_interleave = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_RING_SPREAD")) c->ring_spread = std::atoi(e);
@@ -681,7 +686,7 @@ static int prepare_ls(rtm_ctx* c)
 static int prepare_classes(rtm_ctx* c)
 {
     const Geo& G = c->G;
-    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); cudaFree(k.d_segs_ii); cudaFree(k.d_segs_ib); cudaFree(k.d_thin); }
+    for (auto& k : c->classes) { cudaFree(k.d_tiles_f); cudaFree(k.d_tiles_b); cudaFree(k.d_tiles_ii); cudaFree(k.d_tiles_ib); cudaFree(k.d_tiles_bf); cudaFree(k.d_segs_ii); cudaFree(k.d_segs_ib); cudaFree(k.d_thin); cudaFree(k.d_segs_f1); }
     c->classes.clear();
     const int nf = G.ntx * G.ntz_f, nb = G.ntx * G.ntz_b;
     struct Lists { std::vector<int> fwd, bwd, ii, ib, frame; };
@@ -835,6 +840,21 @@ static int prepare_classes(rtm_ctx* c)
                     if (!rc) rc = encode_tmap(c, &k.tmap_t_row[i], c->field[i], 0, Thin<4>::ROW_H, 0, Thin<4>::ROW_W);
                     if (!rc) rc = encode_tmap(c, &k.tmap_t_col[i], c->field[i], 0, Thin<4>::COL_H, 0, Thin<4>::COL_W);
                     if (rc) return rc;
+                }
+                {   // single-step streaming forward kernel: every interior column, blocks of 8 rows from the first interior row
+                    const int ncol1 = (G.mod_NX + kTX - 1) / kTX, nblk1 = (G.mod_NZ + T::BR - 1) / T::BR;
+                    std::vector<int4> f1;
+                    for (int col = 0; col < ncol1; ++col) {
+                        const int pieces = (nblk1 + seg_blocks - 1) / seg_blocks;
+                        for (int p = 0, b = 0; p < pieces; ++p) {
+                            const int len = nblk1 / pieces + (p < nblk1 % pieces ? 1 : 0);
+                            f1.push_back(make_int4(G.N2 + col * kTX, G.N2 + b * T::BR, len, 0));
+                            b += len;
+                        }
+                    }
+                    if (int rc = up4(f1, &k.d_segs_f1, &k.n_segs_f1)) return rc;
+                    for (int i = 0; i < rtm_ctx::kFields; ++i)
+                        if (int rc = encode_tmap(c, &k.tmap_s_own[i], c->field[i], 0, T::BR, 0, kTX)) return rc;
                 }
                 k.stream_mode = true;
             }
@@ -1161,6 +1181,22 @@ static int dispatch_fwd(rtm_ctx* c, int ns, int buf, int p0buf, FwdArgs a, bool 
         CK(cudaStreamWaitEvent(c->aux[1], c->fork_ev, 0));
         if (int rc = launch_ring<false>(c, c->aux[1], ns, buf, p0buf, ring_args_fwd(c, a))) return rc;
         CK(cudaEventRecord(c->join_ev[1], c->aux[1]));
+        if (c->stream1_fwd && c->classes.size() == 1 && c->classes[0].stream_mode && c->classes[0].n_segs_f1 > 0) {
+            // the interior by the single-step streaming kernel
+            rtm_ctx::TileClass& k = c->classes[0];
+            StrmArgs sa{};
+            sa.Ak[0] = a.P2; sa.src = a.src; sa.wavelet_a = a.wavelet; sa.k = a.k; sa.nshots = ns;
+            sa.segs = k.d_segs_f1; sa.nseg = k.n_segs_f1; sa.fd_nseg = make_fastdiv(k.n_segs_f1);
+            sa.gather = a.gather; sa.xend = c->G.NX - c->G.N2; sa.zend = c->G.NZ - c->G.N2;
+            if (!c->dry) {
+                Strm1Maps tm1;
+                tm1.cur = k.tmap_s_prev[buf]; tm1.prev = k.tmap_s_own[p0buf];
+                ++c->nlaunch;
+                stream1_fwd_kernel<4><<<(unsigned)(k.n_segs_f1 * ns), Strm1<4>::kThreadsS, Strm1<4>::bytes(), c->stream>>>(tm1, c->G, sa);
+            }
+            CK(cudaStreamWaitEvent(c->stream, c->join_ev[1], 0));
+            return RTM_OK;
+        }
         const bool ls0 = c->G.iLSTE == 0;
         int rc = fork_join(c, [&](rtm_ctx::TileClass& k, cudaStream_t st, bool) -> int {
             a.do_ring = 0;

@@ -377,6 +377,122 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
 }
 
 // ------------------------------------------------------------------------------------
+// The forward pass, one slot per pass, in the same streaming form -- `stream1_fwd_kernel`.
+//
+// The forward pass gains nothing from two slots per pass (one field leaves too little arithmetic per block to pay
+// for the second phase and its barrier, and the pair pipeline adds ring and thin-frame launches), but the tile
+// kernel's per-CTA TMA wait and instruction-bound row loop make it clock-sensitive: under the 1 kW power cap of a
+// full-length run it falls from 142 to 154-158 us per step.  Here a CTA marches down a column segment of the WHOLE
+// interior (no thin frame: single steps need none): the producer warp keeps 8 rows of the current field (box 136 x 8,
+// ring of 3 slots + copy as above) and 8 x 128 of the previous field one block ahead; consumer warp w evaluates row w
+// of every block and stores it.  No warp depends on another warp's results, so the only synchronisation is with the
+// TMA engine.  Add_Con :82-114 (double final sum, additive source, gather recording).
+// ------------------------------------------------------------------------------------
+template <int RP> struct Strm1 {
+    static constexpr int BR = 8, NSLOT = 3, RING = NSLOT * BR + BR;
+    static constexpr int W1 = kTX + 2 * RP;
+    static constexpr int CUR_BLK = BR * W1 * 4, P0_BLK = BR * kTX * 4, CUR_RING = RING * W1 * 4;
+    static constexpr int kThreadsS = 32 * (BR + 1);
+    static_assert(CUR_BLK % 128 == 0 && CUR_RING % 128 == 0, "TMA destinations");
+    __host__ __device__ static constexpr int bytes() { return CUR_RING + NSLOT * P0_BLK + 64; }
+};
+struct Strm1Maps { CUtensorMap cur, prev; };   // boxes (128+2RP) x 8 and 128 x 8
+
+#ifndef RTM_STRM1_MINB
+#define RTM_STRM1_MINB 4
+#endif
+template <int RP>
+__global__ void __launch_bounds__(Strm1<RP>::kThreadsS, RTM_STRM1_MINB)
+stream1_fwd_kernel(const __grid_constant__ Strm1Maps tm, const __grid_constant__ Geo G, const StrmArgs a)
+{
+    using T = Strm1<RP>;
+    constexpr int BR = T::BR, W1 = T::W1, COPY = T::NSLOT * BR;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float*    cur  = reinterpret_cast<float*>(smem_raw);                   // [RING][W1]
+    float*    p0s  = reinterpret_cast<float*>(smem_raw + T::CUR_RING);     // [NSLOT][BR][kTX]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + T::CUR_RING + T::NSLOT * T::P0_BLK);
+    uint64_t* done = full + 3;
+    const int  shot = fast_div(blockIdx.x, a.fd_nseg);
+    const int4 sg   = __ldg(a.segs + (blockIdx.x - shot * a.nseg));
+    const int  x0 = sg.x, z0 = sg.y, n = sg.z;
+    const int  tid = threadIdx.x, lane = tid & 31;
+    const int  warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const long long so = (long long)shot * G.shot_stride + G.padL;
+    const int2 src = a.src[shot];
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) mbar_init(full + i, 1);
+        for (int i = 0; i < 2; ++i) mbar_init(done + i, BR);
+    }
+    __syncthreads();
+    // stage s: current-field rows [z0-RP+8s, +8) (+ the copy when it lands in slot 0), previous-field rows of out block s-1
+    auto issue = [&](int s) {
+        const int slot = s % 3;
+        uint64_t* bar = full + slot;
+        mbar_expect_tx(bar, T::CUR_BLK * (slot == 0 ? 2 : 1) + (s >= 1 ? T::P0_BLK : 0));
+        const int xc = G.padL + x0 - RP, zc = z0 - RP + BR * s;
+        tma_load_3d(cur + slot * BR * W1, &tm.cur, bar, xc, zc, shot);
+        if (slot == 0) tma_load_3d(cur + 3 * BR * W1, &tm.cur, bar, xc, zc, shot);
+        if (s >= 1) tma_load_3d(p0s + slot * BR * kTX, &tm.prev, bar, xc + RP, z0 + BR * (s - 1), shot);
+    };
+    if (warp == BR) {   // producer warp
+        if (lane == 0) {
+            issue(0); issue(1);
+            if (n >= 2) issue(2);
+            for (int i = 1; i + 2 <= n; ++i) {
+                mbar_wait_b(done + ((i - 1) & 1), ((i - 1) >> 1) & 1);
+                issue(i + 2);
+            }
+        }
+        return;
+    }
+    const LsTable T0{};
+    const int x = x0 + 4 * lane;
+    const int zlast = min(z0 + BR * n, a.zend);
+    const size_t rowstep = (size_t)BR * G.pitch;
+    int z = z0 + warp;
+    const float* pav = G.avel + G.padL + (size_t)z * G.pitch + x;
+    size_t soz = (size_t)so + (size_t)z * G.pitch + x;
+    const bool colok = x < a.xend;
+    float4 av4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (colok && z < zlast) av4 = __ldg(reinterpret_cast<const float4*>(pav));
+    int slot_i = 0, slot_s = 1;
+    for (int i = 0; i < n; ++i, z += BR, pav += rowstep, soz += rowstep) {
+        const int s = i + 1;
+        const float4 avc = av4;
+        if (i + 1 < n && colok && z + BR < zlast) av4 = __ldg(reinterpret_cast<const float4*>(pav + rowstep));
+        if (i == 0) mbar_wait_b(full + 0, 0);
+        mbar_wait_b(full + slot_s, (s / 3) & 1);
+        if (colok && z < zlast) {
+            int rc = warp < RP ? slot_i * BR + warp + RP : slot_s * BR + warp - RP;
+            if (rc < RP) rc += COPY;
+            float av[4], w1[4], p1[4], p0[4], o[4];
+            unpack(avc, av);
+            stencil_row<RP, false, W1>(G, cur + rc * W1 + RP + 4 * lane, G.nfdmax, T0, make_uint2(0u, 0u), w1, p1);
+            unpack(*reinterpret_cast<const float4*>(p0s + (slot_s * BR + warp) * kTX + 4 * lane), p0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = finish_double(av[q], w1[q], p1[q], p0[q]);
+            if (z == src.x && src.y >= x && src.y < x + 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (x + q == src.y) o[q] = __fadd_rn(o[q], a.wavelet_a);
+            }
+            store4c(a.Ak[0] + soz, o, x, 0, a.xend);
+            if (a.gather && z == G.s_z) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = x + q < a.xend ? data_index(G, z, x + q) : -1;
+                    if (j >= 0) a.gather[((size_t)shot * G.NT + a.k) * G.n + j] = o[q];
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(done + (i & 1));
+        slot_i = slot_s;
+        slot_s = slot_s == 2 ? 0 : slot_s + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // The thin frame: the RP interior cells next to the absorbing ring.  They cannot advance two slots per
 // pass (slot k-1 there needs the ring's one-way solution of slot k), so they -- and only they, not the
 // 128 x 16 tiles around them as in the tile form -- are stepped singly, between the two-step passes of
