@@ -338,7 +338,9 @@ struct rtm_ctx {
     // RTM_SEG_TILES = longest segment in 16-row tiles
     bool   stream2 = true;
     int    seg_tiles = 8;
- bool   stream1_fwd = true;              // single-step forward pass by stream1_fwd_kernel (RTM_STREAM1_FWD=0: tile kernel)
+    bool   stream1_fwd = false;             // single-step forward pass by stream1_fwd_kernel (RTM_STREAM1_FWD=1).  Measured slower than the
+                                            // tile kernel (156 vs 143 us per step: 70 % issue-bound, one row of one field per warp and block
+                                            // does not amortise the block overhead), so off by default
     int    fuse2_fwd = 0;                   // forward pass in pairs: RTM_FUSE2_FWD=1 on (measured slower than single steps: the forward
                                             // step already runs at 74 % of the HBM peak and pays the pipeline's extra launches), default off
     CUtensorMap tmap_s_acc[4];              // rel1, rel2, sumS, sumR with a box of 128 x 8

@@ -387,6 +387,9 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
 // ring of 3 slots + copy as above) and 8 x 128 of the previous field one block ahead; consumer warp w evaluates row w
 // of every block and stores it.  No warp depends on another warp's results, so the only synchronisation is with the
 // TMA engine.  Add_Con :82-114 (double final sum, additive source, gather recording).
+// Measured (profiles/r2_c9_*): bit-exact, but 134 us per 32-shot step against 124 us for the tile kernel's interior
+// launch -- 70 % of the issue slots busy: one row of one field per warp and block does not amortise the per-block
+// waits and address work the way the tile kernel's 4-row loop does.  Kept behind RTM_STREAM1_FWD=1.
 // ------------------------------------------------------------------------------------
 template <int RP> struct Strm1 {
     static constexpr int BR = 8, NSLOT = 3, RING = NSLOT * BR + BR;
