@@ -346,8 +346,10 @@ struct rtm_ctx {
     CUtensorMap tmap_s_acc[4];              // rel1, rel2, sumS, sumR with a box of 128 x 8
     // the absorbing ring as a kernel of its own (rtm_ring.cuh; Taylor operator): RTM_RING2=0 keeps ring_tile<> everywhere,
     // RTM_RING2_FWD=0 keeps it in the single-step forward launches
-    bool   ring2 = true, ring2_fwd = true, ring_ready = false, smem_ring = false;
+    bool   ring2 = true, ring2_fwd = true, ring2_bwd = true, ring_ready = false;
     RingGeo rgeo{};
+    cudaStream_t ring_stream = nullptr;     // the ring kernel runs next to the interior launch of a single step
+    cudaEvent_t  ring_fork = nullptr, ring_join = nullptr;
     float4* d_ring_coef = nullptr;
     int*    d_ring_meta = nullptr;
     CUtensorMap tmap_r_p1b[kFields], tmap_r_p1s[kFields], tmap_r_p0b[kFields], tmap_r_p0s[kFields], tmap_r_avb, tmap_r_avs;
@@ -448,6 +450,9 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     for (auto& e : c->join_ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_ii) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_ib) if (e) cudaEventDestroy(e);
+    if (c->ring_stream) cudaStreamDestroy(c->ring_stream);
+    if (c->ring_fork) cudaEventDestroy(c->ring_fork);
+    if (c->ring_join) cudaEventDestroy(c->ring_join);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -576,6 +581,7 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     if (const char* e = std::getenv("RTM_STREAM2")) c->stream2 = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_RING2")) c->ring2 = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_RING2_FWD")) c->ring2_fwd = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RTM_RING2_BWD")) c->ring2_bwd = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_FUSE2_FWD")) c->fuse2_fwd = std::atoi(e) != 0 ? 1 : 0;
     if (const char* e = std::getenv("RTM_STREAM1_FWD")) c->stream1_fwd = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_SEG_TILES")) c->seg_tiles = std::max(1, std::atoi(e));
@@ -603,6 +609,9 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
         CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         for (int i = 0; i < 3; ++i) CKC(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, i == 2 ? hi : lo));
     }
+    CKC(cudaStreamCreateWithFlags(&c->ring_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&c->ring_fork, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&c->ring_join, cudaEventDisableTiming));
     for (auto& e : c->ev_ii) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : c->ev_ib) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
@@ -879,7 +888,7 @@ static int prepare_classes(rtm_ctx* c)
     }
     // ring kernel (rtm_ring.cuh): per-cell one-way coefficients of this model, tensor maps of the tile boxes
     c->ring_ready = false;
-    if (c->ring2 && !ls && c->have_model && c->have_op) {
+    if (c->ring2 && c->have_model && c->have_op) {
         c->rgeo = make_ring_geo(G, G.mmax, c->RP);
         const int nring = c->rgeo.ntiles;
         cudaDeviceProp prop;
@@ -1135,37 +1144,34 @@ template <class Launch> static int fork_join(rtm_ctx* c, Launch launch, cudaStre
 // buf: index of the field buffer holding slot k-1, or -1 for the store-all slab
 // The ring tiles of one slot by ring_kernel: cur / prev = field buffers of the current / previous slot of the field that
 // carries the absorbing boundary (forward field; backward: receiver field).
+template <int RP, bool BWD, bool LS> static int launch_ring_t(rtm_ctx* c, cudaStream_t st, unsigned grid, int smem, const RingMaps& tm, const RingArgs& a)
+{
+    static thread_local int granted[64] = {0};   // per device: dynamic shared memory already granted to this instantiation
+    if (granted[c->device & 63] < smem) {
+        CK(cudaFuncSetAttribute(ring_kernel<RP, BWD, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        granted[c->device & 63] = smem;
+    }
+    if (c->dry) return RTM_OK;
+    ++c->nlaunch;
+    ring_kernel<RP, BWD, LS><<<grid, kThreads, smem, st>>>(tm, c->G, a);
+    return RTM_OK;
+}
 template <bool BWD> static int launch_ring(rtm_ctx* c, cudaStream_t st, int ns, int cur, int prev, RingArgs a)
 {
     const int smem = c->rgeo.smem_bytes();
-    if (!c->smem_ring) {
-        CK(cudaFuncSetAttribute(ring_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(ring_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(ring_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(ring_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(ring_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(ring_kernel<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(ring_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(ring_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        c->smem_ring = true;
-    }
-    const Geo& G = c->G;
-    const int nring = c->rgeo.ntiles;
     a.nshots = ns; a.rc = RingCoef{c->d_ring_coef, c->d_ring_meta}; a.rg = c->rgeo;
-    if (c->dry) return RTM_OK;
     RingMaps tm;
     tm.p1b = c->tmap_r_p1b[cur]; tm.p1s = c->tmap_r_p1s[cur]; tm.p0b = c->tmap_r_p0b[prev]; tm.p0s = c->tmap_r_p0s[prev];
     tm.avb = c->tmap_r_avb; tm.avs = c->tmap_r_avs;
-    ++c->nlaunch;
-    const unsigned grid = (unsigned)(nring * ns);
+    const unsigned grid = (unsigned)(c->rgeo.ntiles * ns);
+    const bool ls = c->G.iLSTE == 0;
     switch (c->RP) {
-    case 4:  ring_kernel<4, BWD><<<grid, kThreads, smem, st>>>(tm, G, a); break;
-    case 8:  ring_kernel<8, BWD><<<grid, kThreads, smem, st>>>(tm, G, a); break;
-    case 12: ring_kernel<12, BWD><<<grid, kThreads, smem, st>>>(tm, G, a); break;
-    case 16: ring_kernel<16, BWD><<<grid, kThreads, smem, st>>>(tm, G, a); break;
-    default: return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", c->RP);
+    case 4:  return ls ? launch_ring_t<4, BWD, true>(c, st, grid, smem, tm, a) : launch_ring_t<4, BWD, false>(c, st, grid, smem, tm, a);
+    case 8:  return ls ? launch_ring_t<8, BWD, true>(c, st, grid, smem, tm, a) : launch_ring_t<8, BWD, false>(c, st, grid, smem, tm, a);
+    case 12: return ls ? launch_ring_t<12, BWD, true>(c, st, grid, smem, tm, a) : launch_ring_t<12, BWD, false>(c, st, grid, smem, tm, a);
+    case 16: return ls ? launch_ring_t<16, BWD, true>(c, st, grid, smem, tm, a) : launch_ring_t<16, BWD, false>(c, st, grid, smem, tm, a);
     }
-    return RTM_OK;
+    return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", c->RP);
 }
 static RingArgs ring_args_fwd(rtm_ctx* c, const FwdArgs& f)
 {
@@ -1179,10 +1185,10 @@ static int dispatch_fwd(rtm_ctx* c, int ns, int buf, int p0buf, FwdArgs a, bool 
     if (c->ring_ready && buf >= 0 && (frame || c->ring2_fwd)) {
         // the ring by its own kernel: alone (frame step of the pair loop), or next to the interior launch on a side stream
         if (frame) return launch_ring<false>(c, serial ? serial : c->stream, ns, buf, p0buf, ring_args_fwd(c, a));
-        CK(cudaEventRecord(c->fork_ev, c->stream));
-        CK(cudaStreamWaitEvent(c->aux[1], c->fork_ev, 0));
-        if (int rc = launch_ring<false>(c, c->aux[1], ns, buf, p0buf, ring_args_fwd(c, a))) return rc;
-        CK(cudaEventRecord(c->join_ev[1], c->aux[1]));
+        CK(cudaEventRecord(c->ring_fork, c->stream));
+        CK(cudaStreamWaitEvent(c->ring_stream, c->ring_fork, 0));
+        if (int rc = launch_ring<false>(c, c->ring_stream, ns, buf, p0buf, ring_args_fwd(c, a))) return rc;
+        CK(cudaEventRecord(c->ring_join, c->ring_stream));
         if (c->stream1_fwd && c->classes.size() == 1 && c->classes[0].stream_mode && c->classes[0].n_segs_f1 > 0) {
             // the interior by the single-step streaming kernel
             rtm_ctx::TileClass& k = c->classes[0];
@@ -1196,7 +1202,7 @@ static int dispatch_fwd(rtm_ctx* c, int ns, int buf, int p0buf, FwdArgs a, bool 
                 ++c->nlaunch;
                 stream1_fwd_kernel<4><<<(unsigned)(k.n_segs_f1 * ns), Strm1<4>::kThreadsS, Strm1<4>::bytes(), c->stream>>>(tm1, c->G, sa);
             }
-            CK(cudaStreamWaitEvent(c->stream, c->join_ev[1], 0));
+            CK(cudaStreamWaitEvent(c->stream, c->ring_join, 0));
             return RTM_OK;
         }
         const bool ls0 = c->G.iLSTE == 0;
@@ -1211,7 +1217,7 @@ static int dispatch_fwd(rtm_ctx* c, int ns, int buf, int p0buf, FwdArgs a, bool 
             return rtm_fail(RTM_ERR_ARG, "unsupported operator radius %d", k.RP);
         });
         if (rc) return rc;
-        CK(cudaStreamWaitEvent(c->stream, c->join_ev[1], 0));
+        CK(cudaStreamWaitEvent(c->stream, c->ring_join, 0));
         return RTM_OK;
     }
     const bool ls = c->G.iLSTE == 0;
@@ -1252,11 +1258,11 @@ static int launch_stream_fwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st,
     stream2_kernel<4, false><<<(unsigned)(a.nseg * ns), T::kThreadsS, T::bytes(false), st>>>(tm, c->G, a);
     return RTM_OK;
 }
-template <bool STORE> static int dispatch_bwd_t(rtm_ctx* c, int ns, int s1, int r1, int s0, int r0, BwdArgs a, bool frame, cudaStream_t serial)
+template <bool STORE> static int dispatch_bwd_t(rtm_ctx* c, int ns, int s1, int r1, int s0, int r0, BwdArgs a, bool frame, cudaStream_t serial, bool no_ring = false)
 {
     const bool ls = c->G.iLSTE == 0;
     return fork_join(c, [&](rtm_ctx::TileClass& k, cudaStream_t st, bool first) -> int {
-        a.do_ring = first ? 1 : 0;
+        a.do_ring = (first && !no_ring) ? 1 : 0;
         switch (k.RP) {
         case 4:  return ls ? launch_bwd<4, true, STORE>(c, k, st, ns, s1, r1, s0, r0, a, frame) : launch_bwd<4, false, STORE>(c, k, st, ns, s1, r1, s0, r0, a, frame);
         case 8:  return ls ? launch_bwd<8, true, STORE>(c, k, st, ns, s1, r1, s0, r0, a, frame) : launch_bwd<8, false, STORE>(c, k, st, ns, s1, r1, s0, r0, a, frame);
@@ -1273,6 +1279,18 @@ static int dispatch_bwd(rtm_ctx* c, int ns, int s1, int r1, int s0, int r0, cons
         RingArgs r{};
         r.P2 = a.R2; r.SX = a.S2; r.src = a.src; r.inject = 0; r.k = a.k; r.st = a.st; r.seis = a.seis; r.sum_double = 0;
         return launch_ring<true>(c, serial ? serial : c->stream, ns, r1, r0, r);
+    }
+    if (!frame && !serial && c->ring_ready && c->ring2_bwd && !c->store_mode) {
+        // a single step of all tiles: the ring by its own kernel on a side stream, the interior tiles without ring CTAs
+        RingArgs r{};
+        r.P2 = a.R2; r.SX = a.S2; r.src = a.src; r.inject = 0; r.k = a.k; r.st = a.st; r.seis = a.seis; r.sum_double = 0;
+        CK(cudaEventRecord(c->ring_fork, c->stream));
+        CK(cudaStreamWaitEvent(c->ring_stream, c->ring_fork, 0));
+        if (int rc = launch_ring<true>(c, c->ring_stream, ns, r1, r0, r)) return rc;
+        CK(cudaEventRecord(c->ring_join, c->ring_stream));
+        if (int rc = dispatch_bwd_t<false>(c, ns, s1, r1, s0, r0, a, false, nullptr, true)) return rc;
+        CK(cudaStreamWaitEvent(c->stream, c->ring_join, 0));
+        return RTM_OK;
     }
     return c->store_mode ? dispatch_bwd_t<true>(c, ns, s1, r1, s0, r0, a, frame, serial) : dispatch_bwd_t<false>(c, ns, s1, r1, s0, r0, a, frame, serial);
 }

@@ -1,4 +1,4 @@
-// rtm_ring.cuh -- the hybrid absorbing ring as a kernel of its own (fixed-length operator).
+// rtm_ring.cuh -- the hybrid absorbing ring as a kernel of its own (both operators).
 //
 // ring_tile<> of rtm_kernels.cuh spends most of its instructions outside the arithmetic (round-1
 // attribution, profiles/r1_final_ring_attribution.txt: 40 % in the 4-byte cp.async fills with their
@@ -169,7 +169,7 @@ struct RingArgs {
 #define RTM_RING_MINB 4
 #endif
 
-template <int RP, bool BWD>
+template <int RP, bool BWD, bool LS>
 __global__ void __launch_bounds__(kThreads, RTM_RING_MINB)
 ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, const RingArgs a)
 {
@@ -242,7 +242,9 @@ ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, 
 
     // two-way update of the compute rectangle, one float4 group per thread and pass (the interior tiles' row stencil)
     {
-        const LsTable T0{};
+        LsTable T0{};   // adaptive operator: the packed global tables (as ring_tile<>), addressed by the cell's velocity bin
+        T0.ip = G.Index; T0.cp = G.c; T0.bmin = 0; T0.bmax = 0xffff; T0.staged = false;
+        const unsigned short* BN = G.bins + G.padL;
         const float* seis_row = BWD && a.seis ? a.seis + ((size_t)shot * G.NT + (a.k + 1)) * G.n : nullptr;
         int sh = 0;
         while ((1 << sh) < NG) ++sh;
@@ -251,7 +253,16 @@ ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, 
             if (g >= NG) continue;
             const int z = cz0 + lz, x = cx0 + 4 * g;
             float w1[4], p1[4], p0[4], av[4], val[4];
-            stencil_row<RP, false, 0>(G, s1 + (lz + R) * SP + 4 * g + RP, G.nfdmax, T0, make_uint2(0u, 0u), w1, p1, SP);
+            uint2 b4 = make_uint2(0u, 0u);
+            if (LS) {   // (cells of the compute rectangle outside the array: any valid bin, their values feed nobody)
+                const size_t row = (size_t)min(max(z, 0), NZ - 1) * G.pitch;
+                int xq[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) xq[q] = min(max(x + q, 0), NX - 1);
+                b4.x = (unsigned)__ldg(BN + row + xq[0]) | ((unsigned)__ldg(BN + row + xq[1]) << 16);
+                b4.y = (unsigned)__ldg(BN + row + xq[2]) | ((unsigned)__ldg(BN + row + xq[3]) << 16);
+            }
+            stencil_row<RP, LS, 0>(G, s1 + (lz + R) * SP + 4 * g + RP, G.nfdmax, T0, b4, w1, p1, SP);
             unpack(*reinterpret_cast<const float4*>(s0 + lz * CW + 4 * g), p0);
             unpack(*reinterpret_cast<const float4*>(sAv + lz * CW + 4 * g), av);
 #pragma unroll
