@@ -888,7 +888,11 @@ static int prepare_classes(rtm_ctx* c)
     }
     // ring kernel (rtm_ring.cuh): per-cell one-way coefficients of this model, tensor maps of the tile boxes
     c->ring_ready = false;
-    if (c->ring2 && c->have_model && c->have_op) {
+    // (measured with the adaptive operator, profiles/r2_c11_*: the ring on a side stream gains nothing in the forward pass and
+    //  loses 3-12 % in the backward pass, where its two-way phase gathers per-cell coefficients from the global tables next to
+    //  interior tiles that do the same; RTM_RING2_LS=1 enables it there anyway)
+    const bool ring_ls = std::getenv("RTM_RING2_LS") && std::atoi(std::getenv("RTM_RING2_LS")) != 0;
+    if (c->ring2 && (!ls || ring_ls) && c->have_model && c->have_op) {
         c->rgeo = make_ring_geo(G, G.mmax, c->RP);
         const int nring = c->rgeo.ntiles;
         cudaDeviceProp prop;
