@@ -411,7 +411,10 @@ def inproc_arm(args, w: Workload):
         [t.start() for t in th]
         [t.join() for t in th]
     par(setup)
+    devs = np.arange(N, dtype=np.int32)
+    R.lib().rtm_stack_reduce_prepare(R._i(devs), N)   # communicators created ahead, as the executable does next to its shot loop
     par(work, args.warmup, 0)
+    R.stack_reduce(engines)                           # warm-up reduce
     for e in engines:
         e.reset_stats()
         e.stack_reset()

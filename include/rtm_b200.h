@@ -131,6 +131,9 @@ int rtm_stack_reduce(rtm_ctx **ctxs, int nctx, float *up_sum, float *down_sum, i
  * loaded, or ncclCommInitAll / ncclReduce fail, it falls back to NVLink peer copies + a device add.
  * Backend of the last call: "nccl", "p2p" or "none". */
 const char *rtm_stack_reduce_backend(void);
+/* Creates the in-process NCCL communicators for `devices` ahead of time (ncclCommInitAll takes seconds; they are cached
+ * and reused by rtm_stack_reduce over the same devices).  Optional; a failure only means the reduce will try again. */
+int rtm_stack_reduce_prepare(const int *devices, int n);
 /* sum/nrec, optional up/down normalisation (kernel.cu:1042-1059); in/out [mod_NX][mod_NZ] */
 int rtm_stack_finalize(const float *up_sum, const float *down_sum, int nrec, int iNorm,
                        size_t ncell, float *image, float *illum);

@@ -50,7 +50,7 @@ class Stats(C.Structure):
 ABI_SYMBOLS = [
     "rtm_last_error", "rtm_version", "rtm_create", "rtm_destroy", "rtm_set_model", "rtm_set_operator",
     "rtm_forward", "rtm_migrate", "rtm_migrate_raw", "rtm_resample_device", "rtm_upload_gathers", "rtm_migrate_resident", "rtm_stack_reset",
-    "rtm_stack_get", "rtm_stack_device", "rtm_stack_reduce", "rtm_stack_reduce_backend", "rtm_stack_finalize", "rtm_get_stats",
+    "rtm_stack_get", "rtm_stack_device", "rtm_stack_reduce", "rtm_stack_reduce_backend", "rtm_stack_reduce_prepare", "rtm_stack_finalize", "rtm_get_stats",
     "rtm_reset_stats", "rtm_device_count", "rtm_memory_estimate", "rtm_device_free_bytes", "rtm_host_alloc_pinned", "rtm_host_free_pinned", "rtm_store_all_active", "rtm_ricker", "rtm_source_row", "rtm_derived",
     "rtm_pad_velocity", "rtm_velocity_bins", "rtm_taylor_operator", "rtm_ls_operator",
     "rtm_ls_coefficients", "rtm_resample", "rtm_segy_decode", "rtm_segy_encode", "rtm_segy_info",
@@ -88,6 +88,7 @@ def lib():
     L.rtm_stack_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _ip]
     L.rtm_stack_reduce.argtypes = [C.POINTER(C.c_void_p), C.c_int, _fp, _fp, _ip]
     L.rtm_stack_reduce_backend.restype = C.c_char_p
+    L.rtm_stack_reduce_prepare.argtypes = [_ip, C.c_int]
     L.rtm_stack_finalize.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_size_t, _fp, _fp]
     L.rtm_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.rtm_reset_stats.argtypes = [C.c_void_p]

@@ -325,8 +325,16 @@ static int run_driver(const char* run_file, int ngpu, int batch, int verbose)
         workers[i].count  = c.nrec / ngpu + (i < c.nrec % ngpu ? 1 : 0);
         first += workers[i].count;
     }
+    // the communicators of the final reduce are created next to the shot loop (ncclCommInitAll takes seconds)
+    std::thread comm_thread;
+    if (ngpu > 1) {
+        std::vector<int> devs(ngpu);
+        for (int i = 0; i < ngpu; ++i) devs[i] = i;
+        comm_thread = std::thread([devs] { rtm_stack_reduce_prepare(devs.data(), (int)devs.size()); });
+    }
     for (auto& w : workers) threads.emplace_back(run_worker, std::cref(job), std::ref(w));
     for (auto& t : threads) t.join();
+    if (comm_thread.joinable()) comm_thread.join();
     int rc = 0;
     for (auto& w : workers) {
         if (verbose) for (auto& s : w.log) std::fputs(s.c_str(), stdout);

@@ -12,6 +12,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -55,7 +56,44 @@ Nccl* load_nccl(std::string& why)
 #undef SYM
     return &n;
 }
+
+// One communicator set per process, created once (ncclCommInitAll takes seconds) and reused by every reduce over the
+// same devices; rtm_stack_reduce_prepare lets a caller create it ahead of time, next to its other start-up work.
+struct CommCache {
+    std::mutex mu;
+    std::vector<int> devs;
+    std::vector<ncclComm_t> comms;
+};
+CommCache& cache() { static CommCache c; return c; }
+// returns "" on success, the reason otherwise; comms valid while the cache lock is held by the caller
+std::string ensure_comms(Nccl* n, const std::vector<int>& devs, std::vector<ncclComm_t>** out)
+{
+    CommCache& c = cache();
+    if (c.devs != devs || c.comms.empty()) {
+        for (auto cm : c.comms) if (cm) n->CommDestroy(cm);
+        c.comms.assign(devs.size(), nullptr);
+        c.devs.clear();
+        const ncclResult_t r = n->CommInitAll(c.comms.data(), (int)devs.size(), devs.data());
+        if (r) { c.comms.clear(); return std::string("ncclCommInitAll: ") + n->GetErrorString(r); }
+        c.devs = devs;
+    }
+    *out = &c.comms;
+    return "";
+}
 }  // namespace
+
+extern "C" int rtm_stack_reduce_prepare(const int* devices, int n)
+{
+    if (!devices || n < 2) return RTM_OK;
+    std::string why;
+    Nccl* nc = load_nccl(why);
+    if (!nc) return rtm_fail(RTM_ERR_NCCL, "rtm_stack_reduce_prepare: %s", why.c_str());
+    std::lock_guard<std::mutex> l(cache().mu);
+    std::vector<ncclComm_t>* comms = nullptr;
+    why = ensure_comms(nc, std::vector<int>(devices, devices + n), &comms);
+    if (!why.empty()) return rtm_fail(RTM_ERR_NCCL, "rtm_stack_reduce_prepare: %s", why.c_str());
+    return RTM_OK;
+}
 
 extern "C" int rtm_ctx_device(rtm_ctx* ctx);
 int rtm_stack_reduce_p2p(rtm_ctx** ctxs, int nctx, float* out);  // rtm_engine.cu
@@ -90,11 +128,12 @@ extern "C" int rtm_stack_reduce(rtm_ctx** ctxs, int nctx, float* up_sum, float* 
     bool done = false;
     Nccl* n = want_p2p ? nullptr : load_nccl(why);
     if (n) {   // one ncclReduce over NVLink (ncclCommInitAll: all contexts live in this process)
-        std::vector<ncclComm_t> comms(nctx, nullptr);
-        ncclResult_t r = n->CommInitAll(comms.data(), nctx, devs.data());
-        if (r) {
-            why = std::string("ncclCommInitAll: ") + n->GetErrorString(r);
-        } else {
+        std::lock_guard<std::mutex> lock(cache().mu);
+        std::vector<ncclComm_t>* pc = nullptr;
+        why = ensure_comms(n, devs, &pc);
+        if (why.empty()) {
+            std::vector<ncclComm_t>& comms = *pc;
+            ncclResult_t r = 0;
             n->GroupStart();
             for (int i = 0; i < nctx && !r; ++i) {
                 cudaSetDevice(devs[i]);
@@ -106,8 +145,11 @@ extern "C" int rtm_stack_reduce(rtm_ctx** ctxs, int nctx, float* up_sum, float* 
                 cudaSetDevice(devs[i]);
                 if (cudaStreamSynchronize(0) != cudaSuccess && !r) r = 1;
             }
-            for (auto c : comms) if (c) n->CommDestroy(c);
-            if (r) why = std::string("ncclReduce: ") + n->GetErrorString(r);
+            if (r) {   // a failed communicator is not reused
+                why = std::string("ncclReduce: ") + n->GetErrorString(r);
+                for (auto c : comms) if (c) n->CommDestroy(c);
+                cache().comms.clear(); cache().devs.clear();
+            }
             else { done = true; g_backend = "nccl"; }
         }
     }
