@@ -42,7 +42,7 @@ struct RingGeo {            // per context
     FastDiv fd_ntiles;
     int cells;              // cells per tile in the coefficient arrays (N2 * 126, rounded up to 4)
     int n1, nc;             // floats reserved for the halo box / for each compute-rectangle array (both tile kinds, 128-byte multiples)
-    __host__ __device__ int smem_bytes() const { return (n1 + 3 * nc + 5 * cells) * 4 + 16; }
+    __host__ __device__ int smem_bytes() const { return (n1 + 3 * nc) * 4 + 16; }
 };
 __host__ inline RingGeo make_ring_geo(const Geo& G, int R, int RP)
 {
@@ -185,9 +185,7 @@ ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, 
     float* s0  = s1 + a.rg.n1;                         // ch x CW previous field
     float* sAv = s0 + a.rg.nc;                         // ch x CW velocity factor
     float* s2  = sAv + a.rg.nc;                        // ch x CW unblended two-way result
-    float4* sCf = reinterpret_cast<float4*>(s2 + a.rg.nc);          // per-cell coefficients and meta words of this tile
-    int*    sMt = reinterpret_cast<int*>(sCf + a.rg.cells);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sMt + a.rg.cells);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s2 + a.rg.nc);
     const int tid = threadIdx.x;
     const long long so = (long long)shot * G.shot_stride + G.padL;
 
@@ -204,11 +202,12 @@ ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, 
     const int oh = o.zb - o.za, ow = o.xb - o.xa, ncell = oh * ow;
     const float4* cfp = a.rc.coef + (size_t)tile * a.rg.cells;
     const int*    mtp = a.rc.meta + (size_t)tile * a.rg.cells;
-    for (int c = tid; c < ncell; c += kThreads) {   // asynchronous copies, consumed after the two-way phase
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sCf + c)), "l"(cfp + c) : "memory");
-        cp_async4(reinterpret_cast<float*>(sMt + c), reinterpret_cast<const float*>(mtp + c));
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    // (the per-cell coefficients and meta words are read straight from global memory in the one-way loop, one cell ahead:
+    //  they are per-model constants, L2-resident and coalesced; staging them cost 25 KB of shared memory per CTA, i.e. one
+    //  resident ring CTA instead of three next to a streaming CTA)
+    float4 cfn = make_float4(0.f, 0.f, 0.f, 0.f);
+    int    mn  = 0;
+    if (tid < ncell) { cfn = __ldg(cfp + tid); mn = __ldg(mtp + tid); }
     const int2 src = a.src[shot];
     const size_t slot = (size_t)shot * G.NT + a.k;
     const size_t sxs = slot * G.nfdmax * G.mod_NX, szs = slot * G.nfdmax * G.mod_NZ;   // this slot inside up/dw and lf/rt
@@ -286,7 +285,6 @@ ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, 
             *reinterpret_cast<float4*>(s2 + lz * CW + 4 * g) = make_float4(val[0], val[1], val[2], val[3]);
         }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     // one-way solution, blend, stores.  Thread t takes cells t, t + 256, ...: (oz, ox) advance without divisions
@@ -299,8 +297,9 @@ ring_kernel(const __grid_constant__ RingMaps tm, const __grid_constant__ Geo G, 
     int oz = tid / ow, ox = tid - oz * ow;
     for (int c = tid; c < ncell; c += kThreads, oz += dq, ox += dr) {
         if (ox >= ow) { ox -= ow; ++oz; }
-        const float4 cf = sCf[c];
-        const int    m  = sMt[c];
+        const float4 cf = cfn;
+        const int    m  = mn;
+        if (c + kThreads < ncell) { cfn = __ldg(cfp + c + kThreads); mn = __ldg(mtp + c + kThreads); }
         const int lz = o.za + oz - cz0, lx = o.xa + ox - cx0;  // position in the compute rectangle
         const int kind = m & 7;
         const float* q2 = s2 + lz * CW + lx;

@@ -112,8 +112,11 @@ __device__ __forceinline__ void store4c(float* dst, const float (&o)[4], int x, 
 #define RTM_STRM_MINB_F 3
 #endif
 
+#ifndef RTM_STRM_MAXREG_B
+#define RTM_STRM_MAXREG_B 88   // 2 CTAs x 320 threads x 88 registers leave 9216 registers = one thin_frame CTA next to them
+#endif
 template <int RP, bool BWD>
-__global__ void __launch_bounds__(Strm<RP>::kThreadsS, BWD ? RTM_STRM_MINB_B : RTM_STRM_MINB_F)
+__global__ void __launch_bounds__(Strm<RP>::kThreadsS, BWD ? RTM_STRM_MINB_B : RTM_STRM_MINB_F) __maxnreg__(BWD ? RTM_STRM_MAXREG_B : 64)
 stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo G, const StrmArgs a)
 {
     using T = Strm<RP>;
