@@ -67,3 +67,69 @@ def test_fast_div_and_block_roles(tmp_path):
     assert cc.returncode == 0, cc.stderr[-2000:]
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr[-500:])
+
+
+RING_SRC = r"""
+#include "rtm_ring.cuh"
+#include <cstdio>
+#include <vector>
+using namespace rtmk;
+int main()
+{
+    // ring_kernel's tiling: every ring cell lies in exactly one tile's output rectangle; every compute rectangle starts on a
+    // 16-byte boundary in global memory (TMA box) and holds the output rectangle grown by one cell; a tile's cells fit the
+    // per-tile stride of the coefficient arrays; the boxes fit the shared-memory layout
+    const int grids[][3] = {{2301, 751, 10}, {677, 210, 10}, {4096, 4096, 12}, {120, 100, 10}, {60, 400, 10}, {333, 150, 16},
+                            {333, 150, 3}, {700, 280, 10}, {20000, 64, 10}, {90, 70, 12}, {40, 150, 10}, {4096, 512, 12}};
+    for (auto& g3 : grids)
+        for (int R : {1, 4, 5, 8, 12}) {
+            Geo G{};
+            G.mod_NX = g3[0]; G.mod_NZ = g3[1]; G.N2 = g3[2];
+            if (R > G.N2) continue;
+            const int RP = (R + 3) / 4 * 4;
+            G.NX = G.mod_NX + 2 * G.N2; G.NZ = G.mod_NZ + 2 * G.N2;
+            G.padL = (32 - G.N2 % 32) % 32;
+            if (G.padL + G.N2 < RP) G.padL += 32;
+            G.pitch = (G.padL + G.NX + 4 + 31) / 32 * 32;
+            const RingGeo rg = make_ring_geo(G, R, RP);
+            std::vector<int> hit((size_t)G.NZ * G.NX, 0);
+            for (int t = 0; t < rg.ntiles; ++t) {
+                int cz0, cx0;
+                const RingRect o = ring2_rect(G, rg, t, &cz0, &cx0);
+                const bool band = t < 2 * rg.nband;
+                const int ch = band ? rg.chB : rg.chS, cw = band ? rg.cwB : rg.cwS, sp = band ? rg.spB : rg.spS;
+                if ((G.padL + cx0) % 4 != 0) { std::printf("align %d %d %d tile %d\n", g3[0], g3[1], g3[2], t); return 1; }
+                if (o.za >= o.zb || o.xa >= o.xb) continue;   // (an empty trailing tile)
+                if (o.za - 1 < cz0 || o.zb + 1 > cz0 + ch || o.xa - 1 < cx0 || o.xb + 1 > cx0 + cw) { std::printf("grow %d %d %d tile %d\n", g3[0], g3[1], g3[2], t); return 2; }
+                if ((o.zb - o.za) * (o.xb - o.xa) > rg.cells) { std::printf("cells\n"); return 3; }
+                if ((ch + 2 * R) * sp > rg.n1 || ch * cw > rg.nc || sp != cw + 2 * RP) { std::printf("smem\n"); return 4; }
+                for (int z = o.za; z < o.zb; ++z)
+                    for (int x = o.xa; x < o.xb; ++x) ++hit[(size_t)z * G.NX + x];
+            }
+            for (int z = 0; z < G.NZ; ++z)
+                for (int x = 0; x < G.NX; ++x) {
+                    const bool ring = z < G.N2 || z >= G.NZ - G.N2 || x < G.N2 || x >= G.NX - G.N2;
+                    if (hit[(size_t)z * G.NX + x] != (ring ? 1 : 0)) { std::printf("cover %d %d %d at %d %d: %d\n", g3[0], g3[1], g3[2], z, x, hit[(size_t)z * G.NX + x]); return 5; }
+                }
+        }
+    std::printf("ok\n");
+    return 0;
+}
+"""
+
+
+def test_ring_kernel_tiling(tmp_path):
+    nvcc = shutil.which("nvcc")
+    if not nvcc:
+        pytest.skip("nvcc not on PATH")
+    src = tmp_path / "ringgeo.cu"
+    src.write_text(RING_SRC)
+    exe = tmp_path / "ringgeo"
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", "-I",
+           str(ROOT / "rtm_gpu_b200" / "csrc"), "-o", str(exe), str(src), "-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+    cc = subprocess.run(cmd, capture_output=True, text=True)
+    if cc.returncode != 0:
+        cc = subprocess.run(cmd, capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr[-2000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
