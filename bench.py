@@ -6,7 +6,7 @@ Workload (BASELINE.json configs[1]): Marmousi-shaped synthetic model 2301 x 751,
 NT = 7501 (3 s), 2301 data traces at the surface, 64 virtual sources.  A "step" is the full
 migration (forward modelling with boundary-strip saving, reverse-time reconstruction +
 receiver back-propagation + imaging, per-shot image filter and stacking) of one batch of
-SHOTS_PER_STEP = 32 shots (two steps cover the 64 shots; the default K=4 steps migrate them twice).
+SHOTS_PER_STEP = 64 shots (one step = the configuration's 64 shots in one batch; default K=2 steps).
 
   value  Mcell-updates/s, whole job, inputs resident in HBM (CUDA events inside the library,
          on the stream the kernels run on; max over ranks)
@@ -44,7 +44,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-SHOTS_PER_STEP = 32   # shots per launch: 8 -> 267, 16 -> 279, 32 -> 286 Gcell-updates/s at NT=301 (profiles/README.md)
+SHOTS_PER_STEP = 64   # shots per launch (round 1: 8 -> 267, 16 -> 279, 32 -> 286; round 2: 32 -> 329.6, 48 -> 334.3, 64 -> 338.7 Gcell-updates/s at NT=301)
 TOTAL_SHOTS = 64
 
 
@@ -69,7 +69,7 @@ class Workload:
     src_depth_m = 8.0                    # virtual sources at depth index 2
     total_shots = TOTAL_SHOTS
     shots_per_step = SHOTS_PER_STEP
-    default_steps = 4
+    default_steps = 2
     vertical_sources = False             # True: RVSP geometry, sources down a well at column r_x
 
     def __init__(self, scale_nt: int | None = None):
@@ -448,7 +448,7 @@ def inproc_arm(args, w: Workload):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 4 for c2; per-config otherwise)")
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 2 for c2; per-config otherwise)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", help="c2 (default, BASELINE configs[1]) | c3 | c4 | c5[:R][:taylor]")
