@@ -368,6 +368,11 @@ struct rtm_ctx {
     int    nvel = 0;
     float* d_c = nullptr;
     int*   d_Index = nullptr;
+    float* d_ls_rows = nullptr;             // adaptive operator no longer than 4: padded coefficient rows [nvel][8] + lengths (streaming kernels)
+    int*   d_ls_len = nullptr;
+    bool   ring_par = false;                // stream mode: ring launches of the pair loop on the ring stream, next to the ib / thin launches
+    bool   fuse2_on = false;                // pairs of steps for this model + operator (prepare_classes)
+    bool   ring_frame_only = false;         // adaptive operator: ring_kernel only for the frame steps of the pair loop
     Strips st{nullptr, nullptr, nullptr, nullptr};
     float* d_traces = nullptr;   // [S][NT][n]
     float* d_stage  = nullptr;   // [S][n][NT] transpose staging
@@ -436,7 +441,7 @@ extern "C" void rtm_destroy(rtm_ctx* c)
     cudaFree(c->d_ring_coef); cudaFree(c->d_ring_meta);
     for (auto& f : c->field) cudaFree(f);
     for (auto& f : c->acc) cudaFree(f);
-    cudaFree(c->d_v); cudaFree(c->d_avel); cudaFree(c->d_bins); cudaFree(c->d_tile_bins_f); cudaFree(c->d_tile_bins_b); cudaFree(c->d_tile_bins_b2); cudaFree(c->d_c); cudaFree(c->d_Index);
+    cudaFree(c->d_v); cudaFree(c->d_avel); cudaFree(c->d_bins); cudaFree(c->d_tile_bins_f); cudaFree(c->d_tile_bins_b); cudaFree(c->d_tile_bins_b2); cudaFree(c->d_c); cudaFree(c->d_Index); cudaFree(c->d_ls_rows); cudaFree(c->d_ls_len);
     cudaFree(c->st.up); cudaFree(c->st.dw); cudaFree(c->st.lf); cudaFree(c->st.rt);
     cudaFree(c->d_traces); cudaFree(c->d_stage); cudaFree(c->d_raw); cudaFree(c->d_sinc); cudaFree(c->d_src);
     cudaFree(c->d_up); cudaFree(c->d_down); cudaFree(c->d_stack); cudaFree(c->d_stable);
@@ -576,7 +581,8 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     G.fd_ntx = make_fastdiv(G.ntx); G.fd_nring = make_fastdiv(2 * G.nband + 2 * G.nside);
     if (const char* e = std::getenv("RTM_NO_GRAPH")) c->use_graphs = std::atoi(e) == 0;
     if (const char* e = std::getenv("RTM_FUSE2")) { c->fuse2 = std::atoi(e) != 0; c->fuse2_forced = c->fuse2; }
-    if (!c->fuse2_forced && p->iLSTE == 0) c->fuse2 = false;
+    // (adaptive operator: pairs only in the streaming form, i.e. when no bin's operator is longer than 4 -- prepare_classes)
+    if (const char* e = std::getenv("RTM_RING_PAR")) c->ring_par = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_FUSE2_MAXRP")) c->fuse2_maxrp = std::atoi(e);
     if (const char* e = std::getenv("RTM_STREAM2")) c->stream2 = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_RING2")) c->ring2 = std::atoi(e) != 0;
@@ -609,7 +615,12 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
         CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         for (int i = 0; i < 3; ++i) CKC(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, i == 2 ? hi : lo));
     }
-    CKC(cudaStreamCreateWithFlags(&c->ring_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const char* e = std::getenv("RTM_RING_PRIO");
+        CKC(cudaStreamCreateWithPriority(&c->ring_stream, cudaStreamNonBlocking, (e && std::atoi(e) != 0) ? hi : lo));
+    }
     CKC(cudaEventCreateWithFlags(&c->ring_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->ring_join, cudaEventDisableTiming));
     for (auto& e : c->ev_ii) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -703,6 +714,10 @@ static int prepare_classes(rtm_ctx* c)
     struct Lists { std::vector<int> fwd, bwd, ii, ib, frame; };
     std::map<int, Lists> lists;  // RP -> tile lists
     const bool ls = G.iLSTE == 0;
+    // pairs of steps: the fixed-length operator; the adaptive operator only in the streaming form (its tile form measured
+    // slower than single steps, profiles/README.md), i.e. when every bin's operator fits radius 4 -- or when forced
+    const bool ls_stream = ls && c->stream2 && c->RP == 4 && G.ls_rows != nullptr;
+    const bool fuse2 = c->fuse2 && (!ls || c->fuse2_forced || ls_stream);
     // an inner tile: full, and grown by one (rounded) radius it still lies in the interior
     const int TZb = kWarps * RTM_NR_B;
     auto inner = [&](int t) {
@@ -723,7 +738,7 @@ static int prepare_classes(rtm_ctx* c)
     std::vector<char> ok(nb, 0), covered(nb, 0), head(nb, 0);
     for (int t = 0; t < nb; ++t) {
         rp2[t] = ls ? radius_class(tb2[t]) : c->RP;
-        ok[t]  = c->fuse2 && inner(t) && rp2[t] <= c->fuse2_maxrp && rp2[t] <= 8;
+        ok[t]  = fuse2 && inner(t) && rp2[t] <= c->fuse2_maxrp && rp2[t] <= 8;
     }
     constexpr int gsz = Tile2<4>::TZ / (kWarps * RTM_NR_B);  // single-step tiles stacked in one two-step tile
     for (int tx = 0; tx < G.ntx; ++tx)
@@ -784,7 +799,7 @@ static int prepare_classes(rtm_ctx* c)
         }
         if (int rc = upload(L.ib, &k.d_tiles_ib)) return rc;
         if (int rc = upload(L.frame, &k.d_tiles_bf)) return rc;
-        if (c->stream2 && c->fuse2 && !ls && k.RP == 4) {
+        if (c->stream2 && fuse2 && (!ls || ls_stream) && k.RP == 4 && lists.size() == 1) {
             // z-streaming form (rtm_stream.cuh).  Regions, for the forward and the backward pass alike:
             //   ring        the N2 outermost cells                    ring tiles of the single-step kernels
             //   thin frame  the RP interior cells next to the ring    thin_frame_kernel, stepped singly
@@ -888,11 +903,15 @@ static int prepare_classes(rtm_ctx* c)
     }
     // ring kernel (rtm_ring.cuh): per-cell one-way coefficients of this model, tensor maps of the tile boxes
     c->ring_ready = false;
+    const bool streaming = c->classes.size() == 1 && c->classes[0].stream_mode;
+    c->fuse2_on = fuse2 && (!ls || c->fuse2_forced || streaming);
+    c->ring_frame_only = false;
     // (measured with the adaptive operator, profiles/r2_c11_*: the ring on a side stream gains nothing in the forward pass and
     //  loses 3-12 % in the backward pass, where its two-way phase gathers per-cell coefficients from the global tables next to
     //  interior tiles that do the same; RTM_RING2_LS=1 enables it there anyway)
     const bool ring_ls = std::getenv("RTM_RING2_LS") && std::atoi(std::getenv("RTM_RING2_LS")) != 0;
-    if (c->ring2 && (!ls || ring_ls) && c->have_model && c->have_op) {
+    if (c->ring2 && (!ls || ring_ls || (streaming && c->fuse2_on)) && c->have_model && c->have_op) {
+        c->ring_frame_only = ls && !ring_ls;
         c->rgeo = make_ring_geo(G, G.mmax, c->RP);
         const int nring = c->rgeo.ntiles;
         cudaDeviceProp prop;
@@ -966,6 +985,24 @@ extern "C" int rtm_set_operator(rtm_ctx* c, const int* Index, int nvel, const fl
         CK(cudaMemcpyAsync(c->d_Index + nvel + 1, Index + nvel, sizeof(int), cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         G.c = c->d_c; G.Index = c->d_Index;
+        cudaFree(c->d_ls_rows); cudaFree(c->d_ls_len);
+        c->d_ls_rows = nullptr; c->d_ls_len = nullptr;
+        G.ls_rows = nullptr; G.ls_len = nullptr; G.ls_nbins = 0;
+        int longest = 1;
+        for (int i = 0; i < nvel; ++i) longest = std::max(longest, Index[i + 1] - Index[i] - 1);
+        if (longest <= 4) {   // rows of the streaming kernels: c[Index[b] .. Index[b]+M] zero-padded to 8 floats, M per bin
+            std::vector<float> rows((size_t)nvel * 8, 0.0f);
+            std::vector<int> len(nvel, -1);
+            for (int b = 0; b < nvel; ++b) {
+                len[b] = Index[b + 1] - Index[b] - 1;
+                for (int l = 0; l <= len[b]; ++l) rows[(size_t)b * 8 + l] = coef[Index[b] + l];
+            }
+            CK(cudaMalloc(&c->d_ls_rows, sizeof(float) * rows.size()));
+            CK(cudaMalloc(&c->d_ls_len, sizeof(int) * len.size()));
+            CK(cudaMemcpy(c->d_ls_rows, rows.data(), sizeof(float) * rows.size(), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(c->d_ls_len, len.data(), sizeof(int) * len.size(), cudaMemcpyHostToDevice));
+            G.ls_rows = c->d_ls_rows; G.ls_len = c->d_ls_len; G.ls_nbins = nvel;
+        }
         // (1+hzx2_1) a power of two (e.g. hz == h): A*c0 is exact in float for every bin
         int ex = 0;
         G.cc0_exact = (std::frexp(G.A, &ex) == 0.5 && (double)(float)G.A == G.A) ? 1 : 0;
@@ -1070,9 +1107,12 @@ template <int RP, bool LS> static int launch_bwd2(rtm_ctx* c, rtm_ctx::TileClass
 static int launch_stream_bwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, int s0, int r0, const Bwd2Args& a2, bool border)
 {
     using T = Strm<4>;
+    const bool ls = c->G.iLSTE == 0;
     if (!k.smem_s2) {
-        CK(cudaFuncSetAttribute(stream2_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::bytes(true)));
-        CK(cudaFuncSetAttribute(stream2_kernel<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(stream2_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::bytes(true)));
+        CK(cudaFuncSetAttribute(stream2_kernel<4, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(stream2_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::bytes(true)));
+        CK(cudaFuncSetAttribute(stream2_kernel<4, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         k.smem_s2 = true;
     }
     StrmArgs a{};
@@ -1089,7 +1129,8 @@ static int launch_stream_bwd(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st,
     tm.prev[0] = k.tmap_s_prev[s0]; tm.prev[1] = k.tmap_s_prev[r0];
     for (int i = 0; i < 4; ++i) tm.acc[i] = c->tmap_s_acc[i];
     ++c->nlaunch;
-    stream2_kernel<4, true><<<(unsigned)(a.nseg * ns), T::kThreadsS, T::bytes(true), st>>>(tm, c->G, a);
+    if (ls) stream2_kernel<4, true, true><<<(unsigned)(a.nseg * ns), T::kThreadsS, T::bytes(true), st>>>(tm, c->G, a);
+    else    stream2_kernel<4, true, false><<<(unsigned)(a.nseg * ns), T::kThreadsS, T::bytes(true), st>>>(tm, c->G, a);
     return RTM_OK;
 }
 // The thin frame (stream mode), one slot: backward (b1 = current source / receiver buffers, P0/P2 in `a`) or forward.
@@ -1097,7 +1138,8 @@ template <bool BWD> static int launch_thin(rtm_ctx* c, rtm_ctx::TileClass& k, cu
 {
     using T = Thin<4>;
     if (!k.smem_t) {
-        CK(cudaFuncSetAttribute(thin_frame_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::bytes(true)));
+        CK(cudaFuncSetAttribute(thin_frame_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::bytes(true)));
+        CK(cudaFuncSetAttribute(thin_frame_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::bytes(true)));
         CK(cudaFuncSetAttribute(thin_frame_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::bytes(false)));
         k.smem_t = true;
     }
@@ -1107,7 +1149,8 @@ template <bool BWD> static int launch_thin(rtm_ctx* c, rtm_ctx::TileClass& k, cu
     tm.row[0] = k.tmap_t_row[cur0]; tm.col[0] = k.tmap_t_col[cur0];
     tm.row[1] = k.tmap_t_row[cur1]; tm.col[1] = k.tmap_t_col[cur1];
     ++c->nlaunch;
-    thin_frame_kernel<4, BWD><<<(unsigned)(k.n_thin * ns), T::kThreadsT, T::bytes(BWD), st>>>(tm, c->G, a);
+    if (BWD && c->G.iLSTE == 0) thin_frame_kernel<4, BWD, true><<<(unsigned)(k.n_thin * ns), T::kThreadsT, T::bytes(BWD), st>>>(tm, c->G, a);
+    else                        thin_frame_kernel<4, BWD, false><<<(unsigned)(k.n_thin * ns), T::kThreadsT, T::bytes(BWD), st>>>(tm, c->G, a);
     return RTM_OK;
 }
 static int dispatch_bwd2_class(rtm_ctx* c, rtm_ctx::TileClass& k, cudaStream_t st, int ns, int s1, int r1, int s0, int r0, const Bwd2Args& a, bool border)
@@ -1186,7 +1229,7 @@ static RingArgs ring_args_fwd(rtm_ctx* c, const FwdArgs& f)
 }
 static int dispatch_fwd(rtm_ctx* c, int ns, int buf, int p0buf, FwdArgs a, bool frame = false, cudaStream_t serial = nullptr)
 {
-    if (c->ring_ready && buf >= 0 && (frame || c->ring2_fwd)) {
+    if (c->ring_ready && buf >= 0 && (frame || (c->ring2_fwd && !c->ring_frame_only))) {
         // the ring by its own kernel: alone (frame step of the pair loop), or next to the interior launch on a side stream
         if (frame) return launch_ring<false>(c, serial ? serial : c->stream, ns, buf, p0buf, ring_args_fwd(c, a));
         CK(cudaEventRecord(c->ring_fork, c->stream));
@@ -1284,7 +1327,7 @@ static int dispatch_bwd(rtm_ctx* c, int ns, int s1, int r1, int s0, int r0, cons
         r.P2 = a.R2; r.SX = a.S2; r.src = a.src; r.inject = 0; r.k = a.k; r.st = a.st; r.seis = a.seis; r.sum_double = 0;
         return launch_ring<true>(c, serial ? serial : c->stream, ns, r1, r0, r);
     }
-    if (!frame && !serial && c->ring_ready && c->ring2_bwd && !c->store_mode) {
+    if (!frame && !serial && c->ring_ready && c->ring2_bwd && !c->ring_frame_only && !c->store_mode) {
         // a single step of all tiles: the ring by its own kernel on a side stream, the interior tiles without ring CTAs
         RingArgs r{};
         r.P2 = a.R2; r.SX = a.S2; r.src = a.src; r.inject = 0; r.k = a.k; r.st = a.st; r.seis = a.seis; r.sum_double = 0;
@@ -1364,7 +1407,7 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
     const size_t slab = (size_t)c->S * G.shot_stride;
     // forward pass in pairs (inner segments two slots per pass, ring + frame tiles singly): 4 rotating buffers
     bool pairs = false;
-    if (!use_store && nsnap == 0 && c->fuse2_fwd != 0 && c->classes.size() == 1 && c->classes[0].stream_mode)
+    if (!use_store && nsnap == 0 && c->fuse2_fwd != 0 && G.iLSTE != 0 && c->classes.size() == 1 && c->classes[0].stream_mode)
         pairs = c->fuse2_fwd == 1 || c->fuse2_forced || c->classes[0].ii_blocks / 2 * ns >= rtm_ctx::kFuse2MinCtas;
     const int NB = pairs ? 4 : 3;
     auto slot = [&](int k) -> float* { return use_store ? c->store + (size_t)k * slab : c->field[k % NB]; };
@@ -1621,13 +1664,27 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
                 }
                 return RTM_OK;
             };
-            if (int rc = dispatch_bwd(c, ns, Sb, Rb, Sa, Ra, args1(k, Sa, Sc, Ra, Rb, Rc), true, B)) return rc;
+            // Stream mode: the ring of slot k depends on the previous pair only and touches no cell the ib launch writes, and
+            // the ring of slot k-1 and the thin frame of slot k-1 write disjoint cells from the same inputs (ring of slot k,
+            // ib launch): each ring launch runs on the ring stream next to its neighbour on B (RTM_RING_PAR=0: in B's order).
+            const bool par = c->ring_par && c->ring_ready && c->classes.size() == 1 && c->classes[0].stream_mode;
+            cudaStream_t RS = par ? c->ring_stream : B;
+            if (par) { CK(cudaEventRecord(c->ring_fork, B)); CK(cudaStreamWaitEvent(RS, c->ring_fork, 0)); }
+            if (int rc = dispatch_bwd(c, ns, Sb, Rb, Sa, Ra, args1(k, Sa, Sc, Ra, Rb, Rc), true, RS)) return rc;
+            if (par) CK(cudaEventRecord(c->ring_join, RS));
             if (j > 0) CK(cudaStreamWaitEvent(B, c->ev_ii[(j - 1) & 1], 0));
             for (auto& kc : c->classes)
                 if (int rc = dispatch_bwd2_class(c, kc, B, ns, Sb, Rb, Sa, Ra, a2, true)) return rc;
             CK(cudaEventRecord(c->ev_ib[j & 1], B));
-            if (int rc = dispatch_bwd(c, ns, Sc, Rc, Sb, Rb, args1(k - 1, Sb, Sd, Rb, Rc, Rd), true, B)) return rc;
+            if (par) {
+                CK(cudaStreamWaitEvent(B, c->ring_join, 0));
+                CK(cudaEventRecord(c->ring_fork, B));
+                CK(cudaStreamWaitEvent(RS, c->ring_fork, 0));
+            }
+            if (int rc = dispatch_bwd(c, ns, Sc, Rc, Sb, Rb, args1(k - 1, Sb, Sd, Rb, Rc, Rd), true, RS)) return rc;
+            if (par) CK(cudaEventRecord(c->ring_join, RS));
             if (int rc = thin(k - 1, Sc, Rc, Sb, Rb, Sd, Rd)) return rc;
+            if (par) CK(cudaStreamWaitEvent(B, c->ring_join, 0));
             std::swap(Sa, Sc); std::swap(Sb, Sd);
             std::swap(Ra, Rc); std::swap(Rb, Rd);
         }
@@ -1635,7 +1692,7 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
         CK(cudaStreamWaitEvent(A, c->join_ev[2], 0));
         return RTM_OK;
     };
-    bool pairs = c->fuse2 && !store;
+    bool pairs = c->fuse2_on && !store;
     if (pairs) {
         long nii = 0, nb2 = 0;
         for (auto& kc : c->classes) { nii += kc.stream_mode ? kc.ii_blocks / 2 : kc.n_ii; nb2 += kc.stream_mode ? kc.n_segs_ii + kc.n_segs_ib : kc.n_b2; }

@@ -107,6 +107,11 @@ struct Geo {
     const int2* tile_bins_b;      // [ntz_b*ntx]
     const int2* tile_bins_b2;     // [ntz_b*ntx] same tiles grown by the operator radius (two-step kernel)
     const float* v;          // [NZ][pitch], shared by all shots
+    // adaptive operator no longer than 4 everywhere (streaming kernels): every bin's coefficients zero-padded to
+    // 8 floats (one 32-byte sector per cell, read through L1) and its length, in global memory
+    const float* ls_rows;    // [nvel][8]
+    const int*   ls_len;     // [nvel]
+    int          ls_nbins;
     float  w[65];            // blend weights l/N2
 };
 
@@ -416,6 +421,72 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
             for (int l = 1; l <= RP; ++l)
                 if (l <= M) term(l);
         }
+    }
+}
+
+// The adaptive operator of the streaming kernels (every length <= 4): a cell's coefficients are one zero-padded row of 8
+// floats in a global table (Geo::ls_rows), its length one int (Geo::ls_len).  The table offsets and lengths of the four
+// cells of a float4 group are looked up once (ls_cells) and shared by every field evaluated at those cells; the
+// arithmetic per cell is stencil_row<RP, true>'s, term by term (terms beyond a cell's own length are skipped, not
+// multiplied by the zero padding).
+struct LsCells { int off[4]; int Mc[4]; int Mx; };
+__device__ __forceinline__ LsCells ls_cells(const Geo& G, uint2 bins4)
+{
+    LsCells L;
+    const int b4[4] = {(int)(bins4.x & 0xffffu), (int)(bins4.x >> 16), (int)(bins4.y & 0xffffu), (int)(bins4.y >> 16)};
+    L.Mx = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int b = min(b4[q], G.ls_nbins - 1);
+        L.off[q] = b * 8;
+        L.Mc[q]  = __ldg(G.ls_len + b);
+        L.Mx     = max(L.Mx, L.Mc[q]);
+    }
+    return L;
+}
+template <int SPT>
+__device__ __forceinline__ void stencil_row_ls4(const Geo& G, const float* sc, const LsCells& L, float (&w1)[4], float (&p1)[4])
+{
+    constexpr int RP = 4, SP = SPT;
+    float xr[4 + 2 * RP];
+#pragma unroll
+    for (int g = 0; g < (4 + 2 * RP) / 4; ++g) {
+        const float4 t4 = *reinterpret_cast<const float4*>(sc - RP + 4 * g);
+        xr[4 * g + 0] = t4.x; xr[4 * g + 1] = t4.y; xr[4 * g + 2] = t4.z; xr[4 * g + 3] = t4.w;
+    }
+    float cg[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        p1[q] = xr[RP + q];
+        unpack(__ldg(reinterpret_cast<const float4*>(G.ls_rows + L.off[q])), cg[q]);
+        w1[q] = w1_first_ls(G, cg[q][0], p1[q]);
+    }
+    auto term = [&](int l, const float (&cl)[4]) {
+        float zm[4], zp[4];
+        unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
+        unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (l <= L.Mc[q]) {
+                const float s = __fadd_rn(zm[q], zp[q]);
+                const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
+                const float u = __fadd_rn(t, xr[RP + q + l]);
+                w1[q]         = __fmaf_rn(cl[q], u, w1[q]);
+            }
+        }
+    };
+#pragma unroll
+    for (int l = 1; l <= 3; ++l) {
+        if (l <= L.Mx) {
+            const float cl[4] = {cg[0][l], cg[1][l], cg[2][l], cg[3][l]};
+            term(l, cl);
+        }
+    }
+    if (L.Mx >= 4) {
+        float c4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c4[q] = __ldg(G.ls_rows + L.off[q] + 4);
+        term(4, c4);
     }
 }
 

@@ -105,6 +105,14 @@ __device__ __forceinline__ void store4c(float* dst, const float (&o)[4], int x, 
     }
 }
 
+// RTM_STRM_BARSYNC=1 (checking builds): the A -> B barrier of stream2_kernel as `bar.sync 1, 288` instead of the split
+// mbarrier arrive / wait.  compute-sanitizer's racecheck does not count an mbarrier phase completed by plain arrivals as
+// an ordering between shared-memory accesses of different warps (it reports every phase-A write of the mid ring against
+// the phase-B reads of the other warps); with the named barrier in the same place the same run is clean
+// (profiles/README.md, "racecheck").
+#ifndef RTM_STRM_BARSYNC
+#define RTM_STRM_BARSYNC 0
+#endif
 #ifndef RTM_STRM_MINB_B
 #define RTM_STRM_MINB_B 2
 #endif
@@ -115,8 +123,11 @@ __device__ __forceinline__ void store4c(float* dst, const float (&o)[4], int x, 
 #ifndef RTM_STRM_MAXREG_B
 #define RTM_STRM_MAXREG_B 88   // 2 CTAs x 320 threads x 88 registers leave 9216 registers = one thin_frame CTA next to them
 #endif
-template <int RP, bool BWD>
-__global__ void __launch_bounds__(Strm<RP>::kThreadsS, BWD ? RTM_STRM_MINB_B : RTM_STRM_MINB_F) __maxnreg__(BWD ? RTM_STRM_MAXREG_B : 64)
+#ifndef RTM_STRM_MAXREG_LS
+#define RTM_STRM_MAXREG_LS 96  // adaptive operator: per-cell coefficient rows and lengths on top (2 x 320 x 96 = 61440 registers)
+#endif
+template <int RP, bool BWD, bool LS = false>
+__global__ void __launch_bounds__(Strm<RP>::kThreadsS, BWD ? RTM_STRM_MINB_B : RTM_STRM_MINB_F) __maxnreg__(BWD ? (LS ? RTM_STRM_MAXREG_LS : RTM_STRM_MAXREG_B) : 64)
 stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo G, const StrmArgs a)
 {
     using T = Strm<RP>;
@@ -171,7 +182,10 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
     };
 
     const float* AV = G.avel + G.padL;
+    // adaptive operator (every length <= RP): a cell's coefficient row comes from the padded global table, addressed by its
+    // velocity bin -- stencil_row's "staged" form with the rows in global memory (L1 hits: neighbouring cells share bins)
     const LsTable T0{};
+    const unsigned short* BN = G.bins + G.padL;
     const uint2 nobins = make_uint2(0u, 0u);
 
     // Row of block `blk` handled in phase A: r (0..7); first mid column colm (float4 group); own: the group lies in the
@@ -212,15 +226,26 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
     size_t soA = (size_t)so + (size_t)zA * G.pitch + xA, soB = (size_t)so + (size_t)((ptrdiff_t)zO * G.pitch) + xB;
     // velocity factor a = ((v*v)*tao2)*h2 of the two rows (L2-resident, shared by all shots), loaded one iteration ahead
     float4 avA4 = make_float4(0.f, 0.f, 0.f, 0.f), avB4 = avA4;
-    if (workA && zA < G.NZ) avA4 = __ldg(reinterpret_cast<const float4*>(pavA));
+    uint2  bnA2 = nobins, bnB2 = nobins;        // ... and the velocity bins of the same cells (adaptive operator)
+    if (workA && zA < G.NZ) {
+        avA4 = __ldg(reinterpret_cast<const float4*>(pavA));
+        if (LS) bnA2 = __ldg(reinterpret_cast<const uint2*>(BN + (pavA - AV)));
+    }
     for (int i = 0; i <= n; ++i, zA += BR, zO += BR, pavA += rowstep, pavB += rowstep, soA += rowstep, soB += rowstep) {
         const int s = i + 1;
         const bool doA = workA;                                // (mid block n is needed whole: out block n reads RP rows past its end)
         const bool doB = warp < BR && i >= 1 && zO < zlast && xB < a.xend;   // (rows / groups past the region's end feed nobody)
         const float4 avAc = avA4, avBc = avB4;                 // this iteration's; the next iteration's go in flight now
+        const uint2  bnAc = bnA2, bnBc = bnB2;
         if (i < n) {
-            if (workA && zA + BR < G.NZ) avA4 = __ldg(reinterpret_cast<const float4*>(pavA + rowstep));
-            if (warp < BR && zO + BR < zlast && xB < a.xend) avB4 = __ldg(reinterpret_cast<const float4*>(pavB + rowstep));
+            if (workA && zA + BR < G.NZ) {
+                avA4 = __ldg(reinterpret_cast<const float4*>(pavA + rowstep));
+                if (LS) bnA2 = __ldg(reinterpret_cast<const uint2*>(BN + (pavA + rowstep - AV)));
+            }
+            if (warp < BR && zO + BR < zlast && xB < a.xend) {
+                avB4 = __ldg(reinterpret_cast<const float4*>(pavB + rowstep));
+                if (LS) bnB2 = __ldg(reinterpret_cast<const uint2*>(BN + (pavB + rowstep - AV)));
+            }
         }
 
         if (i == 0) mbar_wait_b(full + 0, 0);
@@ -235,13 +260,16 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
             const int rm = slot_s * BR + rA;              // mid block i lives in the slot of stage i+1
             float av[4];
             unpack(avAc, av);
+            LsCells LC{};
+            if (LS) LC = ls_cells(G, bnAc);
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 const float* pc = cur + f * CURF + rc * W1 + colm + RP;
                 float*       pm = mid + f * MIDF + rm * WM + colm;
                 float w1[4], p1[4], p0[4];
                 float (&o)[4] = oA[f];
-                stencil_row<RP, false, W1>(G, pc, G.nfdmax, T0, nobins, w1, p1);
+                if constexpr (LS) stencil_row_ls4<W1>(G, pc, LC, w1, p1);
+                else stencil_row<RP, false, W1>(G, pc, G.nfdmax, T0, nobins, w1, p1);
                 unpack(*reinterpret_cast<const float4*>(pm), p0);
                 if (f == 0) {   // source field / forward field: double final sum (Add_Con, BKAdd_EFF_Con), + wavelet
 #pragma unroll
@@ -274,7 +302,9 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
         }
         // A -> B barrier, split: arrive now, store this warp's slot-k values, then wait for the other warps' rows
         __syncwarp();
+#if !RTM_STRM_BARSYNC
         if (lane == 0) mbar_arrive(midr + (i & 1));
+#endif
         if (doA && zA >= zloA && zA < zhiA && xA + 3 >= xloA && xA < xhiA) {
 #pragma unroll
             for (int f = 0; f < NF; ++f) store4c(a.Ak[f] + soA, oA[f], xA, xloA, xhiA);
@@ -286,7 +316,11 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
                 }
             }
         }
+#if RTM_STRM_BARSYNC
+        bar_consumers(32 * (BR + 1));   // checking build: the same A -> B barrier as a named hardware barrier
+#else
         mbar_wait_b(midr + (i & 1), (i >> 1) & 1);
+#endif
 
         // ---- phase B: out block i (slot k-1 / forward: k+1), rows [z0+8(i-1), +8)
         if (doB) {
@@ -297,10 +331,13 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
             unpack(avBc, av);
             float ok[NF][4], okm[NF][4];
             const size_t o = soB;
+            LsCells LC{};
+            if (LS) LC = ls_cells(G, bnBc);
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 float w1[4], p0[4];
-                stencil_row<RP, false, WM>(G, mid + f * MIDF + rb * WM + RP + 4 * lane, G.nfdmax, T0, nobins, w1, ok[f]);
+                if constexpr (LS) stencil_row_ls4<WM>(G, mid + f * MIDF + rb * WM + RP + 4 * lane, LC, w1, ok[f]);
+                else stencil_row<RP, false, WM>(G, mid + f * MIDF + rb * WM + RP + 4 * lane, G.nfdmax, T0, nobins, w1, ok[f]);
                 unpack(*reinterpret_cast<const float4*>(cur + f * CURF + rp * W1 + 2 * RP + 4 * lane), p0);
                 if (f == 0) {
 #pragma unroll
@@ -536,7 +573,7 @@ template <int RP> struct Thin {
     __host__ __device__ static constexpr int bytes(bool bwd) { return (bwd ? 2 : 1) * ((FLOATS * 4 + 127) / 128 * 128) + 16; }
 };
 
-template <int RP, bool BWD>
+template <int RP, bool BWD, bool LS = false>
 __global__ void __launch_bounds__(Thin<RP>::kThreadsT)
 thin_frame_kernel(const __grid_constant__ ThinMaps tm, const __grid_constant__ Geo G, const ThinArgs a)
 {
@@ -568,8 +605,10 @@ thin_frame_kernel(const __grid_constant__ ThinMaps tm, const __grid_constant__ G
     const size_t cell = (size_t)z * G.pitch + x;
     float4 av4 = make_float4(0.f, 0.f, 0.f, 0.f), p04[2] = {av4, av4}, a1 = av4, a2 = av4, aS = av4, aR = av4;
     const bool compen = BWD && G.iCompen == 1;
+    uint2 bn2 = make_uint2(0u, 0u);
     if (work) {   // (whole float4 groups: the row pitch leaves room past the last column)
         av4 = __ldg(reinterpret_cast<const float4*>(G.avel + G.padL + cell));
+        if (LS) bn2 = __ldg(reinterpret_cast<const uint2*>(G.bins + G.padL + cell));
 #pragma unroll
         for (int f = 0; f < NF; ++f) p04[f] = *reinterpret_cast<const float4*>(a.P0[f] + so + cell);
         if (BWD) {
@@ -583,14 +622,15 @@ thin_frame_kernel(const __grid_constant__ ThinMaps tm, const __grid_constant__ G
     }
     mbar_wait_b(bar, 0);
     if (!work) return;
-    const LsTable T0{};
+    LsTable T0{};
+    if (LS) { T0.rows = G.ls_rows; T0.len = G.ls_len; T0.bmin = 0; T0.bmax = G.ls_nbins - 1; T0.staged = true; }
     float av[4], o[NF][4], c1[NF][4];   // c1: the current fields at the cell
     unpack(av4, av);
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
         float w1[4], p0[4];
         float (&p1)[4] = c1[f];
-        stencil_row<RP, false, 0>(G, tile + f * FSTRIDE + (lr + RP) * SP + 4 * lg + RP, G.nfdmax, T0, make_uint2(0u, 0u), w1, p1, SP);
+        stencil_row<RP, LS, 0>(G, tile + f * FSTRIDE + (lr + RP) * SP + 4 * lg + RP, G.nfdmax, T0, bn2, w1, p1, SP);
         unpack(p04[f], p0);
         if (f == 0) {   // forward field (Add_Con) / reconstructed source field (BKAdd_EFF_Con): double final sum, source term
 #pragma unroll

@@ -85,3 +85,52 @@ def test_stream_equals_tile_form_equals_single_steps(monkeypatch):
     assert np.array_equal(u1, u4) and np.array_equal(d1, d4) and np.array_equal(s1, s4)
     assert np.array_equal(g1, g2) and np.array_equal(g1, g3) and np.array_equal(g1, g4)
     assert n1 == 0 and n2 > 0 and n3 > n2 and n4 == n3   # cell-steps advanced two slots per pass: none / tile form / streamed region
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The adaptive operator in the streaming form: when no velocity bin needs an operator longer than 4 the pair of
+# steps runs through stream2_kernel<4, true, LS> / thin_frame_kernel<.., LS> / ring_kernel<.., LS> (per-cell
+# coefficient rows from the padded global table).
+# ---------------------------------------------------------------------------------------------------------------
+def _adaptive_case(name, nt1, mod_NX=700, mod_NZ=280, icompen=1, nrec=3):
+    return Case(name=name, nfdmax=4, nfdmin=2, N2=10, f0=15.0, fmax=31.0, iLSTE=0, iCompen=icompen, hz=20.0, h=20.0, tao=1e-3,
+                tao1=1e-3, mod_NZ=mod_NZ, mod_NX=mod_NX, NT1=nt1, s_l=5, s_z=10 + 16 * 3 - 1 - 9, n=230, ds=3, r_x=1, nrec=nrec,
+                NX_ED=mod_NX, NZ_ED=mod_NZ, nthita=100, dv=1.0)
+
+
+@pytest.mark.parametrize("seg,nt1,icompen", [(1, 27, 1), (3, 30, 0), (8, 29, 1)])
+def test_stream_adaptive_vs_oracle(monkeypatch, seg, nt1, icompen):
+    """Adaptive operator 2..4 on 700 x 280 (lengths 2, 3 and 4 inside one float4 group where the layers meet)."""
+    env(monkeypatch, seg=seg)
+    case = _adaptive_case("stream_ls", nt1, icompen=icompen)
+    run_case(case, [10 + 16 * seg, 10 + 16 * 2 * seg + 15, 10 + 16 * 5 + 7], [10 + 128 * 2 - 1, 10 + 128 * 3, 10 + 300],
+             snaps=(2,))
+
+
+def test_stream_adaptive_runs_in_pairs_and_equals_single_steps(monkeypatch):
+    """2301 x 751, adaptive 2..4, 121 slots: the default policy (nothing forced) picks the streaming pairs for a launch of
+    4 shots; same bits as single stepping."""
+    case = _adaptive_case("c2_ls", 121, mod_NX=2301, mod_NZ=751, nrec=4)
+    vel = layered(case)
+    v = R.pad_velocity(vel, case.N2, 0)
+    vmin, vmax, nvel, need = R.velocity_bins(v, case.dv)
+    hzx = float(np.float32(case.hz) / np.float32(case.h))
+    _, M, Index, c = R.ls_operator(case.nthita, case.nfdmax, case.nfdmin, nvel, case.tao, case.h, case.df, case.eps, case.fmax,
+                                   vmin, case.dv, hzx, need)
+    assert M.max() <= 4 and len(set(M[M > 0].tolist())) >= 2, "the model should need more than one operator length"
+    seis = traces(case, 4)
+    r_u, r_x = [12, 300, 500, 740], [700, 1500, 30, 2290]
+
+    def migrate():
+        with R.engine_for_case(case, max_batch=4) as e:
+            e.set_model(v, vmin, vmax, case.dv)
+            e.set_operator(c, Index)
+            out = e.migrate(r_u, r_x, seis)
+            return out, e.stats()["pair_cell_steps_backward"]
+    monkeypatch.delenv("RTM_FUSE2", raising=False)
+    (u2, d2, s2), n2 = migrate()
+    monkeypatch.setenv("RTM_FUSE2", "0")
+    (u1, d1, s1), n1 = migrate()
+    assert n1 == 0 and n2 > 0
+    assert np.abs(u1).max() > 0 and np.isfinite(u1).all()
+    assert np.array_equal(u1, u2) and np.array_equal(d1, d2) and np.array_equal(s1, s2)

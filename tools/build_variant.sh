@@ -1,16 +1,17 @@
 #!/bin/bash
-# tools/build_variant.sh NAME "-DRTM_KNR=8 ..."  -> rtm_gpu_b200/build/variants/librtm_NAME.so (experiments only)
+# A kernel-variant build of the library for experiments / checking builds:
+#   tools/build_variant.sh NAME -DRTM_STRM_BARSYNC=1 ...   ->  rtm_gpu_b200/variants/librtm_b200_NAME.so
+# (select it with RTM_LIB_PATH=rtm_gpu_b200/variants/librtm_b200_NAME.so; .so files are git-ignored but travel with gpurun)
 set -e
-name=$1; defs=$2
-mkdir -p rtm_gpu_b200/build/variants /tmp/rtmv_$name
-cd rtm_gpu_b200/csrc
-F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-O2,-pthread $defs"
-nvcc $F -c rtm_engine.cu -o /tmp/rtmv_$name/e.o 2>&1 | grep -v warning || true
-objs=/tmp/rtmv_$name/e.o
-for f in host_abi.cpp rtm_nccl.cpp driver.cpp host/fd_operator.cpp host/model.cpp host/config.cpp host/resample.cpp host/segy_io.cpp host/poststack.cpp; do
-  o=/tmp/rtmv_$name/$(basename $f).o
-  [ -f ../build/$(basename $f).o ] && objs="$objs ../build/$(basename $f).o" && continue
-  nvcc $F -c $f -o $o; objs="$objs $o"
+cd "$(dirname "$0")/.."
+name=$1; shift
+mkdir -p rtm_gpu_b200/variants /tmp/rtm_variant_$name
+objs=""
+for s in rtm_gpu_b200/csrc/*.cu rtm_gpu_b200/csrc/*.cpp rtm_gpu_b200/csrc/host/*.cpp; do
+  case $s in */main.cpp) continue;; esac
+  o=/tmp/rtm_variant_$name/$(basename $s).o
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-O2,-pthread --threads 4 -Iinclude "$@" -c $s -o $o
+  objs="$objs $o"
 done
-nvcc -shared -o ../build/variants/librtm_$name.so $objs -lcudart_static -ldl -lpthread -lrt 2>&1 | grep -v warning || true
-echo built $name
+nvcc -shared -o rtm_gpu_b200/variants/librtm_b200_$name.so $objs -lcudart_static -ldl -lpthread -lrt
+ls -la rtm_gpu_b200/variants/librtm_b200_$name.so
