@@ -370,7 +370,7 @@ struct rtm_ctx {
     int*   d_Index = nullptr;
     float* d_ls_rows = nullptr;             // adaptive operator no longer than 4: padded coefficient rows [nvel][8] + lengths (streaming kernels)
     int*   d_ls_len = nullptr;
-    bool   ring_par = false;                // stream mode: ring launches of the pair loop on the ring stream, next to the ib / thin launches
+    bool   ring_par = true;                 // stream mode: ring launches of the pair loop on the ring stream, next to the ib / thin launches
     bool   fuse2_on = false;                // pairs of steps for this model + operator (prepare_classes)
     bool   ring_frame_only = false;         // adaptive operator: ring_kernel only for the frame steps of the pair loop
     Strips st{nullptr, nullptr, nullptr, nullptr};

@@ -213,6 +213,21 @@ __device__ __forceinline__ float w1_first_ls(const Geo& G, float c0, float p1)
     return G.cc0_exact ? __fmul_rn(__fmul_rn(G.cc0f, c0), p1)   // cc0f = 1+hzx2_1 (a power of two)
                        : __double2float_rn(__dmul_rn(__dmul_rn(G.A, (double)c0), (double)p1));
 }
+// The same for the four cells of a float4 group, with the (uniform) test outside the cell loop: inside it the compiler
+// if-converts the double path, and its two conversions, two double multiplies and the conversion back are then issued
+// predicated-off for every cell (round 2, ncu source counters of the streaming kernel: 7 % of its instructions, 15 % of
+// its stall samples).  Used by the streaming kernels only: in the tile kernels the real branch cost more than it saved
+// (spills in the row loops: forward step at radius 8 100.7 -> 122.2 us, profiles/README.md).
+__device__ __forceinline__ void w1_first_ls4(const Geo& G, const float (&c0)[4], const float (&p1)[4], float (&w1)[4])
+{
+    if (G.cc0_exact) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w1[q] = __fmul_rn(__fmul_rn(G.cc0f, c0[q]), p1[q]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w1[q] = __double2float_rn(__dmul_rn(__dmul_rn(G.A, (double)c0[q]), (double)p1[q]));
+    }
+}
 
 // data cell test of BKAdd (:349-353): row s_z, s_l <= x <= s_r, (x-s_l)%ds==0
 __device__ __forceinline__ int data_index(const Geo& G, int z, int x)
@@ -429,7 +444,8 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
 // cells of a float4 group are looked up once (ls_cells) and shared by every field evaluated at those cells; the
 // arithmetic per cell is stencil_row<RP, true>'s, term by term (terms beyond a cell's own length are skipped, not
 // multiplied by the zero padding).
-struct LsCells { int off[4]; int Mc[4]; int Mx; };
+struct LsCells { int off[4]; int Mc[4]; int Mx; };   // Mx: longest operator among the cells of the WARP (uniform)
+// (called by all 32 lanes of a warp)
 __device__ __forceinline__ LsCells ls_cells(const Geo& G, uint2 bins4)
 {
     LsCells L;
@@ -442,6 +458,7 @@ __device__ __forceinline__ LsCells ls_cells(const Geo& G, uint2 bins4)
         L.Mc[q]  = __ldg(G.ls_len + b);
         L.Mx     = max(L.Mx, L.Mc[q]);
     }
+    L.Mx = __reduce_max_sync(0xffffffffu, L.Mx);   // uniform loop bounds: no divergence handling around the terms
     return L;
 }
 template <int SPT>
@@ -459,20 +476,22 @@ __device__ __forceinline__ void stencil_row_ls4(const Geo& G, const float* sc, c
     for (int q = 0; q < 4; ++q) {
         p1[q] = xr[RP + q];
         unpack(__ldg(reinterpret_cast<const float4*>(G.ls_rows + L.off[q])), cg[q]);
-        w1[q] = w1_first_ls(G, cg[q][0], p1[q]);
+    }
+    {
+        const float c0[4] = {cg[0][0], cg[1][0], cg[2][0], cg[3][0]};
+        w1_first_ls4(G, c0, p1, w1);
     }
     auto term = [&](int l, const float (&cl)[4]) {
         float zm[4], zp[4];
         unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
         unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (l <= L.Mc[q]) {
-                const float s = __fadd_rn(zm[q], zp[q]);
-                const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
-                const float u = __fadd_rn(t, xr[RP + q + l]);
-                w1[q]         = __fmaf_rn(cl[q], u, w1[q]);
-            }
+        for (int q = 0; q < 4; ++q) {   // (a cell shorter than l keeps its sum: selected, not branched around)
+            const float s = __fadd_rn(zm[q], zp[q]);
+            const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
+            const float u = __fadd_rn(t, xr[RP + q + l]);
+            const float w = __fmaf_rn(cl[q], u, w1[q]);
+            w1[q]         = l <= L.Mc[q] ? w : w1[q];
         }
     };
 #pragma unroll

@@ -253,6 +253,8 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
 
         // ---- phase A: mid block i (slot k / forward: k), rows [z0-RP+8i, +8)
         float oA[NF][4];
+        LsCells LC{};
+        if (LS) LC = ls_cells(G, bnAc);   // (all lanes: warp-uniform operator length inside)
         if (doA) {
             // centre row in the current-field ring: rows 0..RP-1 of the mid block lie in stage i, the others in stage i+1
             int rc = rA < RP ? slot_i * BR + rA + RP : slot_s * BR + rA - RP;
@@ -260,8 +262,6 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
             const int rm = slot_s * BR + rA;              // mid block i lives in the slot of stage i+1
             float av[4];
             unpack(avAc, av);
-            LsCells LC{};
-            if (LS) LC = ls_cells(G, bnAc);
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 const float* pc = cur + f * CURF + rc * W1 + colm + RP;
@@ -323,6 +323,7 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
 #endif
 
         // ---- phase B: out block i (slot k-1 / forward: k+1), rows [z0+8(i-1), +8)
+        if (LS) LC = ls_cells(G, bnBc);
         if (doB) {
             int rb = warp < RP ? slot_i * BR + warp + RP : slot_s * BR + warp - RP;   // centre row in the mid ring
             if (rb < RP) rb += COPY;
@@ -331,8 +332,6 @@ stream2_kernel(const __grid_constant__ StrmMaps tm, const __grid_constant__ Geo 
             unpack(avBc, av);
             float ok[NF][4], okm[NF][4];
             const size_t o = soB;
-            LsCells LC{};
-            if (LS) LC = ls_cells(G, bnBc);
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 float w1[4], p0[4];
