@@ -328,6 +328,16 @@ __device__ __forceinline__ LsTable ls_stage_slice(const Geo& G, int2 tb, float* 
 // M <= RP is the uniform length of the Taylor operator; the adaptive operator brings a length
 // and table offset per cell (from the cell's velocity bin).
 // SPT: pitch of the shared tile (floats); 0 = run-time pitch `spr` (ring tiles).
+// RTM_LS_UNIFORM=1: adaptive operators of the radius classes 8, 12, 16 (packed-table path): the term loop runs to the
+// longest operator of the WARP.  (The kernels of the radius-4 class keep per-lane bounds: with the uniform bound and selects
+// instead of branches there, the forward step of the mixed-length C5 model got slower, 89.1 -> 93.5 us.)
+#ifndef RTM_LS_UNIFORM
+#define RTM_LS_UNIFORM 1
+#endif
+// RTM_LS_SAMEBIN=1: the same classes, warps whose lanes each hold four cells of ONE velocity bin: one operator per lane.
+#ifndef RTM_LS_SAMEBIN
+#define RTM_LS_SAMEBIN 0
+#endif
 template <int RP, bool LS, int SPT = kTX + 2 * RP>
 __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M, const LsTable& T,
                                             uint2 bins4, float (&w1)[4], float (&p1)[4], int spr = 0)
@@ -384,6 +394,38 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
                     }
                 }
             }
+        } else if (RTM_LS_SAMEBIN && RP >= 8 &&
+                   __all_sync(__activemask(), (b4[0] == b4[1]) & (b4[1] == b4[2]) & (b4[2] == b4[3]))) {
+            // every lane's four cells share one velocity bin (velocity varies slowly along x): one operator per lane --
+            // one coefficient load and one length test per term instead of four.  Same operations per cell.
+            const int b   = min(max(b4[0], T.bmin), T.bmax);
+            const int top = T.ip[b];
+            const int Ml  = T.ip[b + 1] - top - 1;
+            const float* cl = T.cp + top;
+            Mx = __reduce_max_sync(__activemask(), Ml);
+            {
+                const float c0 = cl[0];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) w1[q] = w1_first_ls(G, c0, p1[q]);
+            }
+#pragma unroll
+            for (int l = 1; l <= RP; ++l) {
+                if (l <= Mx) {
+                    float zm[4], zp[4];
+                    unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
+                    unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
+                    if (l <= Ml) {
+                        const float c = cl[l];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float s = __fadd_rn(zm[q], zp[q]);
+                            const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
+                            const float u = __fadd_rn(t, xr[RP + q + l]);
+                            w1[q]         = __fmaf_rn(c, u, w1[q]);
+                        }
+                    }
+                }
+            }
         } else {
             const float* cq[4];
 #pragma unroll
@@ -395,6 +437,9 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
                 Mx    = max(Mx, Mc[q]);
                 w1[q] = w1_first_ls(G, cq[q][0], p1[q]);
             }
+            // the term loop runs to the longest operator of the (converged part of the) warp: a uniform bound needs no
+            // divergence handling around every term (measured, profiles/r2_c18_*: forced radius 12 +7.7 %, 8 +3.5 %, 6 +2.8 %)
+            if (RTM_LS_UNIFORM && RP >= 8) Mx = __reduce_max_sync(__activemask(), Mx);
 #pragma unroll
             for (int l = 1; l <= RP; ++l) {
                 if (l <= Mx) {
@@ -403,7 +448,7 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
                     unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        if (l <= Mc[q]) {
+                        if (l <= Mc[q]) {   // (the coefficient is only there for l <= Mc: a real test)
                             const float s = __fadd_rn(zm[q], zp[q]);
                             const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
                             const float u = __fadd_rn(t, xr[RP + q + l]);
