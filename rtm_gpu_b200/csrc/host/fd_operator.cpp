@@ -5,7 +5,7 @@
 // Replaces the reference's LSMOrCon_rec_2D.cpp (funMandC :22-73, CAL2DFDCOE_LSM
 // :236-287, fgaus/fgausf :139-233, Gauss :74-137, callenfd2d_ls :293-346,
 // calfdlen_ls :347-524, order :526-551).  The search (bisection over velocity bins,
-// threaded), the quadrature (quad2d: a rewrite of the fgaus state machine) and the
+// threaded), the quadrature (ls_coefficients: the fgaus state machine as plain loops over cached basis values) and the
 // table packing are written from the algorithm; solve_scaled_pivot is a
 // TRANSLITERATION of the reference's Gauss routine (same pivoting decisions, same
 // operation order -- any other elimination order changes the last bits of the
@@ -54,44 +54,6 @@ inline double basis(int i, double theta_c, double theta_s, double beta, double i
            (inv_r2 * one_minus_car);
 }
 
-// Composite 2-D Gauss-Legendre quadrature over theta in [0,2pi] (outer) and
-// beta in [0,bmax] (inner), 4 panels x 5 nodes per axis.  The accumulation order
-// (inner sum first, panel centres advanced by repeated addition of the panel width,
-// inner half-width folded in when the inner integral is added to the outer sum,
-// outer half-width applied last) is that of fgaus :139-202.
-//   pair == true  : integrand f_i * f_j   (normal matrix entry)
-//   pair == false : integrand f_i         (right-hand side)
-double quad2d(int i, int j, double bmax, double r, bool pair, double hzx)
-{
-    const double hzx2  = hzx * hzx;
-    const double inv_r2 = std::pow(r, -2);
-    const double ha = 0.5 * (2 * kPi - 0.0) / kPanels;  // outer half panel width
-    const double hb = 0.5 * (bmax - 0.0) / kPanels;     // inner half panel width
-    double outer = 0.0;
-    double ca = ha + 0.0;  // centre of the current outer panel
-    for (int pa = 0; pa < kPanels; ++pa) {
-        for (int ka = 0; ka < 5; ++ka) {
-            const double theta = ha * kNode[ka] + ca;
-            const double tc = std::cos(theta), ts = std::sin(theta);
-            double inner = 0.0;
-            double cb = hb + 0.0;
-            for (int pb = 0; pb < kPanels; ++pb) {
-                for (int kb = 0; kb < 5; ++kb) {
-                    const double beta = hb * kNode[kb] + cb;
-                    const double omc  = 1 - std::cos(r * beta);
-                    double f = basis(i, tc, ts, beta, inv_r2, omc, hzx, hzx2);
-                    if (pair) f = f * basis(j, tc, ts, beta, inv_r2, omc, hzx, hzx2);
-                    inner = f * kWeight[kb] + inner;
-                }
-                cb = cb + hb * 2.0;
-            }
-            outer = inner * hb * kWeight[ka] + outer;
-        }
-        ca = ca + ha * 2.0;
-    }
-    return outer * ha;
-}
-
 // Dense solve A x = b: rows scaled by their (signed) largest-magnitude entry, then
 // Gaussian elimination with partial pivoting, then back substitution.  Transliterated for
 // bit-identity from Gauss (LSMOrCon_rec_2D.cpp:74-137): statement order and pivot tests are the
@@ -133,13 +95,62 @@ bool solve_scaled_pivot(std::vector<std::vector<double>>& A, std::vector<double>
 
 }  // namespace
 
+// One least-squares system (CAL2DFDCOE_LSM :236-287).  Every matrix entry and right-hand side is a composite 2-D
+// Gauss-Legendre integral over theta in [0, 2 pi] (outer) and beta in [0, bmax] (inner), 4 panels x 5 nodes per axis, of
+//   f_i * f_j  (normal matrix entry)   or   f_i  (right-hand side).
+// The accumulation order -- inner sum first, panel centres advanced by repeated addition of the panel width, inner
+// half-width folded in when the inner integral is added to the outer sum, outer half-width applied last -- is that of
+// fgaus :139-202.  The reference evaluates the basis anew for every (i, j) at the same 400 nodes: M (M + 3) / 2 integrals
+// x 400 nodes x up to 2 basis values.  The values depend on (node, i) only, so they are computed once (M x 400) and the
+// sums formed from them in the same order: same operands, same operation order, same bits
+// (tests/test_host.py::test_ls_operator_golden), ~15x less libm work at M = 10.
 void ls_coefficients(double* c, double r, double bmax, int M, double hzx)
 {
+    constexpr int NA = kPanels * 5, NB = kPanels * 5;   // nodes per axis
+    const double hzx2   = hzx * hzx;
+    const double inv_r2 = std::pow(r, -2);
+    const double ha = 0.5 * (2 * kPi - 0.0) / kPanels;
+    const double hb = 0.5 * (bmax - 0.0) / kPanels;
+    std::vector<double> F((size_t)NA * NB * M);          // [node a][node b][i-1]
+    {
+        double ca = ha + 0.0;
+        for (int pa = 0, na = 0; pa < kPanels; ++pa) {
+            for (int ka = 0; ka < 5; ++ka, ++na) {
+                const double theta = ha * kNode[ka] + ca;
+                const double tc = std::cos(theta), ts = std::sin(theta);
+                double cb = hb + 0.0;
+                for (int pb = 0, nb = 0; pb < kPanels; ++pb) {
+                    for (int kb = 0; kb < 5; ++kb, ++nb) {
+                        const double beta = hb * kNode[kb] + cb;
+                        const double omc  = 1 - std::cos(r * beta);
+                        double* f = &F[((size_t)na * NB + nb) * M];
+                        for (int i = 1; i <= M; ++i) f[i - 1] = basis(i, tc, ts, beta, inv_r2, omc, hzx, hzx2);
+                    }
+                    cb = cb + hb * 2.0;
+                }
+            }
+            ca = ca + ha * 2.0;
+        }
+    }
+    auto integral = [&](int i, int j, bool pair) {
+        double outer = 0.0;
+        for (int na = 0; na < NA; ++na) {
+            double inner = 0.0;
+            for (int nb = 0; nb < NB; ++nb) {
+                const double* fv = &F[((size_t)na * NB + nb) * M];
+                double f = fv[i - 1];
+                if (pair) f = f * fv[j - 1];
+                inner = f * kWeight[nb % 5] + inner;
+            }
+            outer = inner * hb * kWeight[na % 5] + outer;
+        }
+        return outer * ha;
+    };
     std::vector<std::vector<double>> A(M, std::vector<double>(M));
     std::vector<double> rhs(M), x(M);
     for (int i = 0; i < M; ++i) {
-        for (int j = i; j < M; ++j) A[i][j] = quad2d(i + 1, j + 1, bmax, r, true, hzx);
-        rhs[i] = quad2d(i + 1, 0, bmax, r, false, hzx);
+        for (int j = i; j < M; ++j) A[i][j] = integral(i + 1, j + 1, true);
+        rhs[i] = integral(i + 1, 0, false);
     }
     for (int i = 0; i < M; ++i)
         for (int j = 0; j < i; ++j) A[i][j] = A[j][i];
