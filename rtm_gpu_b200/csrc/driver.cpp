@@ -67,6 +67,39 @@ void run_worker(const Job& job, Worker& w)
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     const auto tc0 = now();
+    // Host buffers of the pipeline (declared here: the first pair of them is page-locked by a helper thread while this
+    // thread creates the context -- locking 5 GB takes about as long as allocating the device arrays).
+    const size_t ncell = (size_t)c.mod_NX * c.mod_NZ, ntr = (size_t)c.n * c.NT1;
+    struct Buf {
+        float *seis = nullptr, *up = nullptr, *down = nullptr;
+        bool pinned = false;
+        std::vector<float> stable;
+        std::vector<int> r_u, r_x;
+    } buf[2];
+    const int Bmax = p.max_batch;   // (the batch may shrink below: the buffers are then larger than needed)
+    auto alloc_buf = [&](Buf& b) -> bool {
+        b.stable.assign(Bmax, 0.0f); b.r_u.assign(Bmax, 0); b.r_x.assign(Bmax, 0);
+        b.pinned = rtm_host_alloc_pinned((void**)&b.seis, (size_t)Bmax * ntr * 4) == RTM_OK &&
+                   rtm_host_alloc_pinned((void**)&b.up, (size_t)Bmax * ncell * 4) == RTM_OK &&
+                   rtm_host_alloc_pinned((void**)&b.down, (size_t)Bmax * ncell * 4) == RTM_OK;
+        if (!b.pinned) {   // pageable fallback (slower copies, same results)
+            rtm_host_free_pinned(b.seis); rtm_host_free_pinned(b.up); rtm_host_free_pinned(b.down);
+            b.seis = (float*)std::malloc((size_t)Bmax * ntr * 4);
+            b.up = (float*)std::malloc((size_t)Bmax * ncell * 4);
+            b.down = (float*)std::malloc((size_t)Bmax * ncell * 4);
+            if (!b.seis || !b.up || !b.down) return false;
+        }
+        return true;
+    };
+    auto release = [&]() {
+        for (auto& b : buf) {
+            if (b.pinned) { rtm_host_free_pinned(b.seis); rtm_host_free_pinned(b.up); rtm_host_free_pinned(b.down); }
+            else { std::free(b.seis); std::free(b.up); std::free(b.down); }
+            b.seis = b.up = b.down = nullptr;
+        }
+    };
+    bool buf0_ok = false;
+    std::thread pin0([&] { buf0_ok = alloc_buf(buf[0]); });
     for (;;) {   // the estimate is made for GPU 0: another GPU may have less free memory
         size_t fixed = 0, per_shot = 0, free_b = 0;
         if (p.max_batch > 1 && rtm_memory_estimate(&p, c.NT1, &fixed, &per_shot) == RTM_OK &&
@@ -75,45 +108,24 @@ void run_worker(const Job& job, Worker& w)
             continue;
         }
         if (rtm_create(w.device, &p, &w.ctx) == RTM_OK) break;
-        if (p.max_batch == 1) return fail(RTM_ERR_CUDA, rtm_last_error());
+        if (p.max_batch == 1) { pin0.join(); release(); return fail(RTM_ERR_CUDA, rtm_last_error()); }
         p.max_batch = std::max(1, p.max_batch / 2);
     }
-    if (rtm_set_model(w.ctx, job.v.data(), job.bins.vmin, job.bins.vmax, c.dv)) return fail(RTM_ERR_CUDA, rtm_last_error());
-    if (rtm_set_operator(w.ctx, c.iLSTE == 0 ? job.Index.data() : nullptr, job.bins.nvel, job.c.data(), (int)job.c.size()))
+    if (rtm_set_model(w.ctx, job.v.data(), job.bins.vmin, job.bins.vmax, c.dv)) { pin0.join(); release(); return fail(RTM_ERR_CUDA, rtm_last_error()); }
+    if (rtm_set_operator(w.ctx, c.iLSTE == 0 ? job.Index.data() : nullptr, job.bins.nvel, job.c.data(), (int)job.c.size())) {
+        pin0.join(); release();
         return fail(RTM_ERR_ARG, rtm_last_error());
+    }
+    pin0.join();
+    if (!buf0_ok) { release(); return fail(RTM_ERR_ARG, "out of host memory for the trace / image buffers"); }
 
     w.t_create = secs(tc0, now());
     // Three-stage pipeline per GPU: a reader thread fills batch i+1's traces (files -> pinned host memory) and a
     // writer thread drains batch i-1's images (RVSP_RTM_up/down_<m>.dat) while this thread migrates batch i.
     // Two buffers per direction; stage s of batch i may start when the buffer's previous user (batch i-2) has left it.
-    const size_t ncell = (size_t)c.mod_NX * c.mod_NZ, ntr = (size_t)c.n * c.NT1;
+    // The second pair is allocated by the reader thread before it fills batch 1 (while batch 0 is migrating), and not at
+    // all for a one-batch job.
     const int B = p.max_batch, nb = (w.count + B - 1) / B;
-    struct Buf {
-        float *seis = nullptr, *up = nullptr, *down = nullptr;
-        bool pinned = false;
-        std::vector<float> stable;
-        std::vector<int> r_u, r_x;
-    } buf[2];
-    auto release = [&]() {
-        for (auto& b : buf) {
-            if (b.pinned) { rtm_host_free_pinned(b.seis); rtm_host_free_pinned(b.up); rtm_host_free_pinned(b.down); }
-            else { std::free(b.seis); std::free(b.up); std::free(b.down); }
-            b.seis = b.up = b.down = nullptr;
-        }
-    };
-    for (auto& b : buf) {
-        b.stable.assign(B, 0.0f); b.r_u.assign(B, 0); b.r_x.assign(B, 0);
-        b.pinned = rtm_host_alloc_pinned((void**)&b.seis, (size_t)B * ntr * 4) == RTM_OK &&
-                   rtm_host_alloc_pinned((void**)&b.up, (size_t)B * ncell * 4) == RTM_OK &&
-                   rtm_host_alloc_pinned((void**)&b.down, (size_t)B * ncell * 4) == RTM_OK;
-        if (!b.pinned) {   // pageable fallback (slower copies, same results)
-            rtm_host_free_pinned(b.seis); rtm_host_free_pinned(b.up); rtm_host_free_pinned(b.down);
-            b.seis = (float*)std::malloc((size_t)B * ntr * 4);
-            b.up = (float*)std::malloc((size_t)B * ncell * 4);
-            b.down = (float*)std::malloc((size_t)B * ncell * 4);
-            if (!b.seis || !b.up || !b.down) { release(); return fail(RTM_ERR_ARG, "out of host memory for the trace / image buffers"); }
-        }
-    }
     std::mutex mu;
     std::condition_variable cv;
     int read_done = 0, mig_done = 0, write_done = 0;   // batches that have left each stage
@@ -132,6 +144,7 @@ void run_worker(const Job& job, Worker& w)
                 if (abort_all) return;
             }
             Buf& b = buf[i & 1];
+            if (i == 1 && !alloc_buf(b)) return stop("out of host memory for the trace / image buffers");
             const int b0 = i * B, ns = std::min(B, w.count - b0);
             const auto t0 = now();
             for (int sh = 0; sh < ns; ++sh) {

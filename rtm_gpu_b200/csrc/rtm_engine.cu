@@ -370,6 +370,7 @@ struct rtm_ctx {
     int*   d_Index = nullptr;
     float* d_ls_rows = nullptr;             // adaptive operator no longer than 4: padded coefficient rows [nvel][8] + lengths (streaming kernels)
     int*   d_ls_len = nullptr;
+    bool   ring2_bwd_all = false;           // RTM_RING2_BWD=2
     bool   ring_par = true;                 // stream mode: ring launches of the pair loop on the ring stream, next to the ib / thin launches
     bool   fuse2_on = false;                // pairs of steps for this model + operator (prepare_classes)
     bool   ring_frame_only = false;         // adaptive operator: ring_kernel only for the frame steps of the pair loop
@@ -587,7 +588,7 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     if (const char* e = std::getenv("RTM_STREAM2")) c->stream2 = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_RING2")) c->ring2 = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_RING2_FWD")) c->ring2_fwd = std::atoi(e) != 0;
-    if (const char* e = std::getenv("RTM_RING2_BWD")) c->ring2_bwd = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RTM_RING2_BWD")) { c->ring2_bwd = std::atoi(e) != 0; c->ring2_bwd_all = std::atoi(e) == 2; }
     if (const char* e = std::getenv("RTM_FUSE2_FWD")) c->fuse2_fwd = std::atoi(e) != 0 ? 1 : 0;
     if (const char* e = std::getenv("RTM_STREAM1_FWD")) c->stream1_fwd = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_SEG_TILES")) c->seg_tiles = std::max(1, std::atoi(e));
@@ -1327,7 +1328,9 @@ static int dispatch_bwd(rtm_ctx* c, int ns, int s1, int r1, int s0, int r0, cons
         r.P2 = a.R2; r.SX = a.S2; r.src = a.src; r.inject = 0; r.k = a.k; r.st = a.st; r.seis = a.seis; r.sum_double = 0;
         return launch_ring<true>(c, serial ? serial : c->stream, ns, r1, r0, r);
     }
-    if (!frame && !serial && c->ring_ready && c->ring2_bwd && !c->ring_frame_only && !c->store_mode) {
+    // (measured on 4096^2, one shot per launch, profiles/r2_c23_*: radius 12 +2.4 %, radius 8 -11 % -- there the ring launch ends up
+    //  behind the interior launch instead of next to it; RTM_RING2_BWD=2 forces it for every radius)
+    if (!frame && !serial && c->ring_ready && c->ring2_bwd && (c->RP != 8 || c->ring2_bwd_all) && !c->ring_frame_only && !c->store_mode) {
         // a single step of all tiles: the ring by its own kernel on a side stream, the interior tiles without ring CTAs
         RingArgs r{};
         r.P2 = a.R2; r.SX = a.S2; r.src = a.src; r.inject = 0; r.k = a.k; r.st = a.st; r.seis = a.seis; r.sum_double = 0;

@@ -489,7 +489,11 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
 // cells of a float4 group are looked up once (ls_cells) and shared by every field evaluated at those cells; the
 // arithmetic per cell is stencil_row<RP, true>'s, term by term (terms beyond a cell's own length are skipped, not
 // multiplied by the zero padding).
-struct LsCells { int off[4]; int Mc[4]; int Mx; };   // Mx: longest operator among the cells of the WARP (uniform)
+#ifndef RTM_LS4_SAMEBIN
+#define RTM_LS4_SAMEBIN 0
+#endif
+struct LsCells { int off[4]; int Mc[4]; int Mx; bool uni; };   // Mx: longest operator among the cells of the WARP (uniform);
+                                                               // uni: every lane's four cells share one bin (uniform)
 // (called by all 32 lanes of a warp)
 __device__ __forceinline__ LsCells ls_cells(const Geo& G, uint2 bins4)
 {
@@ -504,6 +508,7 @@ __device__ __forceinline__ LsCells ls_cells(const Geo& G, uint2 bins4)
         L.Mx     = max(L.Mx, L.Mc[q]);
     }
     L.Mx = __reduce_max_sync(0xffffffffu, L.Mx);   // uniform loop bounds: no divergence handling around the terms
+    L.uni = RTM_LS4_SAMEBIN && __all_sync(0xffffffffu, (b4[0] == b4[1]) & (b4[1] == b4[2]) & (b4[2] == b4[3]));
     return L;
 }
 template <int SPT>
@@ -516,12 +521,40 @@ __device__ __forceinline__ void stencil_row_ls4(const Geo& G, const float* sc, c
         const float4 t4 = *reinterpret_cast<const float4*>(sc - RP + 4 * g);
         xr[4 * g + 0] = t4.x; xr[4 * g + 1] = t4.y; xr[4 * g + 2] = t4.z; xr[4 * g + 3] = t4.w;
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) p1[q] = xr[RP + q];
+    if (RTM_LS4_SAMEBIN && L.uni) {   // one operator per lane: one row, one length test per term
+        const float* row = G.ls_rows + L.off[0];
+        float c[4];
+        unpack(__ldg(reinterpret_cast<const float4*>(row)), c);
+        const int Ml = L.Mc[0];
+        {
+            const float c0[4] = {c[0], c[0], c[0], c[0]};
+            w1_first_ls4(G, c0, p1, w1);
+        }
+        auto term1 = [&](int l, float cl) {
+            float zm[4], zp[4];
+            unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
+            unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
+            if (l <= Ml) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float s = __fadd_rn(zm[q], zp[q]);
+                    const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
+                    const float u = __fadd_rn(t, xr[RP + q + l]);
+                    w1[q]         = __fmaf_rn(cl, u, w1[q]);
+                }
+            }
+        };
+#pragma unroll
+        for (int l = 1; l <= 3; ++l)
+            if (l <= L.Mx) term1(l, c[l]);
+        if (L.Mx >= 4) term1(4, __ldg(row + 4));
+        return;
+    }
     float cg[4][4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        p1[q] = xr[RP + q];
-        unpack(__ldg(reinterpret_cast<const float4*>(G.ls_rows + L.off[q])), cg[q]);
-    }
+    for (int q = 0; q < 4; ++q) unpack(__ldg(reinterpret_cast<const float4*>(G.ls_rows + L.off[q])), cg[q]);
     {
         const float c0[4] = {cg[0][0], cg[1][0], cg[2][0], cg[3][0]};
         w1_first_ls4(G, c0, p1, w1);
