@@ -337,7 +337,8 @@ struct rtm_ctx {
     // z-streaming form of the two-step kernel (Taylor operator, radius <= 4): RTM_STREAM2=0 keeps the tile form;
     // RTM_SEG_TILES = longest segment in 16-row tiles
     bool   stream2 = true;
-    int    seg_tiles = 8;
+    int    seg_tiles = 12;                  // segments of <= 24 blocks (2301 x 751: 4 pieces per column; measured 8 -> 12: backward -0.9 %, profiles/r2_c27/28_*)
+    bool   lookahead_f_auto = true;         // forward look-ahead distance by batch size unless RTM_LOOKAHEAD_F is set
     bool   stream1_fwd = false;             // single-step forward pass by stream1_fwd_kernel (RTM_STREAM1_FWD=1).  Measured slower than the
                                             // tile kernel (156 vs 143 us per step: 70 % issue-bound, one row of one field per warp and block
                                             // does not amortise the block overhead), so off by default
@@ -594,7 +595,7 @@ extern "C" int rtm_create(int device, const rtm_params* p, rtm_ctx** out)
     if (const char* e = std::getenv("RTM_SEG_TILES")) c->seg_tiles = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RTM_RING_INTERLEAVE")) c->ring_interleave = std::atoi(e) != 0;
     if (const char* e = std::getenv("RTM_RING_SPREAD")) c->ring_spread = std::atoi(e);
-    if (const char* e = std::getenv("RTM_LOOKAHEAD_F")) c->lookahead_f = std::atoi(e);
+    if (const char* e = std::getenv("RTM_LOOKAHEAD_F")) { c->lookahead_f = std::atoi(e); c->lookahead_f_auto = false; }
     if (const char* e = std::getenv("RTM_LOOKAHEAD_B2")) c->lookahead_b2 = std::atoi(e);
     if (const char* e = std::getenv("RTM_LOOKAHEAD_MORE")) c->lookahead_more = std::atoi(e);
     if (const char* e = std::getenv("RTM_LOOKAHEAD_B")) c->lookahead_b = std::atoi(e);
@@ -1052,7 +1053,10 @@ template <int RP, bool LS> static int launch_fwd(rtm_ctx* c, rtm_ctx::TileClass&
         CK(cudaFuncSetAttribute(fwd_step_kernel<RP, LS, RTM_NR_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k.smem_f = smem;
     }
-    a.tiles = frame ? nullptr : k.d_tiles_f; a.ntiles = frame ? 0 : k.n_f; a.fd_ntiles = make_fastdiv(a.ntiles); a.lookahead = c->lookahead_f;   // frame (stream mode): ring tiles only
+    a.tiles = frame ? nullptr : k.d_tiles_f; a.ntiles = frame ? 0 : k.n_f; a.fd_ntiles = make_fastdiv(a.ntiles);   // frame (stream mode): ring tiles only
+    // L2 look-ahead distance: 148 CTAs tuned in round 1 at 8 shots per launch; with 64 shots per launch 296-444 is the flat
+    // optimum (forward step 273 -> 252 us), with one shot per launch on the large grids 148 stays ahead by ~1 % (profiles/r2_c28_*)
+    a.lookahead = c->lookahead_f_auto ? (ns >= 48 ? 296 : 148) : c->lookahead_f;
     dim3 grid((unsigned)((nring + a.ntiles) * ns));
     if (grid.x == 0 || c->dry) return RTM_OK;
     a.ring_period = ring_period(c, nring * ns, (int)grid.x); a.fd_period = make_fastdiv(a.ring_period);
@@ -1411,7 +1415,7 @@ static int run_forward(rtm_ctx* c, int ns, const int* r_u, const int* r_x, bool 
     // forward pass in pairs (inner segments two slots per pass, ring + frame tiles singly): 4 rotating buffers
     bool pairs = false;
     if (!use_store && nsnap == 0 && c->fuse2_fwd != 0 && G.iLSTE != 0 && c->classes.size() == 1 && c->classes[0].stream_mode)
-        pairs = c->fuse2_fwd == 1 || c->fuse2_forced || c->classes[0].ii_blocks / 2 * ns >= rtm_ctx::kFuse2MinCtas;
+        pairs = c->fuse2_fwd == 1 || c->fuse2_forced || (long)(c->classes[0].stream_cells / 4096.0) * ns >= rtm_ctx::kFuse2MinCtas;
     const int NB = pairs ? 4 : 3;
     auto slot = [&](int k) -> float* { return use_store ? c->store + (size_t)k * slab : c->field[k % NB]; };
     if (use_store) {
@@ -1698,7 +1702,7 @@ static int migrate_batch(rtm_ctx* c, int ns, const int* r_u, const int* r_x, flo
     bool pairs = c->fuse2_on && !store;
     if (pairs) {
         long nii = 0, nb2 = 0;
-        for (auto& kc : c->classes) { nii += kc.stream_mode ? kc.ii_blocks / 2 : kc.n_ii; nb2 += kc.stream_mode ? kc.n_segs_ii + kc.n_segs_ib : kc.n_b2; }
+        for (auto& kc : c->classes) { nii += kc.stream_mode ? (long)(kc.stream_cells / 4096.0) /* streamed cells in tile pairs of 128 x 32: independent of the segment length */ : kc.n_ii; nb2 += kc.stream_mode ? kc.n_segs_ii + kc.n_segs_ib : kc.n_b2; }
         pairs = nb2 > 0 && (c->fuse2_forced || nii * ns >= rtm_ctx::kFuse2MinCtas);
     }
     auto loop = [&](int kfirst) -> int {  // slots kfirst .. 0
