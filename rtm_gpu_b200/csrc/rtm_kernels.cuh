@@ -334,10 +334,6 @@ __device__ __forceinline__ LsTable ls_stage_slice(const Geo& G, int2 tb, float* 
 #ifndef RTM_LS_UNIFORM
 #define RTM_LS_UNIFORM 1
 #endif
-// RTM_LS_SAMEBIN=1: the same classes, warps whose lanes each hold four cells of ONE velocity bin: one operator per lane.
-#ifndef RTM_LS_SAMEBIN
-#define RTM_LS_SAMEBIN 0
-#endif
 template <int RP, bool LS, int SPT = kTX + 2 * RP>
 __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M, const LsTable& T,
                                             uint2 bins4, float (&w1)[4], float (&p1)[4], int spr = 0)
@@ -390,38 +386,6 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
                                 const float u = __fadd_rn(t, xr[RP + q + l]);
                                 w1[q]         = __fmaf_rn(cg[q][j], u, w1[q]);
                             }
-                        }
-                    }
-                }
-            }
-        } else if (RTM_LS_SAMEBIN && RP >= 8 &&
-                   __all_sync(__activemask(), (b4[0] == b4[1]) & (b4[1] == b4[2]) & (b4[2] == b4[3]))) {
-            // every lane's four cells share one velocity bin (velocity varies slowly along x): one operator per lane --
-            // one coefficient load and one length test per term instead of four.  Same operations per cell.
-            const int b   = min(max(b4[0], T.bmin), T.bmax);
-            const int top = T.ip[b];
-            const int Ml  = T.ip[b + 1] - top - 1;
-            const float* cl = T.cp + top;
-            Mx = __reduce_max_sync(__activemask(), Ml);
-            {
-                const float c0 = cl[0];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) w1[q] = w1_first_ls(G, c0, p1[q]);
-            }
-#pragma unroll
-            for (int l = 1; l <= RP; ++l) {
-                if (l <= Mx) {
-                    float zm[4], zp[4];
-                    unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
-                    unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
-                    if (l <= Ml) {
-                        const float c = cl[l];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float s = __fadd_rn(zm[q], zp[q]);
-                            const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
-                            const float u = __fadd_rn(t, xr[RP + q + l]);
-                            w1[q]         = __fmaf_rn(c, u, w1[q]);
                         }
                     }
                 }
@@ -489,11 +453,7 @@ __device__ __forceinline__ void stencil_row(const Geo& G, const float* sc, int M
 // cells of a float4 group are looked up once (ls_cells) and shared by every field evaluated at those cells; the
 // arithmetic per cell is stencil_row<RP, true>'s, term by term (terms beyond a cell's own length are skipped, not
 // multiplied by the zero padding).
-#ifndef RTM_LS4_SAMEBIN
-#define RTM_LS4_SAMEBIN 0
-#endif
-struct LsCells { int off[4]; int Mc[4]; int Mx; bool uni; };   // Mx: longest operator among the cells of the WARP (uniform);
-                                                               // uni: every lane's four cells share one bin (uniform)
+struct LsCells { int off[4]; int Mc[4]; int Mx; };   // Mx: longest operator among the cells of the WARP (uniform)
 // (called by all 32 lanes of a warp)
 __device__ __forceinline__ LsCells ls_cells(const Geo& G, uint2 bins4)
 {
@@ -508,7 +468,6 @@ __device__ __forceinline__ LsCells ls_cells(const Geo& G, uint2 bins4)
         L.Mx     = max(L.Mx, L.Mc[q]);
     }
     L.Mx = __reduce_max_sync(0xffffffffu, L.Mx);   // uniform loop bounds: no divergence handling around the terms
-    L.uni = RTM_LS4_SAMEBIN && __all_sync(0xffffffffu, (b4[0] == b4[1]) & (b4[1] == b4[2]) & (b4[2] == b4[3]));
     return L;
 }
 template <int SPT>
@@ -523,35 +482,6 @@ __device__ __forceinline__ void stencil_row_ls4(const Geo& G, const float* sc, c
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) p1[q] = xr[RP + q];
-    if (RTM_LS4_SAMEBIN && L.uni) {   // one operator per lane: one row, one length test per term
-        const float* row = G.ls_rows + L.off[0];
-        float c[4];
-        unpack(__ldg(reinterpret_cast<const float4*>(row)), c);
-        const int Ml = L.Mc[0];
-        {
-            const float c0[4] = {c[0], c[0], c[0], c[0]};
-            w1_first_ls4(G, c0, p1, w1);
-        }
-        auto term1 = [&](int l, float cl) {
-            float zm[4], zp[4];
-            unpack(*reinterpret_cast<const float4*>(sc - l * SP), zm);
-            unpack(*reinterpret_cast<const float4*>(sc + l * SP), zp);
-            if (l <= Ml) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float s = __fadd_rn(zm[q], zp[q]);
-                    const float t = __fmaf_rn(s, G.hzx2_1, xr[RP + q - l]);
-                    const float u = __fadd_rn(t, xr[RP + q + l]);
-                    w1[q]         = __fmaf_rn(cl, u, w1[q]);
-                }
-            }
-        };
-#pragma unroll
-        for (int l = 1; l <= 3; ++l)
-            if (l <= L.Mx) term1(l, c[l]);
-        if (L.Mx >= 4) term1(4, __ldg(row + 4));
-        return;
-    }
     float cg[4][4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) unpack(__ldg(reinterpret_cast<const float4*>(G.ls_rows + L.off[q])), cg[q]);
