@@ -26,8 +26,10 @@
 // The same kernel with BWD = false advances the FORWARD pass two steps per pass (one field, no
 // accumulators): slot k from k-1/k-2, then slot k+1 from k/k-1, source term and gather recording in
 // both phases.  Reference kernels restated: Add_Con :82-114 (forward); BKAdd_EFF_Con :287-320,
-// BKAdd_Con :381-418, Rel_Compen / Rel_NonCompen :489-517 (backward).  Fixed-length (Taylor)
-// operator, radius <= 4; other operators keep the tile kernels of rtm_kernels.cuh.
+// BKAdd_Con :381-418, Rel_Compen / Rel_NonCompen :489-517 (backward; BKAdd_EFF :246-283 and BKAdd :339-380
+// with the adaptive operator).  Operators up to radius 4: the fixed-length (Taylor) one, and -- LS = true, backward
+// only -- the adaptive one when no velocity bin of the model needs more (per-cell coefficient rows from the padded
+// global table, stencil_row_ls4); longer operators keep the tile kernels of rtm_kernels.cuh.
 #pragma once
 #include "rtm_kernels.cuh"
 
