@@ -810,32 +810,9 @@ static int prepare_classes(rtm_ctx* c)
             //               "ib" = the columns / blocks next to the thin frame (the inner-inner segments' halo
             //               never reaches a cell stepped singly), "ii" = everything inside them
             using T = Strm<4>;
-            const int RPc = k.RP, C0 = G.N2 + RPc, R0 = G.N2 + RPc, xe = G.NX - G.N2 - RPc, ze = G.NZ - G.N2 - RPc;
-            const int ncol = (xe - C0 + kTX - 1) / kTX, nblk = (ze - R0 + T::BR - 1) / T::BR;
-            const int nright = (xe - C0 - (ncol - 1) * kTX >= 2 * RPc) ? 1 : 2;   // right "ib" columns: at least 2*RP cells
-            if (ncol >= 1 + nright && nblk >= 2) {
-                const int seg_blocks = std::max(2, c->seg_tiles * TZb / T::BR);
-                std::vector<int4> ii, ib;
-                // a column's blocks in pieces of (nearly) equal length <= seg_blocks.  "ib": the whole first / last column(s)
-                // and, of every other column, its first and last piece -- long pieces, so the ib launch streams as
-                // efficiently as the ii launch; their outer 8 rows / 2*RP columns are what the ii segments' halo may reach
-                for (int col = 0; col < ncol; ++col) {
-                    const bool edge = col == 0 || col >= ncol - nright;
-                    const int pieces = (nblk + seg_blocks - 1) / seg_blocks;
-                    std::vector<int2> pc;   // (first block, blocks)
-                    for (int p = 0, b = 0; p < pieces; ++p) {
-                        const int len = nblk / pieces + (p < nblk % pieces ? 1 : 0);
-                        pc.push_back(make_int2(b, len));
-                        b += len;
-                    }
-                    int nlast = 1;          // trailing pieces that go to ib: at least 8 valid rows
-                    while (nlast < (int)pc.size() && ze - (R0 + pc[pc.size() - nlast].x * T::BR) < T::BR) ++nlast;
-                    for (int p = 0; p < (int)pc.size(); ++p) {
-                        const bool border = edge || p == 0 || p >= (int)pc.size() - nlast;
-                        const int edges = (col == 0 ? 1 : 0) | (col == ncol - 1 ? 2 : 0) | (p == 0 ? 4 : 0) | (p == (int)pc.size() - 1 ? 8 : 0);
-                        (border ? ib : ii).push_back(make_int4(C0 + col * kTX, R0 + pc[p].x * T::BR, pc[p].y, edges));
-                    }
-                }
+            const int seg_blocks = std::max(2, c->seg_tiles * TZb / T::BR);
+            const StreamRegions sr = make_stream_regions(G, k.RP, seg_blocks);   // rtm_stream.cuh (tests/test_launch_geometry.py)
+            if (sr.ok) {
                 auto up4 = [&](const std::vector<int4>& v, int4** d, int* n) -> int {
                     *n = (int)v.size();
                     if (v.empty()) return RTM_OK;
@@ -843,25 +820,14 @@ static int prepare_classes(rtm_ctx* c)
                     CK(cudaMemcpy(*d, v.data(), sizeof(int4) * v.size(), cudaMemcpyHostToDevice));
                     return RTM_OK;
                 };
-                if (int rc = up4(ii, &k.d_segs_ii, &k.n_segs_ii)) return rc;
-                if (int rc = up4(ib, &k.d_segs_ib, &k.n_segs_ib)) return rc;
+                if (int rc = up4(sr.ii, &k.d_segs_ii, &k.n_segs_ii)) return rc;
+                if (int rc = up4(sr.ib, &k.d_segs_ib, &k.n_segs_ib)) return rc;
                 k.ii_blocks = 0;
-                for (auto& sgm : ii) k.ii_blocks += sgm.z;
-                k.stream_cells = (double)(xe - C0) * (ze - R0);
-                // thin-frame strips
-                std::vector<ThinTile> thin;
-                for (int x0 = G.N2; x0 < G.NX - G.N2; x0 += kTX) {   // top and bottom: RP rows, all interior columns
-                    thin.push_back(ThinTile{x0, G.N2, G.N2, G.NX - G.N2, G.N2 + RPc, 0, 0, 0});
-                    thin.push_back(ThinTile{x0, ze, G.N2, G.NX - G.N2, ze + RPc, 0, 0, 0});
-                }
-                const int xr = xe - ((G.padL + xe) % 4);              // float4-aligned start of the right strip's groups
-                for (int z0 = R0; z0 < ze; z0 += 64) {                // left and right: RP columns, the rows in between
-                    thin.push_back(ThinTile{G.N2, z0, G.N2, C0, std::min(z0 + 64, ze), 1, 0, 0});
-                    thin.push_back(ThinTile{xr, z0, xe, G.NX - G.N2, std::min(z0 + 64, ze), 1, 0, 0});
-                }
-                k.n_thin = (int)thin.size();
-                CK(cudaMalloc(&k.d_thin, sizeof(ThinTile) * thin.size()));
-                CK(cudaMemcpy(k.d_thin, thin.data(), sizeof(ThinTile) * thin.size(), cudaMemcpyHostToDevice));
+                for (auto& sgm : sr.ii) k.ii_blocks += sgm.z;
+                k.stream_cells = sr.stream_cells;
+                k.n_thin = (int)sr.thin.size();
+                CK(cudaMalloc(&k.d_thin, sizeof(ThinTile) * sr.thin.size()));
+                CK(cudaMemcpy(k.d_thin, sr.thin.data(), sizeof(ThinTile) * sr.thin.size(), cudaMemcpyHostToDevice));
                 for (int i = 0; i < rtm_ctx::kFields; ++i) {
                     int rc = encode_tmap(c, &k.tmap_s_cur[i], c->field[i], 0, T::BR, 0, T::W1);
                     if (!rc) rc = encode_tmap(c, &k.tmap_s_prev[i], c->field[i], 0, T::BR, 0, T::WM);

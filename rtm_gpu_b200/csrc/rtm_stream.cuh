@@ -33,6 +33,8 @@
 #pragma once
 #include "rtm_kernels.cuh"
 
+#include <vector>
+
 namespace rtmk {
 
 template <int RP> struct Strm {
@@ -706,6 +708,67 @@ thin_frame_kernel(const __grid_constant__ ThinMaps tm, const __grid_constant__ G
         store4c(a.rel1 + so + cell, r1v, x, tl.xbeg, tl.xend);
         store4c(a.rel2 + so + cell, r2v, x, tl.xbeg, tl.xend);
     }
+}
+
+// ------------------------------------------------------------------------------------
+// Regions of the streaming form (host side; checked on the CPU by tests/test_launch_geometry.py), for the forward and
+// the backward pass alike:
+//   ring        the N2 outermost cells                    ring_kernel / ring tiles of the single-step kernels
+//   thin frame  the RP interior cells next to the ring    thin_frame_kernel, stepped singly
+//   streamed    the rest [C0, xe) x [R0, ze)              stream2_kernel, two slots per pass: 128-wide columns (the last may
+//               be partial) of 8-row blocks (the last may be partial), cut into segments of at most seg_blocks blocks;
+//               "ib" = the columns / pieces next to the thin frame (the inner-inner segments' halo never reaches a cell
+//               stepped singly), "ii" = everything inside them
+// ------------------------------------------------------------------------------------
+struct StreamRegions {
+    bool ok = false;                 // the grid is large enough for the streaming form
+    std::vector<int4> ii, ib;        // segments (x0, z0, blocks, edges), see StrmArgs::segs
+    std::vector<ThinTile> thin;
+    double stream_cells = 0;         // cells per shot advanced two slots per pass
+    int C0 = 0, R0 = 0, xe = 0, ze = 0;
+};
+__host__ inline StreamRegions make_stream_regions(const Geo& G, int RPc, int seg_blocks)
+{
+    using T = Strm<4>;
+    StreamRegions r;
+    const int C0 = G.N2 + RPc, R0 = G.N2 + RPc, xe = G.NX - G.N2 - RPc, ze = G.NZ - G.N2 - RPc;
+    r.C0 = C0; r.R0 = R0; r.xe = xe; r.ze = ze;
+    const int ncol = (xe - C0 + kTX - 1) / kTX, nblk = (ze - R0 + T::BR - 1) / T::BR;
+    const int nright = (xe - C0 - (ncol - 1) * kTX >= 2 * RPc) ? 1 : 2;   // right "ib" columns: at least 2*RP cells
+    if (!(ncol >= 1 + nright && nblk >= 2)) return r;
+    // a column's blocks in pieces of (nearly) equal length <= seg_blocks.  "ib": the whole first / last column(s)
+    // and, of every other column, its first and last piece -- long pieces, so the ib launch streams as
+    // efficiently as the ii launch; their outer 8 rows / 2*RP columns are what the ii segments' halo may reach
+    for (int col = 0; col < ncol; ++col) {
+        const bool edge = col == 0 || col >= ncol - nright;
+        const int pieces = (nblk + seg_blocks - 1) / seg_blocks;
+        std::vector<int2> pc;   // (first block, blocks)
+        for (int p = 0, b = 0; p < pieces; ++p) {
+            const int len = nblk / pieces + (p < nblk % pieces ? 1 : 0);
+            pc.push_back(make_int2(b, len));
+            b += len;
+        }
+        int nlast = 1;          // trailing pieces that go to ib: at least 8 valid rows
+        while (nlast < (int)pc.size() && ze - (R0 + pc[pc.size() - nlast].x * T::BR) < T::BR) ++nlast;
+        for (int p = 0; p < (int)pc.size(); ++p) {
+            const bool border = edge || p == 0 || p >= (int)pc.size() - nlast;
+            const int edges = (col == 0 ? 1 : 0) | (col == ncol - 1 ? 2 : 0) | (p == 0 ? 4 : 0) | (p == (int)pc.size() - 1 ? 8 : 0);
+            (border ? r.ib : r.ii).push_back(make_int4(C0 + col * kTX, R0 + pc[p].x * T::BR, pc[p].y, edges));
+        }
+    }
+    r.stream_cells = (double)(xe - C0) * (ze - R0);
+    // thin-frame strips
+    for (int x0 = G.N2; x0 < G.NX - G.N2; x0 += kTX) {   // top and bottom: RP rows, all interior columns
+        r.thin.push_back(ThinTile{x0, G.N2, G.N2, G.NX - G.N2, G.N2 + RPc, 0, 0, 0});
+        r.thin.push_back(ThinTile{x0, ze, G.N2, G.NX - G.N2, ze + RPc, 0, 0, 0});
+    }
+    const int xr = xe - ((G.padL + xe) % 4);              // float4-aligned start of the right strip's groups
+    for (int z0 = R0; z0 < ze; z0 += 64) {                // left and right: RP columns, the rows in between
+        r.thin.push_back(ThinTile{G.N2, z0, G.N2, C0, z0 + 64 < ze ? z0 + 64 : ze, 1, 0, 0});
+        r.thin.push_back(ThinTile{xr, z0, xe, G.NX - G.N2, z0 + 64 < ze ? z0 + 64 : ze, 1, 0, 0});
+    }
+    r.ok = true;
+    return r;
 }
 
 }  // namespace rtmk

@@ -1,5 +1,6 @@
-"""Host-side check of the launch geometry helpers of rtm_kernels.cuh (compiled for the host with nvcc,
-no GPU needed): the division by multiply-high and the mapping of block indices to ring / interior CTAs."""
+"""Host-side check of the launch geometry helpers of rtm_kernels.cuh / rtm_ring.cuh / rtm_stream.cuh (compiled for the
+host with nvcc, no GPU needed): the division by multiply-high, the mapping of block indices to ring / interior CTAs,
+the tiling of the ring kernel and the regions of the streaming form (segments, thin frame)."""
 import shutil
 import subprocess
 
@@ -130,6 +131,96 @@ def test_ring_kernel_tiling(tmp_path):
     cc = subprocess.run(cmd, capture_output=True, text=True)
     if cc.returncode != 0:
         cc = subprocess.run(cmd, capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr[-2000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
+
+
+STREAM_SRC = r"""
+#include "rtm_stream.cuh"
+#include <cstdio>
+#include <vector>
+using namespace rtmk;
+// Every interior cell belongs to exactly one of: a streamed segment (ii or ib), a thin-frame tile.  Inner-inner
+// segments keep their distance from everything stepped singly; TMA box starts are 16-byte aligned.
+static int check(int mod_NX, int mod_NZ, int N2, int seg_blocks)
+{
+    Geo G{};
+    G.N2 = N2; G.mod_NX = mod_NX; G.mod_NZ = mod_NZ; G.NX = mod_NX + 2 * N2; G.NZ = mod_NZ + 2 * N2;
+    const int RP = 4, BR = Strm<4>::BR;
+    G.padL = (32 - N2 % 32) % 32;   // field_layout() of rtm_engine.cu: the first interior column sits on a 128-byte boundary
+    if (G.padL + N2 < RP) G.padL += 32;
+    const StreamRegions r = make_stream_regions(G, RP, seg_blocks);
+    const int C0 = N2 + RP, R0 = N2 + RP, xe = G.NX - N2 - RP, ze = G.NZ - N2 - RP;
+    if (!r.ok) return (xe - C0 > 2 * kTX && ze - R0 >= 2 * BR) ? 1 : 0;   // must be available on any grid of 3+ columns
+    if (r.C0 != C0 || r.R0 != R0 || r.xe != xe || r.ze != ze) return 2;
+    std::vector<int> own((size_t)G.NZ * G.NX, 0);
+    auto mark = [&](int z, int x, int who) { if (z < 0 || z >= G.NZ || x < 0 || x >= G.NX) return false; int& o = own[(size_t)z * G.NX + x]; if (o) return false; o = who; return true; };
+    double cells = 0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (const int4& s : (pass ? r.ib : r.ii)) {
+            if (s.z < 1 || (s.x - C0) % kTX || (s.y - R0) % BR) return 3;
+            if ((G.padL + s.x - 2 * RP) % 4) return 4;                       // TMA box start (current fields, halo 2 RP)
+            if (s.z > seg_blocks && seg_blocks >= 2) return 5;
+            const int zend = s.y + BR * s.z < ze ? s.y + BR * s.z : ze, xend = s.x + kTX < xe ? s.x + kTX : xe;
+            if (zend <= s.y || xend <= s.x) return 6;                        // no empty segment
+            for (int z = s.y; z < zend; ++z)
+                for (int x = s.x; x < xend; ++x) { if (!mark(z, x, pass ? 2 : 1)) return 7; ++cells; }
+            // edge flags: the segment touches the thin frame on that side
+            const int e = (s.x == C0 ? 1 : 0) | (s.x + kTX >= xe ? 2 : 0) | (s.y == R0 ? 4 : 0) | (s.y + BR * s.z >= ze ? 8 : 0);
+            if (e != s.w) return 8;
+            if (!pass) {   // inner-inner: 8 rows / 2 RP columns inside the streamed region on every side
+                if (s.y - BR < R0 || zend + BR > ze || s.x - 2 * RP < C0 || xend + 2 * RP > xe) return 9;
+            }
+        }
+    if (cells != r.stream_cells) return 10;
+    for (const ThinTile& t : r.thin) {
+        if ((G.padL + t.x0) % 4) return 11;                                  // float4 groups of the tile
+        const int rows = t.kind == 0 ? 4 : 64, cols = t.kind == 0 ? kTX : 8;
+        if (t.zend - t.z0 > rows || t.zend <= t.z0) return 12;
+        for (int z = t.z0; z < t.zend; ++z)
+            for (int x = t.x0; x < t.x0 + cols; ++x)
+                if (x >= t.xbeg && x < t.xend && !mark(z, x, 3)) return 13;
+    }
+    for (int z = 0; z < G.NZ; ++z)
+        for (int x = 0; x < G.NX; ++x) {
+            const bool interior = z >= N2 && z < G.NZ - N2 && x >= N2 && x < G.NX - N2;
+            const bool streamed = z >= R0 && z < ze && x >= C0 && x < xe;
+            const int o = own[(size_t)z * G.NX + x];
+            if (!interior && o) return 14;
+            if (interior && !o) return 15;
+            if (interior && (streamed ? o == 3 : o != 3)) return 16;
+        }
+    return 0;
+}
+int main()
+{
+    const int grids[][3] = {{2301, 751, 10}, {700, 280, 10}, {700, 200, 10}, {4096, 4096, 12}, {20000, 320, 10}, {677, 210, 10},
+                            {401, 97, 5}, {394, 100, 16}, {385, 64, 10}, {300, 50, 10}, {1024, 33, 10}};
+    const int segs[] = {2, 4, 6, 10, 16, 24, 32, 1000};
+    for (auto& g : grids)
+        for (int sb : segs) {
+            const int rc = check(g[0], g[1], g[2], sb);
+            if (rc) { std::printf("grid %d x %d N2 %d seg_blocks %d: check %d\n", g[0], g[1], g[2], sb, rc); return 1; }
+        }
+    std::printf("ok\n");
+    return 0;
+}
+"""
+
+
+def test_stream_regions(tmp_path):
+    """make_stream_regions (rtm_stream.cuh, used by prepare_classes): segments + thin-frame tiles partition the interior."""
+    nvcc = shutil.which("nvcc")
+    if not nvcc:
+        pytest.skip("nvcc not on PATH")
+    src = tmp_path / "streamgeo.cu"
+    src.write_text(STREAM_SRC)
+    exe = tmp_path / "streamgeo"
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", "-I",
+           str(ROOT / "rtm_gpu_b200" / "csrc"), "-I", str(ROOT / "include"), "-o", str(exe), str(src), "-lcudart_static", "-ldl",
+           "-lpthread", "-lrt"]
+    cc = subprocess.run(cmd, capture_output=True, text=True)
     assert cc.returncode == 0, cc.stderr[-2000:]
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
