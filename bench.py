@@ -579,7 +579,9 @@ def main():
     if tf.exists() and w.key == "c2" and not args.nt:
         try:   # ncu dram__bytes of one backward / forward time step, recorded at tj["shots_per_launch"] shots per launch
             tj = json.loads(tf.read_text())
-            key = tj.get("schedule_keys", {}).get("stream" if st["pair_cell_steps_forward"] > 0 else ("pairs" if pairs_b else "single"))
+            # which schedule ran: the streaming form steps ~99 % of the interior in pairs, the tile form ~85 %
+            pair_frac = st["pair_cell_steps_backward"] / (nsteps * B * float(w.mod_NZ * w.mod_NX))
+            key = tj.get("schedule_keys", {}).get("stream" if pair_frac > 0.93 else ("pairs" if pairs_b else "single"))
             rec = tj.get(key) if key else None
             if rec:
                 scale = B / float(rec.get("shots_per_launch", 8))
