@@ -593,7 +593,8 @@ def main():
         except Exception:
             traffic = dram = None
     roofline = {"bound": "hbm",
-                "kernel": ("backward time step = stream2_kernel<BWD> (inner segments, two steps per pass, TMA-fed rings) + bwd_step_kernel (ring + frame tiles)"
+                "kernel": ("backward time step = stream2_kernel<BWD> (streamed segments, two steps per pass, TMA-fed rings) + ring_kernel + "
+                           "thin_frame_kernel (absorbing ring and the cells next to it, stepped singly); tile form: bwd2_step_kernel + bwd_step_kernel"
                            if pairs_b else "bwd_step_kernel (source reconstruction + receiver step + ABC + imaging)"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes_per_launch,
